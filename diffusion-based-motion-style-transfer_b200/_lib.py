@@ -1,0 +1,158 @@
+"""ctypes binding of the mst C-ABI (include/mst.h) and the in-tree build recipe.
+
+The shared library is the product: every device operation of the hot path
+goes through it.  There is no fallback - if the library is missing or a call
+fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG_DIR, "csrc")
+LIB_PATH = os.path.join(_PKG_DIR, "libmst_b200.so")
+SOURCES = ["api.cu", "update.cu", "simt.cu", "tc_gemm.cu", "tc_attn.cu"]
+HEADERS = ["common.cuh", "simt.cuh", "tc.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "mst.h")]
+
+MAX_LAYERS = 32
+PREC_FP32, PREC_BF16 = 0, 1
+SAMPLER_DDPM, SAMPLER_DDIM = 0, 1
+NOISE_NONE, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
+MASK_NONE, MASK_FULL, MASK_FT, MASK_F = 0, 1, 2, 3
+
+# every symbol include/mst.h declares
+EXPORTED = [
+    "mst_version", "mst_last_error", "mst_device_info", "mst_abi_sizes", "mst_engine_create", "mst_engine_destroy",
+    "mst_engine_packed_weight_bytes", "mst_engine_load_weights", "mst_engine_workspace_bytes", "mst_time_embed",
+    "mst_text_embed", "mst_denoiser_forward", "mst_update_step", "mst_q_sample", "mst_cfg_combine",
+    "mst_philox_normal", "mst_test_gemm_bf16", "mst_test_attention_bf16",
+]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("n_feats", "d_model", "n_heads", "d_ff", "n_layers", "clip_dim", "pe_len", "precision")]
+
+
+_LAYER_FIELDS = ("qkv_w", "qkv_b", "o_w", "o_b", "w1", "b1", "w2", "b2", "ln1_g", "ln1_b", "ln2_g", "ln2_b")
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
+
+
+class Weights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("in_w", "in_b", "pe", "t_w1", "t_b1", "t_w2", "t_b2", "txt_w", "txt_b", "out_w", "out_b")] + \
+               [("layers", LayerWeights * MAX_LAYERS)]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("n_frames", C.c_int32), ("cfg", C.c_int32), ("uncond", C.c_int32),
+        ("x", C.c_void_p), ("temb", C.c_void_p), ("temb_row_dev", C.c_void_p), ("temb_row_offset", C.c_int32),
+        ("text_emb", C.c_void_p), ("out_cond", C.c_void_p), ("out_uncond", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class UpdateArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("n_feats", C.c_int32), ("n_frames", C.c_int32),
+        ("sampler", C.c_int32), ("clip_denoised", C.c_int32),
+        ("out_cond", C.c_void_p), ("out_uncond", C.c_void_p), ("cfg_scale", C.c_void_p),
+        ("x_t", C.c_void_p), ("x_prev", C.c_void_p), ("pred_xstart", C.c_void_p),
+        ("mask_kind", C.c_int32), ("mask", C.c_void_p), ("x_inpaint", C.c_void_p), ("mask_noise", C.c_int32),
+        ("t_vec", C.c_void_p), ("t_scalar_dev", C.c_void_p), ("t_imm", C.c_int32), ("advance_t", C.c_int32),
+        ("block_counter", C.c_void_p),
+        ("coef1", C.c_void_p), ("coef2", C.c_void_p), ("sigma", C.c_void_p), ("recip", C.c_void_p),
+        ("recipm1", C.c_void_p),
+        ("noise_kind", C.c_int32), ("noise", C.c_void_p), ("const_noise", C.c_int32),
+        ("philox_seed", C.c_uint64), ("philox_sample_offset", C.c_uint64),
+    ]
+
+
+def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-shared", "-o", out_path] + [os.path.join(_CSRC, s) for s in SOURCES]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(_CSRC, h)) for h in HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libmst_b200.so next to this file."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd))
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _declare(lib):
+    vp, i32, i64, u64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_size_t
+    lib.mst_version.restype = C.c_char_p
+    lib.mst_last_error.restype = C.c_char_p
+    sigs = {
+        "mst_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "mst_abi_sizes": [C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)],
+        "mst_engine_create": [C.POINTER(ModelDesc), C.POINTER(vp)],
+        "mst_engine_destroy": [vp],
+        "mst_engine_packed_weight_bytes": [vp, C.POINTER(sz)],
+        "mst_engine_load_weights": [vp, C.POINTER(Weights), vp, sz, vp],
+        "mst_engine_workspace_bytes": [vp, C.c_int, C.c_int, C.POINTER(sz)],
+        "mst_time_embed": [vp, vp, C.c_int, vp, vp, sz, vp],
+        "mst_text_embed": [vp, vp, C.c_int, vp, vp],
+        "mst_denoiser_forward": [vp, C.POINTER(ForwardArgs), vp],
+        "mst_update_step": [C.POINTER(UpdateArgs), vp],
+        "mst_q_sample": [vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp],
+        "mst_cfg_combine": [vp, vp, vp, vp, i32, i64, vp],
+        "mst_philox_normal": [vp, i32, i64, u64, u64, i32, vp],
+        "mst_test_gemm_bf16": [vp, vp, vp, vp, i32, i32, i32, vp],
+        "mst_test_attention_bf16": [vp, vp, vp, i32, i32, vp, sz, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+
+
+def load():
+    """dlopen libmst_b200.so (building it first when the sources are newer)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                # built artefact missing: compile in-tree (nvcc cross-compiles without a GPU)
+                if os.environ.get("MST_NO_BUILD") == "1" or not os.path.exists(nvcc_command()[0]):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing and cannot be built here; run `python __graft_entry__.py` "
+                        "(there is no CPU fallback)")
+                build(force=True)
+            lib = C.CDLL(LIB_PATH)
+            _declare(lib)
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "mst"):
+    if rc != 0:
+        msg = load().mst_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

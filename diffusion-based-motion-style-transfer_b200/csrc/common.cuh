@@ -1,0 +1,66 @@
+// Shared helpers for the mst (motion-style-transfer sampler) sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/mst.h"
+
+namespace mst {
+
+// thread-local last error, exposed through mst_last_error()
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define MST_CHECK_ARG(cond, msg)                                              \
+  do {                                                                        \
+    if (!(cond)) return ::mst::fail(MST_ERR_INVALID, std::string(__func__) + ": " + (msg)); \
+  } while (0)
+
+#define MST_CUDA_OK(expr)                                                     \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess)                                                    \
+      return ::mst::fail(MST_ERR_CUDA, std::string(__func__) + ": " #expr ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define MST_LAUNCH_OK()                                                       \
+  do {                                                                        \
+    cudaError_t _e = cudaGetLastError();                                      \
+    if (_e != cudaSuccess)                                                    \
+      return ::mst::fail(MST_ERR_CUDA, std::string(__func__) + ": launch: " + cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int sm_count();  // cached multiProcessorCount of the current device
+
+// ---------------------------------------------------------------------------
+// engine (defined in api.cu); kernels get what they need through these structs
+// ---------------------------------------------------------------------------
+struct LayerF32 {
+  const float *qkv_w, *qkv_b, *o_w, *o_b, *w1, *b1, *w2, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+struct LayerBF16 {
+  const __nv_bfloat16 *qkv_w, *o_w, *w1, *w2;  // [N, K] row-major bf16
+};
+
+struct Engine {
+  mst_model_desc desc;
+  bool weights_loaded = false;
+  // fp32 views (always valid once loaded; biases / LN params stay fp32 in both modes)
+  const float *in_w, *in_b, *pe, *t_w1, *t_b1, *t_w2, *t_b2, *txt_w, *txt_b, *out_w, *out_b;
+  LayerF32 lf[MST_MAX_LAYERS];
+  // bf16 packed copies (MST_PREC_BF16)
+  const __nv_bfloat16* in_w_bf = nullptr;   // [d, Fpad]
+  const __nv_bfloat16* out_w_bf = nullptr;  // [Fpad, d]
+  const float* out_b_pad = nullptr;         // [Fpad]
+  LayerBF16 lb[MST_MAX_LAYERS];
+  int f_pad = 0;  // F rounded up to 64
+};
+
+}  // namespace mst

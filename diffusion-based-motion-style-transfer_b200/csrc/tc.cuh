@@ -1,0 +1,50 @@
+// Declarations of the tcgen05 / TMEM / TMA kernels (tc_gemm.cu, tc_attn.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mst {
+
+// Epilogues of the bf16 tensor-core GEMM  D[M,N] = A[M,K] * W[N,K]^T  (+ ...)
+enum TcEpi {
+  TC_EPI_BIAS_BF16 = 0,   // out bf16 [M, ldo]  = acc + bias                     (QKV)
+  TC_EPI_BIAS_GELU_BF16,  // out bf16 [M, ldo]  = gelu(acc + bias)               (FFN1)
+  TC_EPI_BIAS_RES_LN,     // out bf16 [M, N]    = LN(acc + bias + residual)*g+b  (N == 512; out-proj, FFN2)
+  TC_EPI_INPROJ,          // token rows (b, t+1) of every pass = acc + bias + pe[t+1]
+  TC_EPI_OUTPROJ_F32,     // out fp32 [seq][n][s-1] = acc + bias (token 0 dropped, n < n_valid)
+  TC_EPI_BIAS_F32,        // out fp32 [M, ldo]  = acc + bias                     (test hook)
+};
+
+struct TcGemmParams {
+  const __nv_bfloat16* a = nullptr;  // [M, K] row-major, K % 64 == 0, 16B-aligned rows
+  const __nv_bfloat16* w = nullptr;  // [N, K] row-major
+  const float* bias = nullptr;       // [N]
+  void* out = nullptr;
+  int M = 0, N = 0, K = 0;
+  int ldo = 0;
+  int epi = TC_EPI_BIAS_BF16;
+  // LN epilogue
+  const __nv_bfloat16* residual = nullptr;  // [M, N]
+  const float* ln_g = nullptr;
+  const float* ln_b = nullptr;
+  // in/out projection geometry
+  const float* pe = nullptr;
+  int B = 0, T = 0, n_pass = 1, n_valid = 0;
+  float* out2 = nullptr;  // OUTPROJ: rows of sequences >= B go here (uncond pass)
+};
+
+int tc_gemm(const TcGemmParams& p, cudaStream_t s);
+
+// x [B,F,T] fp32 -> A operand of the in-projection: bf16 [B*T, f_pad], zero padded
+int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T, int f_pad, cudaStream_t s);
+
+// fp32 [rows, cols] -> bf16 [rows_pad, cols_pad] zero padded (weight packing)
+int pack_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, int rows_pad, int cols_pad, cudaStream_t s);
+
+struct TcAttnParams {
+  const __nv_bfloat16* qkv = nullptr;  // [n_seqs*S, 3d]  (Q | K | V column blocks)
+  __nv_bfloat16* out = nullptr;        // [n_seqs*S, d]
+  int n_seqs = 0, S = 0, d_model = 0, n_heads = 0;
+};
+int tc_attention(const TcAttnParams& p, cudaStream_t s);
+
+}  // namespace mst

@@ -1,0 +1,655 @@
+"""Host side of the Gaussian diffusion process, B200-native.
+
+Mirrors the public surface of the reference's ``diffusion/gaussian_diffusion.py``
+(class and method names, argument order, return conventions) for the sampling
+hot path, so callers such as ``sample/demo_style_transfer.py:244-258`` and
+``train/finetune_style_diffusion.py:195-211`` keep working unchanged.  The
+work underneath is different:
+
+* schedule tables are built once on the host in float64 exactly as the
+  reference does (``gaussian_diffusion.py:183-219``) and uploaded ONCE per
+  device as fp32 (the reference re-uploads a float64 table five times per
+  step, ``:1615``);
+* every per-step elementwise op (CFG lerp, inpainting blend, clamp, posterior
+  mean, masked noise) is one fused CUDA kernel (``mst_update_step``);
+* a native denoiser (``model.mdm_forstyledataset.MDM`` / ``StyleDiffusion``,
+  optionally inside ``ClassifierFreeSampleModel``) is run through the
+  hand-written sm_100a forward with cond+uncond batched, text/time embeddings
+  hoisted out of the loop, and the step replayed as a CUDA graph.
+
+Nothing here runs on the CPU: tensors must be CUDA tensors.
+"""
+from __future__ import annotations
+
+import enum
+import math
+import os
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch as th
+
+from .. import _lib as L
+from .. import engine as K
+
+
+# ----------------------------------------------------------------------------
+# schedules (reference gaussian_diffusion.py:22-66)
+# ----------------------------------------------------------------------------
+def get_named_beta_schedule(schedule_name, num_diffusion_timesteps, scale_betas=1.):
+    """'linear' (Ho et al., rescaled to the step count) or 'cosine' (Nichol & Dhariwal)."""
+    if schedule_name == "linear":
+        scale = scale_betas * 1000 / num_diffusion_timesteps
+        return np.linspace(scale * 0.0001, scale * 0.02, num_diffusion_timesteps, dtype=np.float64)
+    if schedule_name == "cosine":
+        return betas_for_alpha_bar(
+            num_diffusion_timesteps,
+            lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2,
+        )
+    raise NotImplementedError(f"unknown beta schedule: {schedule_name}")
+
+
+def betas_for_alpha_bar(num_diffusion_timesteps, alpha_bar, max_beta=0.999):
+    """beta_i = min(1 - abar((i+1)/N) / abar(i/N), max_beta)."""
+    n = num_diffusion_timesteps
+    out = [min(1 - alpha_bar((i + 1) / n) / alpha_bar(i / n), max_beta) for i in range(n)]
+    return np.array(out)
+
+
+class ModelMeanType(enum.Enum):
+    PREVIOUS_X = enum.auto()
+    START_X = enum.auto()
+    EPSILON = enum.auto()
+
+
+class ModelVarType(enum.Enum):
+    LEARNED = enum.auto()
+    FIXED_SMALL = enum.auto()
+    FIXED_LARGE = enum.auto()
+    LEARNED_RANGE = enum.auto()
+
+
+class LossType(enum.Enum):
+    MSE = enum.auto()
+    RESCALED_MSE = enum.auto()
+    KL = enum.auto()
+    RESCALED_KL = enum.auto()
+
+    def is_vb(self):
+        return self in (LossType.KL, LossType.RESCALED_KL)
+
+
+def _extract_into_tensor(arr, timesteps, broadcast_shape):
+    """fp32 gather of a host table, broadcast to ``broadcast_shape`` (reference :1605-1618).
+    Kept for API compatibility; the fused kernels never call it."""
+    res = th.from_numpy(np.asarray(arr)).to(device=timesteps.device)[timesteps].float()
+    while len(res.shape) < len(broadcast_shape):
+        res = res[..., None]
+    return res.expand(broadcast_shape)
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, th.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the mst sampler has no CPU path")
+
+
+def _f32c(t):
+    """fp32 + contiguous view of a CUDA tensor (copy only when needed)."""
+    if t.dtype != th.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class GaussianDiffusion:
+    """Sampling utilities of the diffusion process (reference class of the same name, :111)."""
+
+    def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False,
+                 lambda_rcxyz=0., lambda_vel=0., lambda_pose=1., lambda_orient=1., lambda_loc=1., data_rep='rot6d',
+                 lambda_root_vel=0., lambda_vel_rcxyz=0., lambda_fc=0., lambda_sty_cons=0., lambda_sty_trans=0.,
+                 lambda_cont_pers=0., lambda_cont_vel=0., lambda_diff_sty=0., lambda_l1=10.):
+        self.model_mean_type = model_mean_type
+        self.model_var_type = model_var_type
+        self.loss_type = loss_type
+        self.rescale_timesteps = rescale_timesteps
+        self.data_rep = data_rep
+        if data_rep != 'rot_vel' and lambda_pose != 1.:
+            raise ValueError('lambda_pose is relevant only when training on velocities!')
+        self.lambda_pose, self.lambda_orient, self.lambda_loc = lambda_pose, lambda_orient, lambda_loc
+        self.lambda_rcxyz, self.lambda_vel, self.lambda_root_vel = lambda_rcxyz, lambda_vel, lambda_root_vel
+        self.lambda_vel_rcxyz, self.lambda_fc, self.lambda_l1 = lambda_vel_rcxyz, lambda_fc, lambda_l1
+        self.lambda_sty_cons, self.lambda_sty_trans = lambda_sty_cons, lambda_sty_trans
+        self.lambda_cont_pers, self.lambda_cont_vel, self.lambda_diff_sty = lambda_cont_pers, lambda_cont_vel, lambda_diff_sty
+        if (lambda_rcxyz > 0. or lambda_vel > 0. or lambda_root_vel > 0. or lambda_vel_rcxyz > 0. or lambda_fc > 0.):
+            assert self.loss_type == LossType.MSE, 'Geometric losses are supported by MSE loss type only!'
+
+        # float64 host tables, same formulas and evaluation order as the reference (:183-219)
+        betas = np.array(betas, dtype=np.float64)
+        self.betas = betas
+        assert len(betas.shape) == 1, "betas must be 1-D"
+        assert (betas > 0).all() and (betas <= 1).all()
+        self.num_timesteps = int(betas.shape[0])
+        alphas = 1.0 - betas
+        self.alphas_cumprod = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod_prev = np.append(1.0, self.alphas_cumprod[:-1])
+        self.alphas_cumprod_next = np.append(self.alphas_cumprod[1:], 0.0)
+        assert self.alphas_cumprod_prev.shape == (self.num_timesteps,)
+        self.sqrt_alphas_cumprod = np.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)
+        self.log_one_minus_alphas_cumprod = np.log(1.0 - self.alphas_cumprod)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        self.posterior_variance = betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+        self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
+
+        self.l2_loss = lambda a, b: (a - b) ** 2
+
+        # --- B200 runtime knobs (not part of the reference API) ---
+        # rng: 'torch'  -> th.randn_like per step from the global generator, like the reference
+        #      'philox' -> noise generated inside the update kernel, keyed by (seed, global sample, t)
+        self.rng = os.environ.get("MST_RNG", "torch")
+        self.philox_seed = int(os.environ.get("MST_SEED", "0"))
+        self.philox_sample_offset = 0          # global index of this shard's first sample (multi-GPU)
+        self.noise_fn = None                   # optional callable(step_number, shape, device) -> eps tensor
+        self.use_cuda_graph = os.environ.get("MST_GRAPH", "1") != "0"
+        self.steps_per_graph = int(os.environ.get("MST_STEPS_PER_GRAPH", "1"))
+        self._dev = {}
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ tables
+    def _variance_tables(self):
+        if self.model_var_type == ModelVarType.FIXED_SMALL:
+            return self.posterior_variance, self.posterior_log_variance_clipped
+        if self.model_var_type == ModelVarType.FIXED_LARGE:
+            v = np.append(self.posterior_variance[1], self.betas[1:])
+            return v, np.log(v)
+        raise NotImplementedError(
+            f"{self.model_var_type}: learned variances are not on the reference's hot path "
+            "(utils/model_util.py:176 fixes learn_sigma=False)")
+
+    def device_tables(self, device, eta=0.0):
+        """fp32 device copies of the per-timestep coefficients (uploaded once per device/eta)."""
+        key = (str(device), float(eta))
+        tabs = self._dev.get(key)
+        if tabs is None:
+            var, logvar = self._variance_tables()
+            ab, abp = self.alphas_cumprod, self.alphas_cumprod_prev
+            ddim_sigma = eta * np.sqrt((1 - abp) / (1 - ab)) * np.sqrt(1 - ab / abp)
+            host = {
+                "c1": self.posterior_mean_coef1, "c2": self.posterior_mean_coef2,
+                "sigma": np.exp(0.5 * logvar), "var": var, "logvar": logvar,
+                "sqrt_ab": self.sqrt_alphas_cumprod, "sqrt_1m_ab": self.sqrt_one_minus_alphas_cumprod,
+                "recip": self.sqrt_recip_alphas_cumprod, "recipm1": self.sqrt_recipm1_alphas_cumprod,
+                "ddim_c1": np.sqrt(abp), "ddim_c2": np.sqrt(1 - abp - ddim_sigma ** 2), "ddim_sigma": ddim_sigma,
+                "ab": ab, "abp": abp,
+            }
+            tabs = {k: th.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(th.float32).to(device)
+                    for k, v in host.items()}
+            self._dev[key] = tabs
+        return tabs
+
+    # ------------------------------------------------------------------ small API
+    def masked_l2(self, a, b, mask):
+        """sum((a-b)^2 * mask) / (sum(mask) * J*Jdim) per sample (reference :223-235)."""
+        loss = self.l2_loss(a, b)
+        loss = (loss * mask.float()).flatten(1).sum(dim=1)
+        n_entries = a.shape[1] * a.shape[2]
+        non_zero_elements = mask.flatten(1).sum(dim=1) * n_entries
+        return loss / non_zero_elements
+
+    def q_mean_variance(self, x_start, t):
+        mean = _extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+        variance = _extract_into_tensor(1.0 - self.alphas_cumprod, t, x_start.shape)
+        log_variance = _extract_into_tensor(self.log_one_minus_alphas_cumprod, t, x_start.shape)
+        return mean, variance, log_variance
+
+    def _inpainting_mask_for_noise(self, model_kwargs):
+        """Mask applied to the noise; the base process applies none (InpaintingGaussianDiffusion overrides)."""
+        return None
+
+    def q_sample(self, x_start, t, noise=None, model_kwargs=None):
+        """x_t ~ q(x_t | x_0): sqrt(abar_t) x_0 + sqrt(1-abar_t) eps (reference :267-285)."""
+        _require_cuda(x_start, "x_start")
+        if noise is None:
+            noise = th.randn_like(x_start)
+        assert noise.shape == x_start.shape
+        tabs = self.device_tables(x_start.device)
+        mask = self._inpainting_mask_for_noise(model_kwargs)
+        if mask is not None:
+            mask = _f32c(mask)
+        out = K.q_sample(_f32c(x_start), _f32c(noise), mask, t.to(th.int64).contiguous(), 0, tabs["sqrt_ab"],
+                         tabs["sqrt_1m_ab"])
+        if mask is not None:
+            # the reference mutates its `noise` argument in place (inpainting_gaussian_diffusion.py:18);
+            # callers can observe that through `noise=` / `img`, so it is reproduced
+            noise.mul_(1. - mask)
+        return out
+
+    def q_posterior_mean_variance(self, x_start, x_t, t):
+        assert x_start.shape == x_t.shape
+        tabs = self.device_tables(x_t.device)
+        mean = th.empty_like(x_t, dtype=th.float32)
+        K.update_step(sampler=L.SAMPLER_DDPM, out_cond=_f32c(x_start), x_t=_f32c(x_t), x_prev=mean,
+                      coef1=tabs["c1"], coef2=tabs["c2"], t_vec=t.to(th.int64).contiguous(), noise_kind=L.NOISE_NONE)
+        pv = _extract_into_tensor(self.posterior_variance, t, x_t.shape)
+        plv = _extract_into_tensor(self.posterior_log_variance_clipped, t, x_t.shape)
+        return mean, pv, plv
+
+    def _scale_timesteps(self, t):
+        if self.rescale_timesteps:
+            return t.float() * (1000.0 / self.num_timesteps)
+        return t
+
+    def _predict_xstart_from_eps(self, x_t, t, eps):
+        assert x_t.shape == eps.shape
+        return (_extract_into_tensor(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t
+                - _extract_into_tensor(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * eps)
+
+    def _predict_eps_from_xstart(self, x_t, t, pred_xstart):
+        return ((_extract_into_tensor(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t - pred_xstart)
+                / _extract_into_tensor(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape))
+
+    # ------------------------------------------------------------------ model plumbing
+    def _wrap_model(self, model):
+        return model
+
+    def _model_time_index(self, t_index):
+        """timestep handed to the denoiser for process index t (identity here; respaced subclasses remap)."""
+        return t_index
+
+    def _map_model_t(self, t):
+        """tensor version of _model_time_index (what _WrappedModel.__call__ computes, respace.py:129-134)."""
+        return self._scale_timesteps(t)
+
+    @staticmethod
+    def _unwrap(model):
+        """(inner native denoiser or None, cfg wrapper or None)."""
+        from ..model.cfg_sampler import ClassifierFreeSampleModel
+        from ..model.mdm_forstyledataset import NativeDenoiser
+        m = getattr(model, "model", None) if type(model).__name__ == "_WrappedModel" else None
+        m = m if m is not None else model
+        if isinstance(m, ClassifierFreeSampleModel):
+            inner = m.model
+            return (inner if isinstance(inner, NativeDenoiser) else None), m
+        return (m if isinstance(m, NativeDenoiser) else None), None
+
+    def _check_inpainting(self, model_kwargs, shape):
+        y = model_kwargs['y']  # KeyError when absent, like the reference (:341)
+        if 'inpainting_mask' in y.keys() and 'inpainted_motion' in y.keys():
+            assert self.model_mean_type == ModelMeanType.START_X, 'This feature supports only X_start pred for mow!'
+            mask, inp = y['inpainting_mask'], y['inpainted_motion']
+            assert tuple(shape) == tuple(mask.shape) == tuple(inp.shape)
+            return _f32c(mask), _f32c(inp)
+        return None, None
+
+    def _model_outputs(self, model, x, t, model_kwargs):
+        """Run the denoiser.  Returns (out_cond, out_uncond or None, cfg_scale or None)."""
+        native, cfgw = self._unwrap(model)
+        if native is not None and native.mst_ready(x):
+            y = model_kwargs['y']
+            t_model = self._map_model_t(t)
+            if cfgw is not None:
+                oc, ou = native.forward_cfg(x, t_model, y)
+                return oc, ou, _f32c(y['scale'].to(x.device)).view(-1)
+            return _f32c(native(x, t_model, **model_kwargs)), None, None
+        out = self._wrap_model(model)(x, self._scale_timesteps(t), **model_kwargs)
+        return _f32c(out), None, None
+
+    # ------------------------------------------------------------------ one step
+    def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None):
+        """p(x_{t-1} | x_t) and the x_0 prediction (reference :311-424): dict with
+        'mean', 'variance', 'log_variance', 'pred_xstart'."""
+        if model_kwargs is None:
+            model_kwargs = {}
+        _require_cuda(x, "x")
+        B, C = x.shape[:2]
+        assert t.shape == (B,)
+        if self.model_mean_type != ModelMeanType.START_X:
+            raise NotImplementedError(
+                f"{self.model_mean_type}: only START_X is on the reference's hot path (utils/model_util.py:173)")
+        x = _f32c(x)
+        oc, ou, scale = self._model_outputs(model, x, t, model_kwargs)
+        mask, inp = self._check_inpainting(model_kwargs, x.shape)
+        tabs = self.device_tables(x.device)
+        mean, x0 = th.empty_like(x), th.empty_like(x)
+        if denoised_fn is not None:
+            # arbitrary user hook: materialise x0 first (blend only), apply, then finish the posterior
+            K.update_step(sampler=L.SAMPLER_DDPM, out_cond=oc, out_uncond=ou, cfg_scale=scale, x_t=x, x_prev=mean,
+                          pred_xstart=x0, mask=mask, x_inpaint=inp, coef1=tabs["c1"], coef2=tabs["c2"],
+                          t_vec=t.to(th.int64).contiguous(), clip_denoised=False)
+            oc, ou, scale, mask_k, inp_k = _f32c(denoised_fn(x0)), None, None, None, None
+        else:
+            mask_k, inp_k = mask, inp
+        K.update_step(sampler=L.SAMPLER_DDPM, out_cond=oc, out_uncond=ou, cfg_scale=scale, x_t=x, x_prev=mean,
+                      pred_xstart=x0, mask=mask_k, x_inpaint=inp_k, coef1=tabs["c1"], coef2=tabs["c2"],
+                      t_vec=t.to(th.int64).contiguous(), clip_denoised=clip_denoised)
+        shape4 = (-1,) + (1,) * (x.dim() - 1)
+        tl = t.to(th.int64)
+        out = {
+            "mean": mean,
+            "variance": tabs["var"][tl].view(shape4).expand(x.shape),
+            "log_variance": tabs["logvar"][tl].view(shape4).expand(x.shape),
+            "pred_xstart": x0,
+        }
+        assert out["mean"].shape == out["log_variance"].shape == out["pred_xstart"].shape == x.shape
+        return out
+
+    def condition_mean(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
+        gradient = cond_fn(x, self._scale_timesteps(t), **model_kwargs)
+        return p_mean_var["mean"].float() + p_mean_var["variance"] * gradient.float()
+
+    def _draw_noise(self, x, step_no, const_noise=False):
+        if self.noise_fn is not None:
+            eps = self.noise_fn(step_no, tuple(x.shape), x.device)
+            _require_cuda(eps, "noise_fn result")
+            eps = _f32c(eps)
+        else:
+            eps = th.randn_like(x)
+        if const_noise:
+            eps = eps[[0]].repeat(x.shape[0], 1, 1, 1)
+        return eps
+
+    def _sample_step(self, sampler, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, const_noise=False,
+                     eta=0.0, step_no=0):
+        """One reverse step with everything after the denoiser fused (p_sample :532 / ddim_sample :796)."""
+        if model_kwargs is None:
+            model_kwargs = {}
+        _require_cuda(x, "x")
+        if self.model_mean_type != ModelMeanType.START_X:
+            raise NotImplementedError(f"{self.model_mean_type}: only START_X is supported")
+        if cond_fn is not None or denoised_fn is not None:
+            return self._sample_step_unfused(sampler, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs,
+                                             const_noise, eta, step_no)
+        x = _f32c(x)
+        assert t.shape == (x.shape[0],)
+        oc, ou, scale = self._model_outputs(model, x, t, model_kwargs)
+        mask, inp = self._check_inpainting(model_kwargs, x.shape)
+        nmask = self._inpainting_mask_for_noise(model_kwargs)
+        tabs = self.device_tables(x.device, eta)
+        sample, x0 = th.empty_like(x), th.empty_like(x)
+        if self.rng == "philox" and self.noise_fn is None:
+            noise_kind, eps = L.NOISE_PHILOX, None
+        else:
+            noise_kind, eps = L.NOISE_TENSOR, self._draw_noise(x, step_no, const_noise)
+            const_noise = False  # already materialised
+        kmask = mask if mask is not None else (_f32c(nmask) if nmask is not None else None)
+        common = dict(out_cond=oc, out_uncond=ou, cfg_scale=scale, x_t=x, x_prev=sample, pred_xstart=x0, mask=kmask,
+                      x_inpaint=inp, mask_noise=nmask is not None, clip_denoised=clip_denoised,
+                      t_vec=t.to(th.int64).contiguous(), noise_kind=noise_kind, noise=eps, const_noise=const_noise,
+                      philox_seed=self.philox_seed, philox_sample_offset=self.philox_sample_offset)
+        if sampler == L.SAMPLER_DDPM:
+            K.update_step(sampler=sampler, coef1=tabs["c1"], coef2=tabs["c2"], sigma=tabs["sigma"], **common)
+        else:
+            K.update_step(sampler=sampler, coef1=tabs["ddim_c1"], coef2=tabs["ddim_c2"], sigma=tabs["ddim_sigma"],
+                          recip=tabs["recip"], recipm1=tabs["recipm1"], **common)
+        return {"sample": sample, "pred_xstart": x0}
+
+    def _sample_step_unfused(self, sampler, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, const_noise,
+                             eta, step_no):
+        """cond_fn / denoised_fn hooks (unused by every reference caller): p_mean_variance + torch glue."""
+        out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                   model_kwargs=model_kwargs)
+        eps = self._draw_noise(x, step_no, const_noise)
+        nmask = self._inpainting_mask_for_noise(model_kwargs)
+        if nmask is not None:
+            eps = eps * (1. - nmask)
+        nonzero = (t != 0).float().view(-1, *([1] * (x.dim() - 1)))
+        if sampler == L.SAMPLER_DDPM:
+            if cond_fn is not None:
+                out["mean"] = self.condition_mean(cond_fn, out, x, t, model_kwargs=model_kwargs)
+            sample = out["mean"] + nonzero * th.exp(0.5 * out["log_variance"]) * eps
+            return {"sample": sample, "pred_xstart": out["pred_xstart"]}
+        x0 = out["pred_xstart"]
+        if cond_fn is not None:
+            alpha_bar = _extract_into_tensor(self.alphas_cumprod, t, x.shape)
+            e = self._predict_eps_from_xstart(x, t, x0)
+            e = e - (1 - alpha_bar).sqrt() * cond_fn(x, self._scale_timesteps(t), **model_kwargs)
+            x0 = self._predict_xstart_from_eps(x, t, e)
+        e = self._predict_eps_from_xstart(x, t, x0)
+        alpha_bar = _extract_into_tensor(self.alphas_cumprod, t, x.shape)
+        alpha_bar_prev = _extract_into_tensor(self.alphas_cumprod_prev, t, x.shape)
+        sigma = eta * th.sqrt((1 - alpha_bar_prev) / (1 - alpha_bar)) * th.sqrt(1 - alpha_bar / alpha_bar_prev)
+        mean_pred = x0 * th.sqrt(alpha_bar_prev) + th.sqrt(1 - alpha_bar_prev - sigma ** 2) * e
+        return {"sample": mean_pred + nonzero * sigma * eps, "pred_xstart": out["pred_xstart"]}
+
+    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                 const_noise=False, pred_xstart_in_graph=False):
+        """x_{t-1} ~ p(x_{t-1} | x_t) (reference :532-585); returns {'sample', 'pred_xstart'}."""
+        return self._sample_step(L.SAMPLER_DDPM, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs,
+                                 const_noise=const_noise)
+
+    def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0,
+                    pred_xstart_in_graph=False):
+        """One DDIM step (reference :796-847)."""
+        return self._sample_step(L.SAMPLER_DDIM, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, eta=eta)
+
+    def p_sample_with_grad(self, *args, **kwargs):
+        raise NotImplementedError(
+            "p_sample_with_grad (differentiable sampling for few_shot_style_finetune_losses) needs the backward "
+            "kernels, which are the next row of the scope table (DESIGN.md section 'Out of scope / next')")
+
+    ddim_sample_with_grad = p_sample_with_grad
+
+    def few_shot_style_finetune_losses(self, *args, **kwargs):
+        raise NotImplementedError(
+            "few_shot_style_finetune_losses needs the fused backward kernels (SURVEY section 8 rows A19/A20); "
+            "not built in this round - see DESIGN.md")
+
+    # ------------------------------------------------------------------ loops
+    def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                      model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
+                      randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False,
+                      pred_xstart_in_graph=False, dump_all_xstart=False, stop_timesteps=None):
+        """Full DDPM trajectory (reference :644-715).  Returns the final sample, or a list when
+        ``dump_steps`` / ``dump_all_xstart`` is given."""
+        final = None
+        dump = [] if (dump_steps is not None or dump_all_xstart) else None
+        for i, sample in enumerate(self.p_sample_loop_progressive(
+                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+                model_kwargs=model_kwargs, device=device, progress=progress, skip_timesteps=skip_timesteps,
+                init_image=init_image, randomize_class=randomize_class, cond_fn_with_grad=cond_fn_with_grad,
+                const_noise=const_noise, pred_xstart_in_graph=pred_xstart_in_graph, stop_timesteps=stop_timesteps,
+                _want_xstart=dump_all_xstart, _own_buffers=dump is None)):
+            if dump_steps is not None and i in dump_steps:
+                dump.append(deepcopy(sample["sample"]))
+            if dump_all_xstart:
+                dump.append(sample["pred_xstart"])
+            final = sample
+        if dump is not None:
+            return dump
+        return final["sample"]
+
+    def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                  model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
+                                  randomize_class=False, cond_fn_with_grad=False, const_noise=False,
+                                  pred_xstart_in_graph=False, stop_timesteps=None, _want_xstart=True,
+                                  _own_buffers=False):
+        """Generator over the per-step dicts of p_sample (reference :717-794)."""
+        yield from self._loop(L.SAMPLER_DDPM, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs,
+                              device, progress, skip_timesteps, init_image, randomize_class,
+                              cond_fn_with_grad or pred_xstart_in_graph, const_noise, stop_timesteps, 0.0,
+                              _want_xstart, _own_buffers)
+
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0, init_image=None,
+                         randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False,
+                         pred_xstart_in_graph=False, dump_all_xstart=False, stop_timesteps=None):
+        """Full DDIM trajectory (reference :948-1005)."""
+        dump = [] if (dump_steps is not None or dump_all_xstart) else None
+        if const_noise == True:  # noqa: E712  (reference :978)
+            raise NotImplementedError()
+        final = None
+        for sample in self.ddim_sample_loop_progressive(
+                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+                model_kwargs=model_kwargs, device=device, progress=progress, eta=eta, skip_timesteps=skip_timesteps,
+                init_image=init_image, randomize_class=randomize_class, cond_fn_with_grad=cond_fn_with_grad,
+                pred_xstart_in_graph=pred_xstart_in_graph, stop_timesteps=stop_timesteps,
+                _want_xstart=dump_all_xstart, _own_buffers=dump is None):
+            if dump_all_xstart:
+                dump.append(sample["pred_xstart"])
+            final = sample
+        if dump_all_xstart:
+            return dump
+        return final["sample"]
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                     model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0,
+                                     init_image=None, randomize_class=False, cond_fn_with_grad=False,
+                                     pred_xstart_in_graph=False, stop_timesteps=None, _want_xstart=True,
+                                     _own_buffers=False):
+        """Generator over the per-step dicts of ddim_sample (reference :1007-1082)."""
+        yield from self._loop(L.SAMPLER_DDIM, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs,
+                              device, progress, skip_timesteps, init_image, randomize_class,
+                              cond_fn_with_grad or pred_xstart_in_graph, False, stop_timesteps, eta, _want_xstart,
+                              _own_buffers)
+
+    # the shared driver -----------------------------------------------------------
+    def _loop(self, sampler, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress,
+              skip_timesteps, init_image, randomize_class, with_grad, const_noise, stop_timesteps, eta, want_xstart,
+              own_buffers):
+        if with_grad:
+            raise NotImplementedError(
+                "cond_fn_with_grad / pred_xstart_in_graph sampling needs the backward kernels (not built this round)")
+        if device is None:
+            try:
+                device = next(model.parameters()).device
+            except Exception:
+                device = next(model.model.parameters()).device
+        device = th.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("the mst sampler runs on CUDA devices only (model is on %s)" % device)
+        assert isinstance(shape, (tuple, list))
+        if noise is not None:
+            img = noise
+        else:
+            img = th.randn(*shape, device=device)
+        if skip_timesteps and init_image is None:
+            init_image = th.zeros_like(img)
+        indices = list(range(self.num_timesteps - skip_timesteps))[::-1]
+        if stop_timesteps is not None:
+            indices = list(range(stop_timesteps, self.num_timesteps - skip_timesteps))[::-1]
+        if init_image is not None:
+            my_t = th.ones([shape[0]], device=device, dtype=th.long) * indices[0]
+            img = self.q_sample(init_image, my_t, img, model_kwargs=model_kwargs)
+        if not indices:
+            return
+
+        native, cfgw = self._unwrap(model)
+        fused = (native is not None and cond_fn is None and denoised_fn is None and not randomize_class
+                 and model_kwargs is not None and 'y' in model_kwargs and native.mst_ready(img))
+        if fused:
+            yield from self._fused_trajectory(sampler, native, cfgw, img, indices, clip_denoised, model_kwargs,
+                                              const_noise, eta, progress, want_xstart, own_buffers)
+            return
+
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        for step_no, i in enumerate(indices):
+            t = th.full((shape[0],), i, device=device, dtype=th.long)
+            if randomize_class and 'y' in model_kwargs:
+                model_kwargs['y'] = th.randint(low=0, high=model.num_classes, size=model_kwargs['y'].shape,
+                                               device=model_kwargs['y'].device)
+            with th.no_grad():
+                out = self._sample_step(sampler, model, img, t, clip_denoised, denoised_fn, cond_fn, model_kwargs,
+                                        const_noise=const_noise, eta=eta, step_no=step_no)
+                yield out
+                img = out["sample"]
+
+    # ------------------------------------------------------------------ fused native trajectory
+    def _fused_trajectory(self, sampler, native, cfgw, img, indices, clip_denoised, model_kwargs, const_noise, eta,
+                          progress, want_xstart, own_buffers):
+        """Whole trajectory on the hand-written path: per step = one denoiser forward
+        (cond+uncond batched) + one fused update kernel, replayed as a CUDA graph with the
+        timestep living in device memory."""
+        device = img.device
+        y = model_kwargs['y']
+        B, T = img.shape[0], img.shape[-1]
+        eng = native.mst_engine(device)
+        use_cfg = cfgw is not None
+        with th.no_grad():
+            x = _f32c(img).clone()
+            mask, inp = self._check_inpainting(model_kwargs, x.shape)
+            nmask = self._inpainting_mask_for_noise(model_kwargs)
+            kmask = mask if mask is not None else (_f32c(nmask) if nmask is not None else None)
+            kmask = native.compact_mask(kmask)
+            # hoisted out of the loop: CLIP/text embedding (the reference re-encodes every step,
+            # mdm_forstyledataset.py:326) and the time-embedding MLP for every step of this trajectory
+            uncond_all = bool(y.get('uncond', False)) and not use_cfg
+            text_emb = None if uncond_all else native.text_embedding(y, device)
+            t_model = th.tensor([self._model_time_index(i) for i in range(self.num_timesteps)], device=device,
+                                dtype=th.long)
+            temb = eng.time_embed(t_model)                       # row t = time embedding of process index t
+            scale = _f32c(y['scale'].to(device)).view(-1) if use_cfg else None
+            tabs = self.device_tables(device, eta)
+            n_steps = len(indices)
+            assert all(indices[k] - 1 == indices[k + 1] for k in range(n_steps - 1))
+            # device-resident step state: the process index t (the update kernel decrements it)
+            t_dev = th.tensor([indices[0]], device=device, dtype=th.int32)
+            counter = th.zeros(1, device=device, dtype=th.int32)
+            out_c = th.empty_like(x)
+            out_u = th.empty_like(x) if use_cfg else None
+            x0 = th.empty_like(x) if want_xstart or not own_buffers else None
+            use_philox = self.rng == "philox" and self.noise_fn is None
+            eps = None if use_philox else th.empty_like(x)
+            if sampler == L.SAMPLER_DDPM:
+                coefs = dict(coef1=tabs["c1"], coef2=tabs["c2"], sigma=tabs["sigma"])
+            else:
+                coefs = dict(coef1=tabs["ddim_c1"], coef2=tabs["ddim_c2"], sigma=tabs["ddim_sigma"],
+                             recip=tabs["recip"], recipm1=tabs["recipm1"])
+
+            def one_step(draw_noise=True):
+                eng.forward(x, temb, text_emb, cfg=use_cfg, uncond=uncond_all, out_cond=out_c, out_uncond=out_u,
+                            temb_row_dev=t_dev)
+                if eps is not None and draw_noise:
+                    eps.normal_()
+                    if const_noise:
+                        eps.copy_(eps[[0]].expand_as(eps).clone())
+                K.update_step(sampler=sampler, out_cond=out_c, out_uncond=out_u, cfg_scale=scale, x_t=x, x_prev=x,
+                              pred_xstart=x0, mask=kmask, x_inpaint=inp, mask_noise=nmask is not None,
+                              clip_denoised=clip_denoised, t_scalar_dev=t_dev, advance_t=True, block_counter=counter,
+                              noise_kind=L.NOISE_PHILOX if use_philox else L.NOISE_TENSOR, noise=eps,
+                              const_noise=const_noise and use_philox, philox_seed=self.philox_seed,
+                              philox_sample_offset=self.philox_sample_offset, **coefs)
+
+            graph = None
+            if self.use_cuda_graph and self.noise_fn is None:
+                # warm-up on a side stream (allocations, lazy module load), then capture one step
+                snap = (x.clone(), t_dev.clone())
+                rng_state = th.cuda.get_rng_state(device)
+                s = th.cuda.Stream(device=device)
+                s.wait_stream(th.cuda.current_stream(device))
+                with th.cuda.stream(s):
+                    one_step()
+                th.cuda.current_stream(device).wait_stream(s)
+                th.cuda.synchronize(device)
+                x.copy_(snap[0]); t_dev.copy_(snap[1]); counter.zero_()
+                th.cuda.set_rng_state(rng_state, device)
+                graph = th.cuda.CUDAGraph()
+                with th.cuda.graph(graph):
+                    one_step()
+                # capture does not execute: state is still the snapshot
+
+            it = range(n_steps)
+            if progress:
+                from tqdm.auto import tqdm
+                it = tqdm(it)
+            for k in it:
+                if graph is not None:
+                    graph.replay()
+                else:
+                    if self.noise_fn is not None:
+                        e = _f32c(self.noise_fn(k, tuple(x.shape), device))
+                        if const_noise:
+                            e = e[[0]].repeat(B, 1, 1, 1)
+                        eps.copy_(e)
+                        one_step(draw_noise=False)
+                    else:
+                        one_step()
+                if own_buffers:
+                    # the caller only wants the last sample: hand out the live buffers
+                    yield {"sample": x, "pred_xstart": x0}
+                else:
+                    yield {"sample": x.clone(), "pred_xstart": x0.clone()}

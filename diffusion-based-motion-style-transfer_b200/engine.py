@@ -1,0 +1,242 @@
+"""Python handle on the C-ABI denoiser engine and the fused update kernels.
+
+PyTorch is used only for device memory and streams; every device operation is
+a call into libmst_b200.so.  All tensors handed to these wrappers must be
+CUDA, contiguous and of the documented dtype - anything else raises (there is
+no CPU path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def default_precision() -> str:
+    p = os.environ.get("MST_PRECISION", "bf16").lower()
+    if p not in ("bf16", "fp32"):
+        raise ValueError(f"MST_PRECISION must be 'bf16' or 'fp32', got {p!r}")
+    return p
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=torch.float32, name="tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: must live on a CUDA device (the mst kernels have no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: must be contiguous")
+    return t.data_ptr()
+
+
+class Engine:
+    """One denoiser (MDM / StyleDiffusion) instance on one GPU."""
+
+    LAYER_KEYS = L._LAYER_FIELDS
+
+    def __init__(self, n_feats: int, d_model: int = 512, n_heads: int = 4, d_ff: int = 1024, n_layers: int = 8,
+                 clip_dim: int = 512, pe_len: int = 5000, precision: Optional[str] = None,
+                 device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mst Engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        self.precision = precision or default_precision()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.desc = L.ModelDesc(n_feats, d_model, n_heads, d_ff, n_layers, clip_dim, pe_len,
+                                L.PREC_BF16 if self.precision == "bf16" else L.PREC_FP32)
+        h = C.c_void_p()
+        L.check(self.lib.mst_engine_create(C.byref(self.desc), C.byref(h)), "mst_engine_create")
+        self._h = h
+        self._packed = None
+        self._keep = None  # tensors whose storage the engine aliases
+        self._ws = None
+        self.n_feats, self.d_model = n_feats, d_model
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.mst_engine_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- weights -----------------------------------------------------------------
+    def load_weights(self, top: dict, layers: list):
+        """top: in_w,in_b,pe,t_w1,t_b1,t_w2,t_b2,txt_w,txt_b,out_w,out_b -> fp32 CUDA tensors (txt_* may be None);
+        layers: list of dicts keyed by LAYER_KEYS."""
+        w = L.Weights()
+        keep = []
+        with torch.cuda.device(self.device):
+            for k in ("in_w", "in_b", "pe", "t_w1", "t_b1", "t_w2", "t_b2", "txt_w", "txt_b", "out_w", "out_b"):
+                t = top.get(k)
+                if t is not None:
+                    t = t.detach()
+                    if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                        t = t.to(self.device, torch.float32).contiguous()
+                    keep.append(t)
+                setattr(w, k, _ptr(t, name=k))
+            if len(layers) != self.desc.n_layers:
+                raise ValueError(f"expected {self.desc.n_layers} layers, got {len(layers)}")
+            for i, lw in enumerate(layers):
+                for k in self.LAYER_KEYS:
+                    t = lw[k].detach()
+                    if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                        t = t.to(self.device, torch.float32).contiguous()
+                    keep.append(t)
+                    setattr(w.layers[i], k, _ptr(t, name=f"layer{i}.{k}"))
+            nbytes = C.c_size_t()
+            L.check(self.lib.mst_engine_packed_weight_bytes(self._h, C.byref(nbytes)))
+            if self._packed is None or self._packed.numel() < nbytes.value:
+                self._packed = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            L.check(self.lib.mst_engine_load_weights(self._h, C.byref(w), self._packed.data_ptr(), nbytes.value,
+                                                     _stream_ptr()), "mst_engine_load_weights")
+        self._keep = keep
+
+    # -- scratch -----------------------------------------------------------------
+    def workspace(self, n_seqs: int, n_frames: int) -> torch.Tensor:
+        nbytes = C.c_size_t()
+        L.check(self.lib.mst_engine_workspace_bytes(self._h, n_seqs, n_frames, C.byref(nbytes)))
+        if self._ws is None or self._ws.numel() < nbytes.value:
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # -- small embeddings ----------------------------------------------------------
+    def time_embed(self, t: torch.Tensor) -> torch.Tensor:
+        """rows of time_embed(pe[t]) (reference TimestepEmbedder.forward, mdm_forstyledataset.py:421)."""
+        t = t.to(self.device, torch.int64).contiguous()
+        n = t.numel()
+        out = torch.empty(n, self.d_model, dtype=torch.float32, device=self.device)
+        scratch = torch.empty(n, self.d_model, dtype=torch.float32, device=self.device)
+        L.check(self.lib.mst_time_embed(self._h, t.data_ptr(), n, out.data_ptr(), scratch.data_ptr(),
+                                        scratch.numel() * 4, _stream_ptr()), "mst_time_embed")
+        return out
+
+    def text_embed(self, feat: torch.Tensor) -> torch.Tensor:
+        """embed_text(feat) (reference mdm_forstyledataset.py:327)."""
+        n = feat.shape[0]
+        out = torch.empty(n, self.d_model, dtype=torch.float32, device=self.device)
+        L.check(self.lib.mst_text_embed(self._h, _ptr(feat, name="text_feat"), n, out.data_ptr(), _stream_ptr()),
+                "mst_text_embed")
+        return out
+
+    # -- forward -----------------------------------------------------------------
+    def forward(self, x: torch.Tensor, temb: torch.Tensor, text_emb: Optional[torch.Tensor], *, cfg: bool = False,
+                uncond: bool = False, out_cond: Optional[torch.Tensor] = None,
+                out_uncond: Optional[torch.Tensor] = None, temb_row_dev: Optional[torch.Tensor] = None,
+                temb_row_offset: int = 0):
+        """x [B,F,1,T] fp32 -> model output(s) [B,F,1,T].  With cfg=True both the
+        conditional and the unconditional pass run batched and two tensors return."""
+        B, T = x.shape[0], x.shape[-1]
+        if x.numel() != B * self.n_feats * T:
+            raise ValueError(f"x has shape {tuple(x.shape)}, expected [B,{self.n_feats},1,T]")
+        if out_cond is None:
+            out_cond = torch.empty_like(x)
+        if cfg and out_uncond is None:
+            out_uncond = torch.empty_like(x)
+        ws = self.workspace(B * (2 if cfg else 1), T)
+        a = L.ForwardArgs()
+        a.batch, a.n_frames, a.cfg, a.uncond = B, T, int(cfg), int(uncond)
+        a.x = _ptr(x, name="x")
+        a.temb = _ptr(temb, name="temb")
+        a.temb_row_dev = _ptr(temb_row_dev, torch.int32, "temb_row_dev")
+        a.temb_row_offset = temb_row_offset
+        a.text_emb = _ptr(text_emb, name="text_emb")
+        a.out_cond = _ptr(out_cond, name="out_cond")
+        a.out_uncond = _ptr(out_uncond, name="out_uncond") if cfg else None
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        L.check(self.lib.mst_denoiser_forward(self._h, C.byref(a), _stream_ptr()), "mst_denoiser_forward")
+        return (out_cond, out_uncond) if cfg else out_cond
+
+
+# ---------------------------------------------------------------------------------
+# fused diffusion kernels (no engine needed)
+# ---------------------------------------------------------------------------------
+def mask_kind_of(mask: Optional[torch.Tensor], shape) -> int:
+    if mask is None:
+        return L.MASK_NONE
+    B, F, T = shape[0], shape[1] * shape[2], shape[3]
+    n = mask.numel()
+    if n == B * F * T:
+        return L.MASK_FULL
+    if n == F * T:
+        return L.MASK_FT
+    if n == F:
+        return L.MASK_F
+    raise ValueError(f"inpainting mask with {n} elements does not match state shape {tuple(shape)}")
+
+
+def update_step(*, sampler: int, out_cond, x_t, x_prev, coef1, coef2, sigma=None, recip=None, recipm1=None,
+                out_uncond=None, cfg_scale=None, pred_xstart=None, mask=None, x_inpaint=None, mask_noise=True,
+                clip_denoised=False, t_vec=None, t_scalar_dev=None, t_imm=0, advance_t=False, block_counter=None,
+                noise_kind=L.NOISE_NONE, noise=None, const_noise=False, philox_seed=0, philox_sample_offset=0):
+    lib = L.load()
+    B, F, T = x_t.shape[0], x_t.shape[1] * x_t.shape[2], x_t.shape[3]
+    a = L.UpdateArgs()
+    a.batch, a.n_feats, a.n_frames = B, F, T
+    a.sampler, a.clip_denoised = sampler, int(bool(clip_denoised))
+    a.out_cond = _ptr(out_cond, name="out_cond")
+    a.out_uncond = _ptr(out_uncond, name="out_uncond")
+    a.cfg_scale = _ptr(cfg_scale, name="cfg_scale")
+    a.x_t = _ptr(x_t, name="x_t")
+    a.x_prev = _ptr(x_prev, name="x_prev")
+    a.pred_xstart = _ptr(pred_xstart, name="pred_xstart")
+    a.mask_kind = mask_kind_of(mask, x_t.shape)
+    a.mask = _ptr(mask, name="inpainting_mask")
+    a.x_inpaint = _ptr(x_inpaint, name="inpainted_motion")
+    a.mask_noise = int(bool(mask_noise))
+    a.t_vec = _ptr(t_vec, torch.int64, "t")
+    a.t_scalar_dev = _ptr(t_scalar_dev, torch.int32, "t_scalar_dev")
+    a.t_imm, a.advance_t = int(t_imm), int(bool(advance_t))
+    a.block_counter = _ptr(block_counter, torch.int32, "block_counter")
+    a.coef1, a.coef2 = _ptr(coef1, name="coef1"), _ptr(coef2, name="coef2")
+    a.sigma, a.recip, a.recipm1 = _ptr(sigma, name="sigma"), _ptr(recip, name="recip"), _ptr(recipm1, name="recipm1")
+    a.noise_kind = noise_kind
+    a.noise = _ptr(noise, name="noise")
+    a.const_noise = int(bool(const_noise))
+    a.philox_seed, a.philox_sample_offset = int(philox_seed) & (2**64 - 1), int(philox_sample_offset)
+    L.check(lib.mst_update_step(C.byref(a), _stream_ptr()), "mst_update_step")
+    return x_prev
+
+
+def q_sample(x_start, noise, mask, t_vec, t_imm, sqrt_ab, sqrt_1m_ab, out=None):
+    lib = L.load()
+    B, F, T = x_start.shape[0], x_start.shape[1] * x_start.shape[2], x_start.shape[3]
+    if out is None:
+        out = torch.empty_like(x_start)
+    L.check(lib.mst_q_sample(_ptr(x_start, name="x_start"), _ptr(noise, name="noise"), mask_kind_of(mask, x_start.shape),
+                             _ptr(mask, name="inpainting_mask"), _ptr(t_vec, torch.int64, "t"), int(t_imm),
+                             _ptr(sqrt_ab, name="sqrt_ab"), _ptr(sqrt_1m_ab, name="sqrt_1m_ab"), out.data_ptr(), B, F, T,
+                             _stream_ptr()), "mst_q_sample")
+    return out
+
+
+def cfg_combine(out_cond, out_uncond, scale, out=None):
+    lib = L.load()
+    if out is None:
+        out = torch.empty_like(out_cond)
+    B = out_cond.shape[0]
+    L.check(lib.mst_cfg_combine(_ptr(out_cond, name="out_cond"), _ptr(out_uncond, name="out_uncond"),
+                                _ptr(scale, name="scale"), out.data_ptr(), B, out_cond.numel() // B, _stream_ptr()),
+            "mst_cfg_combine")
+    return out
+
+
+def philox_normal(shape, seed: int, sample_offset: int, t: int, device) -> torch.Tensor:
+    lib = L.load()
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    B = shape[0]
+    L.check(lib.mst_philox_normal(out.data_ptr(), B, out.numel() // B, int(seed) & (2**64 - 1), int(sample_offset), int(t),
+                                  _stream_ptr()), "mst_philox_normal")
+    return out

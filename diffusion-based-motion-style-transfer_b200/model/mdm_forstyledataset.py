@@ -1,0 +1,460 @@
+"""Denoisers of the reference's ``model/mdm_forstyledataset.py`` as thin
+``nn.Module`` shells around the hand-written sm_100a forward.
+
+The modules keep the reference's constructor signatures, attribute names and
+``state_dict`` layout (so reference checkpoints load with the same
+``load_model_wo_clip`` / ``load_model_wo_moenc`` discipline,
+``utils/model_util.py:9-23``), but their ``forward`` does not execute any torch
+layer: parameters are handed to the C-ABI engine, which packs them (bf16 for
+the tcgen05 path) and runs InputProcess -> 8 x TransformerEncoderLayer ->
+OutputProcess as fused CUDA kernels.
+
+Scope: ``arch='trans_enc'`` with a single Linear in/out projection
+(``data_rep`` in rot6d / xyz / hml_vec) - the only configuration the reference's
+scripts instantiate (``utils/model_util.py:108-167``).  Other arches raise.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..engine import Engine, default_precision
+
+
+# ----------------------------------------------------------------------------------
+# parameter containers with the reference's state_dict key names
+# ----------------------------------------------------------------------------------
+class _SelfAttnParams(nn.Module):
+    """Keys of nn.MultiheadAttention: in_proj_weight, in_proj_bias, out_proj.{weight,bias}."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+        self.out_proj = nn.Linear(d, d)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+
+class _EncoderLayerParams(nn.Module):
+    """Keys of nn.TransformerEncoderLayer (post-norm): self_attn, linear1, linear2, norm1, norm2."""
+
+    def __init__(self, d, ff):
+        super().__init__()
+        self.self_attn = _SelfAttnParams(d)
+        self.linear1 = nn.Linear(d, ff)
+        self.linear2 = nn.Linear(ff, d)
+        self.norm1 = nn.LayerNorm(d, eps=1e-5)
+        self.norm2 = nn.LayerNorm(d, eps=1e-5)
+
+    def mst_tensors(self):
+        return {
+            "qkv_w": self.self_attn.in_proj_weight, "qkv_b": self.self_attn.in_proj_bias,
+            "o_w": self.self_attn.out_proj.weight, "o_b": self.self_attn.out_proj.bias,
+            "w1": self.linear1.weight, "b1": self.linear1.bias, "w2": self.linear2.weight, "b2": self.linear2.bias,
+            "ln1_g": self.norm1.weight, "ln1_b": self.norm1.bias, "ln2_g": self.norm2.weight, "ln2_b": self.norm2.bias,
+        }
+
+
+class _EncoderParams(nn.Module):
+    """Keys of nn.TransformerEncoder: layers.{i}.*"""
+
+    def __init__(self, d, ff, n_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([_EncoderLayerParams(d, ff) for _ in range(n_layers)])
+
+
+class PositionalEncoding(nn.Module):
+    """Sinusoidal table, persisted buffer 'pe' of shape [max_len, 1, d] (reference :387-404)."""
+
+    def __init__(self, d_model, dropout=0.1, max_len=5000):
+        super().__init__()
+        self.dropout_p = dropout
+        pe = torch.zeros(max_len, d_model)
+        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-np.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer('pe', pe.unsqueeze(0).transpose(0, 1))
+
+
+class TimestepEmbedder(nn.Module):
+    """time_embed = Linear -> SiLU -> Linear applied to pe[t] (reference :408-422)."""
+
+    def __init__(self, latent_dim, sequence_pos_encoder):
+        super().__init__()
+        self.latent_dim = latent_dim
+        self.sequence_pos_encoder = sequence_pos_encoder
+        self.time_embed = nn.Sequential(nn.Linear(latent_dim, latent_dim), nn.SiLU(), nn.Linear(latent_dim, latent_dim))
+
+
+class InputProcess(nn.Module):
+    def __init__(self, data_rep, input_feats, latent_dim):
+        super().__init__()
+        self.data_rep, self.input_feats, self.latent_dim = data_rep, input_feats, latent_dim
+        self.poseEmbedding = nn.Linear(input_feats, latent_dim)
+
+
+class OutputProcess(nn.Module):
+    def __init__(self, data_rep, input_feats, latent_dim, njoints, nfeats):
+        super().__init__()
+        self.data_rep, self.input_feats, self.latent_dim = data_rep, input_feats, latent_dim
+        self.njoints, self.nfeats = njoints, nfeats
+        self.poseFinal = nn.Linear(latent_dim, input_feats)
+
+
+class _NullRot2xyz:
+    """Placeholder for the SMPL forward wrapper the reference instantiates but never calls on the
+    hot path (mdm_forstyledataset.py:270); rendering is out of scope."""
+    smpl_model = None
+
+
+def _load_clip(clip_version):
+    """Frozen CLIP text tower, if the ``clip`` package is importable (it is third-party and absent
+    from the sandbox).  Without it callers must put ``y['text_feat']`` ([B, clip_dim]) in model_kwargs."""
+    try:
+        import clip  # type: ignore
+    except Exception:
+        return None
+    clip_model, _ = clip.load(clip_version, device='cpu', jit=False)
+    clip.model.convert_weights(clip_model)
+    clip_model.eval()
+    for p in clip_model.parameters():
+        p.requires_grad = False
+    return clip_model
+
+
+# ----------------------------------------------------------------------------------
+class NativeDenoiser(nn.Module):
+    """Common engine plumbing of MDM and StyleDiffusion."""
+
+    mst_precision = None  # None -> MST_PRECISION env (bf16 default) ; or 'fp32' / 'bf16'
+
+    # subclasses provide these views -------------------------------------------------
+    def _mst_front(self):
+        """module that owns input_process / sequence_pos_encoder / embed_timestep / embed_text / output_process"""
+        raise NotImplementedError
+
+    def _mst_encoder(self):
+        """the _EncoderParams whose layers run between in- and out-projection"""
+        raise NotImplementedError
+
+    # ---------------------------------------------------------------------------------
+    def _mst_all_tensors(self):
+        f = self._mst_front()
+        top = {
+            "in_w": f.input_process.poseEmbedding.weight, "in_b": f.input_process.poseEmbedding.bias,
+            "pe": f.sequence_pos_encoder.pe,
+            "t_w1": f.embed_timestep.time_embed[0].weight, "t_b1": f.embed_timestep.time_embed[0].bias,
+            "t_w2": f.embed_timestep.time_embed[2].weight, "t_b2": f.embed_timestep.time_embed[2].bias,
+            "txt_w": f.embed_text.weight if hasattr(f, "embed_text") else None,
+            "txt_b": f.embed_text.bias if hasattr(f, "embed_text") else None,
+            "out_w": f.output_process.poseFinal.weight, "out_b": f.output_process.poseFinal.bias,
+        }
+        layers = [l.mst_tensors() for l in self._mst_encoder().layers]
+        return top, layers
+
+    def _mst_signature(self, top, layers):
+        sig = []
+        for d in [top] + layers:
+            for t in d.values():
+                if t is not None:
+                    sig.append((t.data_ptr(), t._version))
+        return tuple(sig)
+
+    def mst_ready(self, x) -> bool:
+        """True when ``x`` and the parameters live on the same CUDA device (the only supported case)."""
+        if not (isinstance(x, torch.Tensor) and x.is_cuda):
+            return False
+        p = self._mst_front().input_process.poseEmbedding.weight
+        if not p.is_cuda or p.device != x.device:
+            raise RuntimeError(f"model parameters are on {p.device} but the input is on {x.device}: move the model "
+                               "to the CUDA device first (there is no CPU fallback)")
+        return True
+
+    def mst_engine(self, device) -> Engine:
+        """Engine for this module on ``device``; weights are (re)packed whenever a parameter changed."""
+        prec = self.mst_precision or default_precision()
+        key = (str(device), prec)
+        cache = self.__dict__.setdefault("_mst_engines", {})
+        top, layers = self._mst_all_tensors()
+        sig = self._mst_signature(top, layers)
+        ent = cache.get(key)
+        if ent is None:
+            f = self._mst_front()
+            eng = Engine(n_feats=self.input_feats, d_model=self.latent_dim, n_heads=self.num_heads,
+                         d_ff=self.ff_size, n_layers=len(layers), clip_dim=self.clip_dim,
+                         pe_len=f.sequence_pos_encoder.pe.shape[0], precision=prec, device=device)
+            ent = [eng, None]
+            cache[key] = ent
+        if ent[1] != sig:
+            top = dict(top)
+            top["pe"] = top["pe"].reshape(top["pe"].shape[0], -1)
+            ent[0].load_weights(top, layers)
+            ent[1] = sig
+        return ent[0]
+
+    # -- conditioning ------------------------------------------------------------------
+    def encode_text(self, raw_text):
+        """CLIP text features [B, clip_dim] fp32 (reference :298-313).  CLIP itself is third-party and
+        outside the hot path; when it is not installed, pass ``y['text_feat']`` instead."""
+        f = self._mst_front()
+        clip_model = getattr(f, "clip_model", None)
+        if clip_model is None:
+            raise RuntimeError("no CLIP text encoder is attached to this model (the `clip` package is not installed); "
+                               "provide precomputed features as y['text_feat'] with shape [B, clip_dim]")
+        import clip  # type: ignore
+        device = next(self.parameters()).device
+        max_text_len = 20 if self.dataset in ['humanml', 'kit'] else None
+        if max_text_len is not None:
+            default_context_length = 77
+            context_length = max_text_len + 2
+            texts = clip.tokenize(raw_text, context_length=context_length, truncate=True).to(device)
+            zero_pad = torch.zeros([texts.shape[0], default_context_length - context_length], dtype=texts.dtype,
+                                   device=texts.device)
+            texts = torch.cat([texts, zero_pad], dim=1)
+        else:
+            texts = clip.tokenize(raw_text, truncate=True).to(device)
+        return clip_model.encode_text(texts).float()
+
+    def mask_cond(self, cond, force_mask=False):
+        bs, d = cond.shape
+        if force_mask:
+            return torch.zeros_like(cond)
+        elif self.training and self.cond_mask_prob > 0.:
+            mask = torch.bernoulli(torch.ones(bs, device=cond.device) * self.cond_mask_prob).view(bs, 1)
+            return cond * (1. - mask)
+        return cond
+
+    def text_features(self, y, device):
+        """[B, clip_dim] fp32 CUDA: y['text_feat'] when given, else CLIP(y['text'])."""
+        if 'text' not in self.cond_mode:
+            return None
+        feat = y.get('text_feat', None)
+        if feat is None:
+            feat = self.encode_text(y['text'])
+        return self.mask_cond(feat.to(device).float()).contiguous()
+
+    def text_embedding(self, y, device):
+        """embed_text(mask_cond(clip(text))) [B, d]; computed once per trajectory by the sampler."""
+        feat = self.text_features(y, device)
+        if feat is None:
+            return None
+        return self.mst_engine(device).text_embed(feat)
+
+    @staticmethod
+    def compact_mask(mask):
+        """[B,F,1,T] mask that does not vary over batch and time -> [F] vector (all named masks of
+        data_loaders/*_utils.py except in_between/prefix).  Saves one state-sized read per step."""
+        if mask is None or mask.dim() != 4:
+            return mask
+        col = mask[:1, :, :, :1]
+        if bool((mask == col).all()):
+            return col.reshape(-1).contiguous()
+        row = mask[:1]
+        if bool((mask == row).all()):
+            return row.reshape(mask.shape[1] * mask.shape[2], mask.shape[3]).contiguous()
+        return mask
+
+    # -- forward -----------------------------------------------------------------------
+    def forward(self, x, timesteps, y=None):
+        """x: [B, njoints, nfeats, T] (x_t); timesteps: [B] int; y: dict with 'text' or 'text_feat',
+        optional 'uncond'.  Returns the x_0 prediction [B, njoints, nfeats, T] (reference :315-364)."""
+        if not self.mst_ready(x):
+            raise RuntimeError("the mst denoiser runs on CUDA tensors only (no CPU fallback)")
+        y = y if y is not None else {}
+        eng = self.mst_engine(x.device)
+        force_mask = bool(y.get('uncond', False))
+        xc = x.float().contiguous()
+        temb = eng.time_embed(timesteps)
+        text_emb = None if force_mask else self.text_embedding(y, x.device)
+        if 'text' in self.cond_mode and text_emb is None and not force_mask:
+            raise RuntimeError("text-conditioned model called without text")
+        return eng.forward(xc, temb, text_emb, cfg=False, uncond=force_mask or text_emb is None)
+
+    def forward_cfg(self, x, timesteps, y):
+        """Both passes of ClassifierFreeSampleModel.forward batched: returns (out_cond, out_uncond)."""
+        eng = self.mst_engine(x.device)
+        xc = x.float().contiguous()
+        temb = eng.time_embed(timesteps)
+        text_emb = self.text_embedding(y, x.device)
+        if text_emb is None:
+            raise RuntimeError("classifier-free guidance needs a text-conditioned model")
+        return eng.forward(xc, temb, text_emb, cfg=True)
+
+
+def _common_init(self, modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot, latent_dim,
+                 ff_size, num_layers, num_heads, dropout, ablation, activation, legacy, data_rep, dataset, clip_dim,
+                 arch, emb_trans_dec, clip_version, kargs):
+    self.legacy = legacy
+    self.modeltype = modeltype
+    self.njoints = njoints
+    self.nfeats = nfeats
+    self.num_actions = num_actions
+    self.data_rep = data_rep
+    self.dataset = dataset
+    self.pose_rep = pose_rep
+    self.glob = glob
+    self.glob_rot = glob_rot
+    self.translation = translation
+    self.latent_dim = latent_dim
+    self.ff_size = ff_size
+    self.num_layers = num_layers
+    self.num_heads = num_heads
+    self.dropout = dropout
+    self.ablation = ablation
+    self.activation = activation
+    self.clip_dim = clip_dim
+    self.action_emb = kargs.get('action_emb', None)
+    self.input_feats = self.njoints * self.nfeats
+    self.normalize_output = kargs.get('normalize_encoder_output', False)
+    self.cond_mode = kargs.get('cond_mode', 'no_cond')
+    self.cond_mask_prob = kargs.get('cond_mask_prob', 0.)
+    self.arch = arch
+    self.gru_emb_dim = self.latent_dim if self.arch == 'gru' else 0
+    self.emb_trans_dec = emb_trans_dec
+    self.clip_version = clip_version
+    if arch != 'trans_enc':
+        raise NotImplementedError(f"arch={arch!r}: only 'trans_enc' is on the reference's hot path "
+                                  "(sample/demo_style_transfer.py and train/finetune_style_diffusion.py)")
+    if data_rep not in ('rot6d', 'xyz', 'hml_vec'):
+        raise NotImplementedError(f"data_rep={data_rep!r}: the 'rot_vel' two-projection variant is not built")
+    if activation != "gelu":
+        raise NotImplementedError("only the GELU feed-forward the reference configures is built")
+    if 'action' in self.cond_mode:
+        raise NotImplementedError("action conditioning is not used by the reference's scripts and is not built")
+
+
+class MDM(NativeDenoiser):
+    """Reference ``MDM`` (mdm_forstyledataset.py:183-384): text-conditioned transformer-encoder denoiser."""
+
+    def __init__(self, modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot,
+                 latent_dim=256, ff_size=1024, num_layers=8, num_heads=4, dropout=0.1,
+                 ablation=None, activation="gelu", legacy=False, data_rep='rot6d', dataset='amass', clip_dim=512,
+                 arch='trans_enc', emb_trans_dec=False, clip_version=None, **kargs):
+        super().__init__()
+        _common_init(self, modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot, latent_dim,
+                     ff_size, num_layers, num_heads, dropout, ablation, activation, legacy, data_rep, dataset,
+                     clip_dim, arch, emb_trans_dec, clip_version, kargs)
+        self.input_process = InputProcess(self.data_rep, self.input_feats + self.gru_emb_dim, self.latent_dim)
+        self.sequence_pos_encoder = PositionalEncoding(self.latent_dim, self.dropout)
+        self.seqTransEncoder = _EncoderParams(self.latent_dim, self.ff_size, self.num_layers)
+        self.embed_timestep = TimestepEmbedder(self.latent_dim, self.sequence_pos_encoder)
+        if self.cond_mode != 'no_cond' and 'text' in self.cond_mode:
+            self.embed_text = nn.Linear(self.clip_dim, self.latent_dim)
+            clip_model = _load_clip(clip_version) if kargs.get('load_clip', True) else None
+            if clip_model is not None:
+                self.clip_model = clip_model
+        self.output_process = OutputProcess(self.data_rep, self.input_feats, self.latent_dim, self.njoints, self.nfeats)
+        self.rot2xyz = _NullRot2xyz()
+
+    def _mst_front(self):
+        return self
+
+    def _mst_encoder(self):
+        return self.seqTransEncoder
+
+    def parameters_wo_clip(self):
+        return [p for name, p in self.named_parameters() if not name.startswith('clip_model.')]
+
+
+class MotionEncoder(nn.Module):
+    """Parameter holder of the reference's frozen semantic discriminator (mdm_forstyledataset.py:11-124).
+    Its own forward (mu/sigma query tokens + key-padding mask) is only used by the finetune loss and is
+    listed under "next" in the scope table; here it carries ``mdm_model``, whose projections and
+    embedders ``StyleDiffusion`` borrows."""
+
+    def __init__(self, modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot,
+                 latent_dim=256, ff_size=1024, num_layers=8, num_heads=4, dropout=0.1,
+                 ablation=None, activation="gelu", legacy=False, data_rep='rot6d', dataset='amass', clip_dim=512,
+                 arch='trans_enc', emb_trans_dec=False, clip_version=None, **kargs):
+        super().__init__()
+        self.latent_dim, self.ff_size, self.num_layers, self.num_heads = latent_dim, ff_size, num_layers, num_heads
+        self.njoints, self.nfeats = njoints, nfeats
+        self.input_feats = njoints * nfeats
+        self.cond_mask_prob = kargs.get('cond_mask_prob', 0.)
+        self.muQuery = nn.Parameter(torch.randn(1, latent_dim))
+        self.sigmaQuery = nn.Parameter(torch.randn(1, latent_dim))
+        self.seqTransEncoder = _EncoderParams(latent_dim, ff_size, num_layers)
+        self.mdm_model = MDM(modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot,
+                             latent_dim, ff_size, num_layers, num_heads, dropout, ablation, activation, legacy,
+                             data_rep, dataset, clip_dim, arch, emb_trans_dec, clip_version, **kargs)
+        mdm_path = kargs.get("mdm_path", "")
+        if mdm_path:
+            print("load mdm_model from checkpoint {}".format(mdm_path))
+            self.load_model_wo_clip(self.mdm_model, torch.load(mdm_path, map_location='cpu'))
+        self.mdm_model.eval()
+        for p in self.mdm_model.parameters():
+            p.requires_grad = False
+
+    def parameters_wo_clip(self):
+        return [p for name, p in self.named_parameters() if not name.startswith('mdm_model.')]
+
+    @staticmethod
+    def load_model_wo_clip(model, state_dict):
+        missing_keys, unexpected_keys = model.load_state_dict(state_dict, strict=False)
+        assert len(unexpected_keys) == 0
+        assert all([k.startswith('clip_model.') for k in missing_keys])
+
+    def forward(self, x, y=None):
+        raise NotImplementedError("MotionEncoder.forward (semantic guidance of the finetune loss) is the N3 "
+                                  "'next' row of the scope table and is not built in this round")
+
+
+class StyleDiffusion(NativeDenoiser):
+    """Reference ``StyleDiffusion`` (mdm_forstyledataset.py:494-625): its own trainable ``seqTransEncoder``
+    between the frozen ``motion_enc.mdm_model``'s projections and embedders."""
+
+    def __init__(self, modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot,
+                 latent_dim=256, ff_size=1024, num_layers=8, num_heads=4, dropout=0.1,
+                 ablation=None, activation="gelu", legacy=False, data_rep='rot6d', dataset='amass', clip_dim=512,
+                 arch='trans_enc', emb_trans_dec=False, clip_version=None, **kargs):
+        super().__init__()
+        _common_init(self, modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot, latent_dim,
+                     ff_size, num_layers, num_heads, dropout, ablation, activation, legacy, data_rep, dataset,
+                     clip_dim, arch, emb_trans_dec, clip_version, kargs)
+        self.kargs = kargs
+        self.seqTransEncoder = _EncoderParams(self.latent_dim, self.ff_size, self.num_layers)
+        self.motion_enc = MotionEncoder(modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot,
+                                        latent_dim, ff_size, num_layers, num_heads, dropout, ablation, activation,
+                                        legacy, data_rep, dataset, clip_dim, arch, emb_trans_dec, clip_version, **kargs)
+        self.load_motion_enc()
+
+    def load_motion_enc(self):
+        path = self.kargs.get("semantic_discriminator_path", "")
+        if path:
+            print("load motion_enc from checkpoint {}".format(path))
+            self.load_model(self.motion_enc, torch.load(path, map_location='cpu'))
+        self.motion_enc = self.motion_enc.eval()
+        for p in self.motion_enc.parameters():
+            p.requires_grad = False
+        assert all([not para.requires_grad for para in self.motion_enc.parameters()])
+
+    @staticmethod
+    def load_model(model, state_dict):
+        missing_keys, unexpected_keys = model.load_state_dict(state_dict, strict=False)
+        assert len(unexpected_keys) == 0
+        assert all([k.startswith('mdm_model.') for k in missing_keys])
+
+    def parameters_wo_enc(self):
+        return [p for name, p in self.named_parameters() if not name.startswith('motion_enc.')]
+
+    def _mst_front(self):
+        return self.motion_enc.mdm_model
+
+    def _mst_encoder(self):
+        return self.seqTransEncoder
+
+    def encode_text(self, raw_text):
+        return self.motion_enc.mdm_model.encode_text(raw_text)
+
+
+# name the reference exports for the (unused) style/content-code variant; utils/model_util.py imports it
+class DiffuseTrasnfer(StyleDiffusion):
+    def __init__(self, *args, **kargs):
+        raise NotImplementedError("DiffuseTrasnfer is defined but never instantiated by the reference's scripts "
+                                  "(SURVEY section 2); use StyleDiffusion")

@@ -1,0 +1,255 @@
+/*
+ * mst.h — C-ABI of the B200-native motion-style-transfer sampler ("mst").
+ *
+ * This is the drop-in boundary for ONE hot path of
+ * hlcdyy/diffusion-based-motion-style-transfer: the MDM-style denoising loop
+ * (p_sample_loop / ddim_sample_loop + respacing + inpainting blend + CFG)
+ * around the transformer-encoder denoiser.  The reference is pure
+ * Python/PyTorch and has no FFI of its own; each entry point below cites the
+ * Python function (file:line, relative to the reference root) whose device
+ * work it replaces.  The Python host layer that mirrors the reference's class
+ * API lives in `diffusion-based-motion-style-transfer_b200/` and binds these
+ * symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer named *_dev / documented "device" is a CUDA device pointer
+ *     owned by the caller (PyTorch allocates; the library never frees it);
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream()
+ *     .cuda_stream); all launches are asynchronous on it and are legal inside
+ *     CUDA-graph capture (no allocation, no sync, no host reads);
+ *   - every function returns 0 on success, non-zero on error;
+ *     mst_last_error() returns a thread-local message for the last failure;
+ *   - tensors are dense, row-major, fp32 unless stated.  The motion state is
+ *     [B, F, 1, T] (reference layout, model/mdm_forstyledataset.py:317) which
+ *     is addressed here as [B][F][T].
+ *   - there is NO CPU fallback: a missing GPU / wrong arch is an error.
+ */
+#ifndef MST_H_
+#define MST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MST_OK 0
+#define MST_ERR_INVALID 1
+#define MST_ERR_CUDA 2
+#define MST_ERR_UNSUPPORTED 3
+
+#define MST_MAX_LAYERS 32
+
+/* precision of the denoiser forward */
+#define MST_PREC_FP32 0 /* SIMT fp32 everywhere: parity mode (<=1e-4 rel)   */
+#define MST_PREC_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulate      */
+
+/* sampler kind for mst_update_step */
+#define MST_SAMPLER_DDPM 0 /* p_sample,   inpainting_gaussian_diffusion.py:25  */
+#define MST_SAMPLER_DDIM 1 /* ddim_sample, inpainting_gaussian_diffusion.py:125 */
+
+/* noise source for mst_update_step */
+#define MST_NOISE_NONE 0   /* no noise term (t==0 everywhere / eta==0)        */
+#define MST_NOISE_TENSOR 1 /* read eps from `noise` (torch RNG or injected)   */
+#define MST_NOISE_PHILOX 2 /* Philox4x32-10 + Box-Muller generated in-kernel  */
+
+/* inpainting-mask storage */
+#define MST_MASK_NONE 0
+#define MST_MASK_FULL 1 /* [B,F,T] fp32, exactly what the reference reads     */
+#define MST_MASK_FT 2   /* [F,T]  fp32, batch-invariant mask                  */
+#define MST_MASK_F 3    /* [F]    fp32, batch- and time-invariant mask        */
+
+const char* mst_version(void);
+const char* mst_last_error(void);
+
+/* Number of SMs / compute capability of the current device (diagnostics). */
+int mst_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* sizeof() of the argument structs as this library was compiled - lets a
+ * foreign-language binding verify its own struct layout (no GPU needed).   */
+int mst_abi_sizes(size_t* model_desc, size_t* weights, size_t* forward_args, size_t* update_args);
+
+/* ------------------------------------------------------------------------ *
+ * Denoiser description — model/mdm_forstyledataset.py:184-270 (MDM.__init__),
+ * :495-567 (StyleDiffusion.__init__); utils/model_util.py:108-167.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_feats;   /* F = njoints*nfeats (181 stylexia, 263 humanml)       */
+  int32_t d_model;   /* latent_dim (512)                                     */
+  int32_t n_heads;   /* 4                                                    */
+  int32_t d_ff;      /* 1024                                                 */
+  int32_t n_layers;  /* 8                                                    */
+  int32_t clip_dim;  /* 512                                                  */
+  int32_t pe_len;    /* rows of the positional-encoding table (5000)         */
+  int32_t precision; /* MST_PREC_*                                           */
+} mst_model_desc;
+
+/* One nn.TransformerEncoderLayer (post-norm, GELU) — fp32 device pointers in
+ * the reference's own state_dict layout (mdm_forstyledataset.py:231-238).   */
+typedef struct {
+  const float* qkv_w; /* self_attn.in_proj_weight [3d, d] */
+  const float* qkv_b; /* self_attn.in_proj_bias   [3d]    */
+  const float* o_w;   /* self_attn.out_proj.weight [d, d] */
+  const float* o_b;   /* self_attn.out_proj.bias   [d]    */
+  const float* w1;    /* linear1.weight [ff, d]           */
+  const float* b1;    /* linear1.bias   [ff]              */
+  const float* w2;    /* linear2.weight [d, ff]           */
+  const float* b2;    /* linear2.bias   [d]               */
+  const float* ln1_g; /* norm1.weight [d]                 */
+  const float* ln1_b; /* norm1.bias   [d]                 */
+  const float* ln2_g; /* norm2.weight [d]                 */
+  const float* ln2_b; /* norm2.bias   [d]                 */
+} mst_layer_weights;
+
+typedef struct {
+  const float* in_w;  /* input_process.poseEmbedding.weight [d, F]  (:431) */
+  const float* in_b;  /* input_process.poseEmbedding.bias   [d]            */
+  const float* pe;    /* sequence_pos_encoder.pe [pe_len, d]        (:392) */
+  const float* t_w1;  /* embed_timestep.time_embed.0.weight [d, d]  (:415) */
+  const float* t_b1;
+  const float* t_w2;  /* embed_timestep.time_embed.2.weight [d, d]         */
+  const float* t_b2;
+  const float* txt_w; /* embed_text.weight [d, clip_dim]            (:258) */
+  const float* txt_b;
+  const float* out_w; /* output_process.poseFinal.weight [F, d]     (:460) */
+  const float* out_b;
+  mst_layer_weights layers[MST_MAX_LAYERS];
+} mst_weights;
+
+typedef struct mst_engine_s* mst_engine_t;
+
+int mst_engine_create(const mst_model_desc* desc, mst_engine_t* out);
+int mst_engine_destroy(mst_engine_t e);
+
+/* Bytes of device memory the engine needs for its packed copy of the weights
+ * (bf16 tiles padded for TMA in MST_PREC_BF16; 0-copy aliases in FP32).     */
+int mst_engine_packed_weight_bytes(mst_engine_t e, size_t* bytes);
+
+/* (Re)pack weights.  Call after load_state_dict and after every optimizer
+ * step.  `packed_dev` must stay alive while the engine is used.             */
+int mst_engine_load_weights(mst_engine_t e, const mst_weights* w, void* packed_dev,
+                            size_t packed_bytes, void* stream);
+
+/* Workspace (activations) needed for one forward over n_seqs sequences of
+ * n_frames frames (n_seqs = 2B under batched CFG).                          */
+int mst_engine_workspace_bytes(mst_engine_t e, int n_seqs, int n_frames, size_t* bytes);
+
+/* TimestepEmbedder.forward (mdm_forstyledataset.py:421): rows of
+ * time_embed(pe[t]).  t_dev: int64[n] device.  out: [n, d] device.          */
+int mst_time_embed(mst_engine_t e, const int64_t* t_dev, int n, float* out_dev,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* embed_text (mdm_forstyledataset.py:327 / :615): feat [n, clip_dim] -> [n, d] */
+int mst_text_embed(mst_engine_t e, const float* feat_dev, int n, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Denoiser forward — MDM.forward (:315-364) / StyleDiffusion.forward
+ * (:602-625), optionally with the two passes of ClassifierFreeSampleModel
+ * .forward (model/cfg_sampler.py:36-43) batched into one launch sequence.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t batch;     /* B                                                    */
+  int32_t n_frames;  /* T  (S = T+1 tokens)                                  */
+  int32_t cfg;       /* 0: one pass;  1: cond + uncond passes batched (2B)   */
+  int32_t uncond;    /* cfg==0 only: force_mask (y['uncond']) for all rows   */
+  const float* x;    /* [B, F, T] device                                     */
+  /* token-0 ingredients */
+  const float* temb; /* [n_rows, d] device: time_embed rows                  */
+  const int32_t* temb_row_dev; /* device scalar: row of `temb` shared by all
+                                  samples (graph-replayable); NULL => row b  */
+  int32_t temb_row_offset;     /* added to *temb_row_dev (or to b)           */
+  const float* text_emb;       /* [B, d] device: embed_text(clip(text)); may
+                                  be NULL when uncond or cond_mode has no text*/
+  /* outputs */
+  float* out_cond;   /* [B, F, T] device (the only output when cfg==0)       */
+  float* out_uncond; /* [B, F, T] device, cfg==1                             */
+  void* workspace;   /* device, >= mst_engine_workspace_bytes                */
+  size_t workspace_bytes;
+} mst_forward_args;
+
+int mst_denoiser_forward(mst_engine_t e, const mst_forward_args* a, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Fused per-step update — replaces, in ONE memory-bound kernel:
+ *   cfg lerp          model/cfg_sampler.py:43
+ *   inpainting blend  diffusion/gaussian_diffusion.py:341-349
+ *   x0 clamp          :390-396
+ *   posterior mean    :287-309 (coef1*x0 + coef2*x_t), FIXED_SMALL var :375-388
+ *   masked noise      diffusion/inpainting_gaussian_diffusion.py:51-63
+ *   (DDIM variant     :125-174)
+ * All coefficient tables are fp32[N] device arrays produced on the host in
+ * float64 and cast once (gaussian_diffusion.py:1605-1618 casts per call).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t batch, n_feats, n_frames;
+  int32_t sampler;          /* MST_SAMPLER_*                                 */
+  int32_t clip_denoised;    /* clamp x0 to [-1,1]                            */
+  /* model output(s) */
+  const float* out_cond;    /* [B,F,T]                                       */
+  const float* out_uncond;  /* [B,F,T] or NULL (no CFG)                      */
+  const float* cfg_scale;   /* [B] or NULL                                   */
+  /* state */
+  const float* x_t;         /* [B,F,T]                                       */
+  float* x_prev;            /* [B,F,T] out: "sample"                         */
+  float* pred_xstart;       /* [B,F,T] out or NULL                           */
+  /* inpainting */
+  int32_t mask_kind;        /* MST_MASK_*                                    */
+  const float* mask;        /* per mask_kind                                 */
+  const float* x_inpaint;   /* [B,F,T] (y['inpainted_motion']) or NULL       */
+  int32_t mask_noise;       /* 1: eps *= (1-mask) (Inpainting override);
+                               0: base GaussianDiffusion.p_sample            */
+  /* timestep: exactly one of the three sources */
+  const int64_t* t_vec;     /* [B] device, per-sample t, or NULL             */
+  int32_t* t_scalar_dev;    /* device scalar shared by the batch, or NULL    */
+  int32_t t_imm;            /* host immediate, used when both are NULL       */
+  int32_t advance_t;        /* 1: after the step, *t_scalar_dev -= 1 (last
+                               block does it) so a captured graph can replay */
+  int32_t* block_counter;   /* device int32 scratch (zeroed), for advance_t  */
+  /* schedule tables, fp32[N] device */
+  const float* coef1;       /* DDPM: posterior_mean_coef1 | DDIM: sqrt(abar_prev)          */
+  const float* coef2;       /* DDPM: posterior_mean_coef2 | DDIM: sqrt(1-abar_prev-sig^2)  */
+  const float* sigma;       /* DDPM: exp(.5*post_log_var_clipped) | DDIM: eta-sigma        */
+  const float* recip;       /* DDIM: sqrt_recip_alphas_cumprod    (NULL for DDPM)          */
+  const float* recipm1;     /* DDIM: sqrt_recipm1_alphas_cumprod  (NULL for DDPM)          */
+  /* noise */
+  int32_t noise_kind;       /* MST_NOISE_*                                   */
+  const float* noise;       /* [B,F,T] when MST_NOISE_TENSOR                 */
+  int32_t const_noise;      /* 1: every sample uses sample 0's noise (:571)  */
+  uint64_t philox_seed;
+  uint64_t philox_sample_offset; /* global index of sample 0 of this shard   */
+} mst_update_args;
+
+int mst_update_step(const mst_update_args* a, void* stream);
+
+/* q_sample with the inpainting override (inpainting_gaussian_diffusion.py:6-23):
+ * x_t = sqrt_ab[t]*x0 + sqrt_1m_ab[t]*(eps*(1-mask)).  `noise` is read-only
+ * here; the in-place mutation the reference performs on its `noise` argument is
+ * reproduced by the Python layer when it matters.  mask may be NULL.        */
+int mst_q_sample(const float* x_start, const float* noise, int32_t mask_kind, const float* mask,
+                 const int64_t* t_vec, int32_t t_imm, const float* sqrt_ab, const float* sqrt_1m_ab,
+                 float* x_t, int32_t batch, int32_t n_feats, int32_t n_frames, void* stream);
+
+/* out = out_u + scale[b]*(out_c - out_u)  (model/cfg_sampler.py:43)         */
+int mst_cfg_combine(const float* out_cond, const float* out_uncond, const float* scale,
+                    float* out, int32_t batch, int64_t per_sample, void* stream);
+
+/* Fill `out` [B,F,T] with the N(0,1) stream MST_NOISE_PHILOX uses for (seed,
+ * step key `t`): lets tests and the oracle check the in-kernel generator.   */
+int mst_philox_normal(float* out, int32_t batch, int64_t per_sample, uint64_t seed,
+                      uint64_t sample_offset, int32_t t, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Kernel-level test hooks (used by tests/ and bench.py roofline legs only).
+ * ------------------------------------------------------------------------ */
+/* C[M,N] (fp32) = A[M,K](bf16) * W[N,K](bf16)^T + bias[N], tcgen05 path.    */
+int mst_test_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, float* c,
+                       int32_t m, int32_t n, int32_t k, void* stream);
+/* softmax(QK^T/sqrt(dh))V for qkv [n_seqs*S, 3d] bf16 -> out [n_seqs*S, d] bf16 */
+int mst_test_attention_bf16(mst_engine_t e, const void* qkv_bf16, void* out_bf16, int32_t n_seqs,
+                            int32_t seq_len, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MST_H_ */
