@@ -25,7 +25,7 @@ MASK_NONE, MASK_FULL, MASK_FT, MASK_F = 0, 1, 2, 3
 
 # every symbol include/mst.h declares
 EXPORTED = [
-    "mst_version", "mst_last_error", "mst_device_info", "mst_abi_sizes", "mst_engine_create", "mst_engine_destroy",
+    "mst_version", "mst_last_error", "mst_launch_count", "mst_profile_begin", "mst_profile_end", "mst_device_info", "mst_abi_sizes", "mst_engine_create", "mst_engine_destroy",
     "mst_engine_packed_weight_bytes", "mst_engine_load_weights", "mst_engine_workspace_bytes", "mst_time_embed",
     "mst_text_embed", "mst_denoiser_forward", "mst_update_step", "mst_q_sample", "mst_cfg_combine",
     "mst_philox_normal", "mst_test_gemm_bf16", "mst_test_attention_bf16",
@@ -110,8 +110,12 @@ def _declare(lib):
     vp, i32, i64, u64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_size_t
     lib.mst_version.restype = C.c_char_p
     lib.mst_last_error.restype = C.c_char_p
+    lib.mst_launch_count.restype = C.c_uint64
+    lib.mst_launch_count.argtypes = []
     sigs = {
         "mst_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "mst_profile_begin": [vp],
+        "mst_profile_end": [C.POINTER(C.c_float), C.c_char_p, i32, sz, C.POINTER(i32)],
         "mst_abi_sizes": [C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)],
         "mst_engine_create": [C.POINTER(ModelDesc), C.POINTER(vp)],
         "mst_engine_destroy": [vp],

@@ -7,7 +7,11 @@
 #include "simt.cuh"
 #include "tc.cuh"
 
+#include <string.h>
+
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace mst {
 
@@ -16,6 +20,28 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
+}
+
+// ---- launch accounting / per-launch timing -----------------------------------
+static std::atomic<uint64_t> g_launches{0};
+struct Profile {
+  bool open = false;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> ev;  // ev[0] = begin, ev[i+1] = after launch i
+  std::vector<const char*> names;
+};
+static thread_local Profile g_prof;
+
+void note_launch(const char* name, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_prof.open && s == g_prof.stream) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, s);
+      g_prof.ev.push_back(e);
+      g_prof.names.push_back(name);
+    }
+  }
 }
 
 int sm_count() {
@@ -110,6 +136,54 @@ using namespace mst;
 extern "C" const char* mst_version(void) { return "mst-b200 0.1 (sm_100a)"; }
 extern "C" const char* mst_last_error(void) { return g_last_error.c_str(); }
 
+extern "C" uint64_t mst_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int mst_profile_begin(void* stream) {
+  MST_CHECK_ARG(!g_prof.open, "a profile is already open on this thread");
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  MST_CUDA_OK(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
+  MST_CHECK_ARG(cs == cudaStreamCaptureStatusNone, "cannot profile inside CUDA-graph capture");
+  g_prof.stream = (cudaStream_t)stream;
+  g_prof.ev.clear();
+  g_prof.names.clear();
+  cudaEvent_t e;
+  MST_CUDA_OK(cudaEventCreate(&e));
+  MST_CUDA_OK(cudaEventRecord(e, g_prof.stream));
+  g_prof.ev.push_back(e);
+  g_prof.open = true;
+  return MST_OK;
+}
+
+extern "C" int mst_profile_end(float* ms, char* names, int32_t cap, size_t names_cap, int32_t* n_out) {
+  MST_CHECK_ARG(g_prof.open, "no profile is open on this thread");
+  MST_CHECK_ARG(n_out != nullptr, "null n_out");
+  g_prof.open = false;
+  const int n = (int)g_prof.names.size();
+  cudaError_t err = cudaEventSynchronize(g_prof.ev.back());
+  size_t off = 0;
+  if (names && names_cap) names[0] = 0;
+  for (int i = 0; i < n && err == cudaSuccess; ++i) {
+    float t = 0.0f;
+    err = cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
+    if (ms && i < cap) ms[i] = t;
+    if (names && i < cap) {
+      size_t len = strlen(g_prof.names[i]);
+      if (off + len + 2 <= names_cap) {
+        memcpy(names + off, g_prof.names[i], len);
+        names[off + len] = '\n';
+        names[off + len + 1] = 0;
+        off += len + 1;
+      }
+    }
+  }
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  g_prof.names.clear();
+  *n_out = n;
+  if (err != cudaSuccess) return fail(MST_ERR_CUDA, std::string("mst_profile_end: ") + cudaGetErrorString(err));
+  return MST_OK;
+}
+
 extern "C" int mst_device_info(int* sm, int* cc_major, int* cc_minor) {
   int dev = 0;
   MST_CUDA_OK(cudaGetDevice(&dev));
@@ -193,7 +267,7 @@ extern "C" int mst_engine_load_weights(mst_engine_t h, const mst_weights* w, voi
     if ((rc = pack_bf16(w->out_w, out_w, d.n_feats, d.d_model, e->f_pad, d.d_model, s))) return rc;
     auto* out_b = c.take<float>(e->f_pad);
     pad_copy_f32_kernel<<<ceil_div(e->f_pad, 128), 128, 0, s>>>(w->out_b, out_b, d.n_feats, e->f_pad);
-    MST_LAUNCH_OK();
+    MST_LAUNCHED("pad_copy", s);
     e->in_w_bf = in_w; e->out_w_bf = out_w; e->out_b_pad = out_b;
     for (int l = 0; l < d.n_layers; ++l) {
       const mst_layer_weights& L = w->layers[l];

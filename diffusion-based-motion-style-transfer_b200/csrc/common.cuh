@@ -26,11 +26,16 @@ int fail(int code, const std::string& msg);
       return ::mst::fail(MST_ERR_CUDA, std::string(__func__) + ": " #expr ": " + cudaGetErrorString(_e)); \
   } while (0)
 
-#define MST_LAUNCH_OK()                                                       \
+// after every kernel launch: surface launch errors, count the launch, and (when a
+// profile is open on this thread, mst_profile_begin) record a CUDA event after it.
+void note_launch(const char* name, cudaStream_t s);
+
+#define MST_LAUNCHED(name, stream)                                            \
   do {                                                                        \
     cudaError_t _e = cudaGetLastError();                                      \
     if (_e != cudaSuccess)                                                    \
-      return ::mst::fail(MST_ERR_CUDA, std::string(__func__) + ": launch: " + cudaGetErrorString(_e)); \
+      return ::mst::fail(MST_ERR_CUDA, std::string(__func__) + ": launch of " + (name) + ": " + cudaGetErrorString(_e)); \
+    ::mst::note_launch((name), (stream));                                     \
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32Params p) {
 int gemm_f32(const GemmF32Params& p, cudaStream_t s) {
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
   gemm_f32_kernel<<<grid, 256, 0, s>>>(p);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("gemm_f32", s);
   return MST_OK;
 }
 
@@ -141,7 +141,7 @@ __global__ void token0_kernel(Token0Params p) {
 
 int token0(const Token0Params& p, int n_seqs, cudaStream_t s) {
   token0_kernel<<<n_seqs, 128, 0, s>>>(p);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("token0", s);
   return MST_OK;
 }
 
@@ -176,7 +176,7 @@ int layernorm_f32(const float* x, const float* g, const float* b, float* y, int 
   if (d % 32 != 0 || d > 1024) return fail(MST_ERR_UNSUPPORTED, "layernorm_f32: d must be a multiple of 32 and <= 1024");
   int warps_per_block = 8;
   layernorm_f32_kernel<<<ceil_div(M, warps_per_block), warps_per_block * 32, 0, s>>>(x, g, b, y, M, d);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("layernorm_f32", s);
   return MST_OK;
 }
 
@@ -257,7 +257,7 @@ int attention_f32(const float* qkv, float* out, int n_seqs, int S, int d, int n_
   }
   dim3 grid(ceil_div(S, ATT_QROWS), n_heads, n_seqs);
   attention_f32_kernel<<<grid, 128, smem, s>>>(qkv, out, S, d, dh, 1.0f / sqrtf((float)dh));
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("attention_f32", s);
   return MST_OK;
 }
 

@@ -204,7 +204,7 @@ int tc_attention(const TcAttnParams& p, cudaStream_t s) {
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)ATT_DH);
   dim3 grid(p.n_heads, p.n_seqs);
   tc_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tkv, p.out, p.S, s_pad, p.d_model, scale_log2e);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("tc_attention", s);
   return MST_OK;
 }
 

@@ -406,7 +406,9 @@ static int launch_gemm(const TcGemmParams& p, cudaStream_t s) {
   const int tiles = ceil_div(p.M, BLOCK_M) * ((p.N / BN) / npt);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   tc_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, p);
-  MST_LAUNCH_OK();
+  static const char* const kNames[] = {"tc_gemm_qkv", "tc_gemm_ffn1_gelu", "tc_gemm_res_ln", "tc_gemm_inproj",
+                                       "tc_gemm_outproj", "tc_gemm_f32"};
+  MST_LAUNCHED(kNames[EPI], s);
   return MST_OK;
 }
 
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(256) motion_to_tokens_kernel(const float* __re
 int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T, int f_pad, cudaStream_t s) {
   dim3 grid(ceil_div(T, 32), ceil_div(f_pad, 32), B);
   motion_to_tokens_kernel<<<grid, 256, 0, s>>>(x, a, F, T, f_pad);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("motion_to_tokens", s);
   return MST_OK;
 }
 
@@ -480,7 +482,7 @@ int pack_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, int rows
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
   pack_bf16_kernel<<<blocks, 256, 0, s>>>(src, dst, rows, cols, rows_pad, cols_pad);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("pack_bf16", s);
   return MST_OK;
 }
 

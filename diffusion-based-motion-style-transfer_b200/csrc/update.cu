@@ -203,7 +203,7 @@ static int launch_update(const mst_update_args& a, cudaStream_t s) {
     update_kernel<SAMPLER, NOISE, true><<<(unsigned)blocks, threads, 0, s>>>(a);
   else
     update_kernel<SAMPLER, NOISE, false><<<(unsigned)blocks, threads, 0, s>>>(a);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("update", s);
   return MST_OK;
 }
 
@@ -306,7 +306,7 @@ extern "C" int mst_q_sample(const float* x_start, const float* noise, int32_t ma
   int64_t total = (int64_t)batch * n_feats * n_frames;
   q_sample_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x_start, noise, mask_kind, mask, t_vec, t_imm,
                                                                      sqrt_ab, sqrt_1m_ab, x_t, batch, n_feats, n_frames);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("q_sample", (cudaStream_t)stream);
   return MST_OK;
 }
 
@@ -316,7 +316,7 @@ extern "C" int mst_cfg_combine(const float* out_cond, const float* out_uncond, c
   MST_CHECK_ARG(batch > 0 && per_sample > 0, "empty shape");
   cfg_combine_kernel<<<grid_for((int64_t)batch * per_sample), 256, 0, (cudaStream_t)stream>>>(out_cond, out_uncond, scale,
                                                                                             out, batch, per_sample);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("cfg_combine", (cudaStream_t)stream);
   return MST_OK;
 }
 
@@ -325,6 +325,6 @@ extern "C" int mst_philox_normal(float* out, int32_t batch, int64_t per_sample, 
   MST_CHECK_ARG(out != nullptr && batch > 0 && per_sample > 0, "bad arguments");
   philox_normal_kernel<<<grid_for((int64_t)batch * ((per_sample + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(
       out, batch, per_sample, seed, sample_offset, t);
-  MST_LAUNCH_OK();
+  MST_LAUNCHED("philox_normal", (cudaStream_t)stream);
   return MST_OK;
 }

@@ -157,6 +157,7 @@ class GaussianDiffusion:
         self.steps_per_graph = int(os.environ.get("MST_STEPS_PER_GRAPH", "1"))
         self._dev = {}
         self._graphs = {}
+        self.last_plan_launches = 0        # kernels per denoise step of the most recent fused trajectory
 
     # ------------------------------------------------------------------ tables
     def _variance_tables(self):
@@ -459,7 +460,7 @@ class GaussianDiffusion:
             final = sample
         if dump is not None:
             return dump
-        return final["sample"]
+        return final["sample"].clone() if final.get("_live") else final["sample"]
 
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                                   model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
@@ -492,7 +493,7 @@ class GaussianDiffusion:
             final = sample
         if dump_all_xstart:
             return dump
-        return final["sample"]
+        return final["sample"].clone() if final.get("_live") else final["sample"]
 
     def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                                      model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0,
@@ -561,95 +562,163 @@ class GaussianDiffusion:
     # ------------------------------------------------------------------ fused native trajectory
     def _fused_trajectory(self, sampler, native, cfgw, img, indices, clip_denoised, model_kwargs, const_noise, eta,
                           progress, want_xstart, own_buffers):
-        """Whole trajectory on the hand-written path: per step = one denoiser forward
-        (cond+uncond batched) + one fused update kernel, replayed as a CUDA graph with the
-        timestep living in device memory."""
+        """Whole trajectory on the hand-written path: per step = one denoiser forward (cond+uncond batched)
+        + one fused update kernel, replayed as a CUDA graph with the timestep living in device memory.
+
+        The static buffers and the captured graph form a *plan* that is cached on this diffusion object per
+        (sampler, shape, conditioning layout, precision ...): a second trajectory of the same kind only copies
+        its inputs into the plan's buffers and replays."""
         device = img.device
         y = model_kwargs['y']
         B, T = img.shape[0], img.shape[-1]
         eng = native.mst_engine(device)
         use_cfg = cfgw is not None
         with th.no_grad():
-            x = _f32c(img).clone()
-            mask, inp = self._check_inpainting(model_kwargs, x.shape)
+            mask, inp = self._check_inpainting(model_kwargs, img.shape)
             nmask = self._inpainting_mask_for_noise(model_kwargs)
             kmask = mask if mask is not None else (_f32c(nmask) if nmask is not None else None)
             kmask = native.compact_mask(kmask)
-            # hoisted out of the loop: CLIP/text embedding (the reference re-encodes every step,
-            # mdm_forstyledataset.py:326) and the time-embedding MLP for every step of this trajectory
             uncond_all = bool(y.get('uncond', False)) and not use_cfg
+            # hoisted out of the loop: CLIP/text embedding (the reference re-encodes every step,
+            # mdm_forstyledataset.py:326)
             text_emb = None if uncond_all else native.text_embedding(y, device)
-            t_model = th.tensor([self._model_time_index(i) for i in range(self.num_timesteps)], device=device,
-                                dtype=th.long)
-            temb = eng.time_embed(t_model)                       # row t = time embedding of process index t
-            scale = _f32c(y['scale'].to(device)).view(-1) if use_cfg else None
-            tabs = self.device_tables(device, eta)
+            use_philox = self.rng == "philox" and self.noise_fn is None
+            use_graph = self.use_cuda_graph and self.noise_fn is None
             n_steps = len(indices)
             assert all(indices[k] - 1 == indices[k + 1] for k in range(n_steps - 1))
-            # device-resident step state: the process index t (the update kernel decrements it)
-            t_dev = th.tensor([indices[0]], device=device, dtype=th.int32)
-            counter = th.zeros(1, device=device, dtype=th.int32)
-            out_c = th.empty_like(x)
-            out_u = th.empty_like(x) if use_cfg else None
-            x0 = th.empty_like(x) if want_xstart or not own_buffers else None
-            use_philox = self.rng == "philox" and self.noise_fn is None
-            eps = None if use_philox else th.empty_like(x)
-            if sampler == L.SAMPLER_DDPM:
-                coefs = dict(coef1=tabs["c1"], coef2=tabs["c2"], sigma=tabs["sigma"])
-            else:
-                coefs = dict(coef1=tabs["ddim_c1"], coef2=tabs["ddim_c2"], sigma=tabs["ddim_sigma"],
-                             recip=tabs["recip"], recipm1=tabs["recipm1"])
-
-            def one_step(draw_noise=True):
-                eng.forward(x, temb, text_emb, cfg=use_cfg, uncond=uncond_all, out_cond=out_c, out_uncond=out_u,
-                            temb_row_dev=t_dev)
-                if eps is not None and draw_noise:
-                    eps.normal_()
-                    if const_noise:
-                        eps.copy_(eps[[0]].expand_as(eps).clone())
-                K.update_step(sampler=sampler, out_cond=out_c, out_uncond=out_u, cfg_scale=scale, x_t=x, x_prev=x,
-                              pred_xstart=x0, mask=kmask, x_inpaint=inp, mask_noise=nmask is not None,
-                              clip_denoised=clip_denoised, t_scalar_dev=t_dev, advance_t=True, block_counter=counter,
-                              noise_kind=L.NOISE_PHILOX if use_philox else L.NOISE_TENSOR, noise=eps,
-                              const_noise=const_noise and use_philox, philox_seed=self.philox_seed,
-                              philox_sample_offset=self.philox_sample_offset, **coefs)
-
-            graph = None
-            if self.use_cuda_graph and self.noise_fn is None:
-                # warm-up on a side stream (allocations, lazy module load), then capture one step
-                snap = (x.clone(), t_dev.clone())
-                rng_state = th.cuda.get_rng_state(device)
-                s = th.cuda.Stream(device=device)
-                s.wait_stream(th.cuda.current_stream(device))
-                with th.cuda.stream(s):
-                    one_step()
-                th.cuda.current_stream(device).wait_stream(s)
-                th.cuda.synchronize(device)
-                x.copy_(snap[0]); t_dev.copy_(snap[1]); counter.zero_()
-                th.cuda.set_rng_state(rng_state, device)
-                graph = th.cuda.CUDAGraph()
-                with th.cuda.graph(graph):
-                    one_step()
-                # capture does not execute: state is still the snapshot
+            key = (sampler, str(device), tuple(img.shape), id(eng), use_cfg, uncond_all, text_emb is not None,
+                   None if kmask is None else tuple(kmask.shape), inp is not None, nmask is not None,
+                   bool(clip_denoised), use_philox, bool(const_noise), bool(want_xstart or not own_buffers),
+                   float(eta), use_graph)
+            plan = self._graphs.get(key)
+            if plan is None:
+                plan = _TrajectoryPlan(self, sampler, eng, device, tuple(img.shape), use_cfg, uncond_all, text_emb,
+                                       kmask, inp, nmask is not None, clip_denoised, use_philox, const_noise,
+                                       want_xstart or not own_buffers, eta, use_graph)
+                if len(self._graphs) >= 16:  # bound the cache: plans own state-sized buffers
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = plan
+            scale = _f32c(y['scale'].to(device)).view(-1) if use_cfg else None
+            t_model = th.tensor([self._model_time_index(i) for i in range(self.num_timesteps)], device=device,
+                                dtype=th.long)
+            plan.load(img, text_emb, scale, kmask, inp, eng.time_embed(t_model), indices[0],
+                      self.philox_seed, self.philox_sample_offset)
+            self.last_plan_launches = plan.launches_per_step
 
             it = range(n_steps)
             if progress:
                 from tqdm.auto import tqdm
                 it = tqdm(it)
             for k in it:
-                if graph is not None:
-                    graph.replay()
-                else:
-                    if self.noise_fn is not None:
-                        e = _f32c(self.noise_fn(k, tuple(x.shape), device))
-                        if const_noise:
-                            e = e[[0]].repeat(B, 1, 1, 1)
-                        eps.copy_(e)
-                        one_step(draw_noise=False)
-                    else:
-                        one_step()
+                if self.noise_fn is not None:
+                    e = _f32c(self.noise_fn(k, tuple(img.shape), device))
+                    if const_noise:
+                        e = e[[0]].repeat(B, 1, 1, 1)
+                    plan.eps.copy_(e)
+                plan.step()
                 if own_buffers:
-                    # the caller only wants the last sample: hand out the live buffers
-                    yield {"sample": x, "pred_xstart": x0}
+                    # the caller (p_sample_loop / ddim_sample_loop) only keeps the last dict and clones it
+                    yield {"sample": plan.x, "pred_xstart": plan.x0, "_live": True}
                 else:
-                    yield {"sample": x.clone(), "pred_xstart": x0.clone()}
+                    yield {"sample": plan.x.clone(), "pred_xstart": plan.x0.clone()}
+
+
+class _TrajectoryPlan:
+    """Static device buffers + the captured one-step CUDA graph of a fused trajectory."""
+
+    def __init__(self, diffusion, sampler, eng, device, shape, use_cfg, uncond_all, text_emb, kmask, inp, mask_noise,
+                 clip_denoised, use_philox, const_noise, want_xstart, eta, use_graph):
+        self.eng, self.device, self.shape = eng, device, shape
+        B, T = shape[0], shape[-1]
+        f32 = dict(dtype=th.float32, device=device)
+        self.x = th.empty(shape, **f32)
+        self.out_c = th.empty(shape, **f32)
+        self.out_u = th.empty(shape, **f32) if use_cfg else None
+        self.x0 = th.empty(shape, **f32) if want_xstart else None
+        self.eps = None if use_philox else th.empty(shape, **f32)
+        self.text_emb = th.empty_like(text_emb) if text_emb is not None else None
+        self.scale = th.empty(B, **f32) if use_cfg else None
+        self.mask = th.empty_like(kmask) if kmask is not None else None
+        self.inp = th.empty(shape, **f32) if inp is not None else None
+        self.temb = th.empty(diffusion.num_timesteps, eng.d_model, **f32)
+        self.t_dev = th.zeros(1, dtype=th.int32, device=device)
+        self.counter = th.zeros(1, dtype=th.int32, device=device)
+        self.ws = th.empty(eng.workspace_bytes(B * (2 if use_cfg else 1), T), dtype=th.uint8, device=device)
+        self.seed = th.zeros(2, dtype=th.int64, device=device)  # reserved: philox seed/offset are launch arguments
+        tabs = diffusion.device_tables(device, eta)
+        if sampler == L.SAMPLER_DDPM:
+            coefs = dict(coef1=tabs["c1"], coef2=tabs["c2"], sigma=tabs["sigma"])
+        else:
+            coefs = dict(coef1=tabs["ddim_c1"], coef2=tabs["ddim_c2"], sigma=tabs["ddim_sigma"],
+                         recip=tabs["recip"], recipm1=tabs["recipm1"])
+        self._args = dict(sampler=sampler, use_cfg=use_cfg, uncond_all=uncond_all, mask_noise=mask_noise,
+                          clip_denoised=clip_denoised, use_philox=use_philox, const_noise=const_noise, coefs=coefs)
+        self.use_graph = use_graph
+        self.graph = None
+        self.graph_key = None
+        self.launches_per_step = 0
+        self.draw_noise = self.eps is not None and diffusion.noise_fn is None
+
+    def _one_step(self, seed, offset):
+        a = self._args
+        self.eng.forward(self.x, self.temb, self.text_emb, cfg=a["use_cfg"], uncond=a["uncond_all"], out_cond=self.out_c,
+                         out_uncond=self.out_u, temb_row_dev=self.t_dev, workspace=self.ws)
+        if self.draw_noise:
+            self.eps.normal_()
+            if a["const_noise"]:
+                self.eps.copy_(self.eps[[0]].expand_as(self.eps).clone())
+        K.update_step(sampler=a["sampler"], out_cond=self.out_c, out_uncond=self.out_u, cfg_scale=self.scale,
+                      x_t=self.x, x_prev=self.x, pred_xstart=self.x0, mask=self.mask, x_inpaint=self.inp,
+                      mask_noise=a["mask_noise"], clip_denoised=a["clip_denoised"], t_scalar_dev=self.t_dev,
+                      advance_t=True, block_counter=self.counter,
+                      noise_kind=L.NOISE_PHILOX if a["use_philox"] else L.NOISE_TENSOR, noise=self.eps,
+                      const_noise=a["const_noise"] and a["use_philox"], philox_seed=seed, philox_sample_offset=offset,
+                      **a["coefs"])
+
+    def load(self, img, text_emb, scale, kmask, inp, temb, t_start, seed, offset):
+        """Copy this trajectory's inputs into the static buffers; (re)capture the step graph when needed."""
+        self.x.copy_(_f32c(img))
+        if self.text_emb is not None:
+            self.text_emb.copy_(text_emb)
+        if self.scale is not None:
+            self.scale.copy_(scale)
+        if self.mask is not None:
+            self.mask.copy_(kmask)
+        if self.inp is not None:
+            self.inp.copy_(inp)
+        self.temb.copy_(temb)
+        self.seed_off = (int(seed), int(offset))
+        if self.use_graph and (self.graph is None or self.graph_key != self.seed_off):
+            self._capture()
+        self.t_dev.fill_(int(t_start))
+        self.counter.zero_()
+
+    def _capture(self):
+        device = self.device
+        snap = self.x.clone()
+        self.t_dev.fill_(1)
+        self.counter.zero_()
+        rng_state = th.cuda.get_rng_state(device)
+        s = th.cuda.Stream(device=device)
+        s.wait_stream(th.cuda.current_stream(device))
+        with th.cuda.stream(s):  # warm-up outside capture: lazy module loads, allocator
+            self._one_step(*self.seed_off)
+        th.cuda.current_stream(device).wait_stream(s)
+        th.cuda.synchronize(device)
+        th.cuda.set_rng_state(rng_state, device)
+        n0 = K.launch_count()
+        graph = th.cuda.CUDAGraph()
+        with th.cuda.graph(graph):
+            self._one_step(*self.seed_off)
+        self.launches_per_step = K.launch_count() - n0
+        self.graph, self.graph_key = graph, self.seed_off
+        self.x.copy_(snap)
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+            K.count_graph_replay()
+        else:
+            n0 = K.launch_count()
+            self._one_step(*self.seed_off)
+            self.launches_per_step = K.launch_count() - n0

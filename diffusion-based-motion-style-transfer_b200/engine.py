@@ -105,7 +105,13 @@ class Engine:
         self._keep = keep
 
     # -- scratch -----------------------------------------------------------------
+    def workspace_bytes(self, n_seqs: int, n_frames: int) -> int:
+        nbytes = C.c_size_t()
+        L.check(self.lib.mst_engine_workspace_bytes(self._h, n_seqs, n_frames, C.byref(nbytes)))
+        return int(nbytes.value)
+
     def workspace(self, n_seqs: int, n_frames: int) -> torch.Tensor:
+        """Engine-owned scratch for eager calls (grown on demand; captured graphs bring their own)."""
         nbytes = C.c_size_t()
         L.check(self.lib.mst_engine_workspace_bytes(self._h, n_seqs, n_frames, C.byref(nbytes)))
         if self._ws is None or self._ws.numel() < nbytes.value:
@@ -135,7 +141,7 @@ class Engine:
     def forward(self, x: torch.Tensor, temb: torch.Tensor, text_emb: Optional[torch.Tensor], *, cfg: bool = False,
                 uncond: bool = False, out_cond: Optional[torch.Tensor] = None,
                 out_uncond: Optional[torch.Tensor] = None, temb_row_dev: Optional[torch.Tensor] = None,
-                temb_row_offset: int = 0):
+                temb_row_offset: int = 0, workspace: Optional[torch.Tensor] = None):
         """x [B,F,1,T] fp32 -> model output(s) [B,F,1,T].  With cfg=True both the
         conditional and the unconditional pass run batched and two tensors return."""
         B, T = x.shape[0], x.shape[-1]
@@ -145,7 +151,7 @@ class Engine:
             out_cond = torch.empty_like(x)
         if cfg and out_uncond is None:
             out_uncond = torch.empty_like(x)
-        ws = self.workspace(B * (2 if cfg else 1), T)
+        ws = workspace if workspace is not None else self.workspace(B * (2 if cfg else 1), T)
         a = L.ForwardArgs()
         a.batch, a.n_frames, a.cfg, a.uncond = B, T, int(cfg), int(uncond)
         a.x = _ptr(x, name="x")
@@ -240,3 +246,46 @@ def philox_normal(shape, seed: int, sample_offset: int, t: int, device) -> torch
     L.check(lib.mst_philox_normal(out.data_ptr(), B, out.numel() // B, int(seed) & (2**64 - 1), int(sample_offset), int(t),
                                   _stream_ptr()), "mst_philox_normal")
     return out
+
+
+# ---------------------------------------------------------------------------------
+# launch accounting / per-launch timing (mst_launch_count, mst_profile_begin/end)
+# ---------------------------------------------------------------------------------
+_graph_replays = 0
+
+
+def count_graph_replay(n: int = 1):
+    global _graph_replays
+    _graph_replays += n
+
+
+def graph_replays() -> int:
+    """CUDA-graph replays of captured denoise steps issued by this process (each re-launches
+    ``diffusion.last_plan_launches`` kernels without passing through the host library)."""
+    return _graph_replays
+
+
+def launch_count() -> int:
+    """Kernels launched by libmst_b200.so in this process so far (graph replays excluded, see mst.h)."""
+    return int(L.load().mst_launch_count())
+
+
+class profile:
+    """``with profile() as p: ...`` -> ``p.records`` = [(kernel name, ms)] for every launch the block made
+    through the library on the current stream (CUDA events between launches; synchronises on exit)."""
+
+    def __init__(self, cap: int = 4096):
+        self.cap, self.records = cap, []
+
+    def __enter__(self):
+        L.check(L.load().mst_profile_begin(_stream_ptr()), "mst_profile_begin")
+        return self
+
+    def __exit__(self, *exc):
+        ms = (C.c_float * self.cap)()
+        names = C.create_string_buffer(self.cap * 32)
+        n = C.c_int32()
+        L.check(L.load().mst_profile_end(ms, names, self.cap, len(names), C.byref(n)), "mst_profile_end")
+        nm = names.value.decode().split("\n")[:-1]
+        self.records = [(nm[i] if i < len(nm) else "?", float(ms[i])) for i in range(min(n.value, self.cap))]
+        return False

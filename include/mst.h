@@ -66,6 +66,21 @@ const char* mst_last_error(void);
 /* Number of SMs / compute capability of the current device (diagnostics). */
 int mst_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Number of kernels this library has launched in this process (all threads,
+ * all streams).  Launches recorded into a CUDA graph are counted once, at
+ * capture; a replay re-issues them without passing through the host library,
+ * so callers multiply the captured count by their replays (bench.py does). */
+uint64_t mst_launch_count(void);
+
+/* Per-launch device timing of everything this thread launches through the
+ * library on `stream` between begin and end: a CUDA event is recorded after
+ * every kernel launch.  mst_profile_end synchronises, writes the duration of
+ * launch i to ms[i] (i < cap) and the '\n'-separated kernel names to `names`,
+ * and returns the number of launches in *n.  Not legal during graph capture.
+ * This is the live source of bench.py's roofline numbers.                   */
+int mst_profile_begin(void* stream);
+int mst_profile_end(float* ms, char* names, int32_t cap, size_t names_cap, int32_t* n);
+
 /* sizeof() of the argument structs as this library was compiled - lets a
  * foreign-language binding verify its own struct layout (no GPU needed).   */
 int mst_abi_sizes(size_t* model_desc, size_t* weights, size_t* forward_args, size_t* update_args);
