@@ -9,7 +9,7 @@ if [ "${1:-}" != "noncu" ]; then
 timeout 300 python tools/profile_step.py > gpurun_out/profile_step.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 135 -c 90 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 27 -c 6 -o gpurun_out/prof_gemm python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 35 -c 4 -o gpurun_out/prof_gemm python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 fi
 cat gpurun_out/profile_step.log
