@@ -459,6 +459,21 @@ extern "C" int mst_test_gemm_bf16(const void* a_bf16, const void* w_bf16, const 
   return tc_gemm(p, (cudaStream_t)stream);
 }
 
+extern "C" int mst_test_gemm_epi_bf16(int32_t epi, const void* a_bf16, const void* w_bf16, const float* bias,
+                                      const void* residual_bf16, const float* ln_g, const float* ln_b, void* out_bf16,
+                                      int32_t m, int32_t n, int32_t k, void* stream) {
+  MST_CHECK_ARG(a_bf16 && w_bf16 && bias && out_bf16, "null pointer");
+  MST_CHECK_ARG(epi >= 0 && epi <= 2, "epi must be 0 (bias), 1 (gelu) or 2 (residual + layernorm)");
+  TcGemmParams p;
+  p.a = static_cast<const __nv_bfloat16*>(a_bf16);
+  p.w = static_cast<const __nv_bfloat16*>(w_bf16);
+  p.bias = bias; p.out = out_bf16; p.ldo = n; p.M = m; p.N = n; p.K = k;
+  p.epi = epi == 0 ? TC_EPI_BIAS_BF16 : (epi == 1 ? TC_EPI_BIAS_GELU_BF16 : TC_EPI_BIAS_RES_LN);
+  p.residual = static_cast<const __nv_bfloat16*>(residual_bf16);
+  p.ln_g = ln_g; p.ln_b = ln_b;
+  return tc_gemm(p, (cudaStream_t)stream);
+}
+
 extern "C" int mst_test_attention_bf16(mst_engine_t h, const void* qkv_bf16, void* out_bf16, int32_t n_seqs,
                                        int32_t seq_len, void* workspace, size_t workspace_bytes, void* stream) {
   MST_CHECK_ARG(h && qkv_bf16 && out_bf16, "null pointer");

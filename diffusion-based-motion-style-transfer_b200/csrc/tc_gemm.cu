@@ -1,12 +1,23 @@
-// Persistent, warp-specialised tcgen05 GEMM for the denoiser's dense layers
+// Persistent, warp-specialised tcgen05 GEMMs for the denoiser's dense layers
 // (MST_PREC_BF16):   D[M,N] = A[M,K] * W[N,K]^T  with fused epilogues.
 //
-//   A, W : bf16, K-major (row-major [rows, K]); TMA 128B-swizzled 128x64 / BNx64 tiles
-//   D    : fp32 accumulators in TMEM, 2 stages of BN columns (epilogue of tile i
-//          overlaps the MMAs of tile i+1)
+//   A, W : bf16, K-major (row-major [rows, K]); TMA 128B-swizzled 128x64 / 256x64 tiles, 3-4 stage ring
+//   D    : fp32 accumulators in TMEM, 2 stages of 256 columns (the epilogue of tile i overlaps the
+//          MMAs of tile i+1)
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2..9  : epilogue, 8 warps; warp w may touch TMEM lanes 32*(w%4)..+31
+//   warps 2..9  : epilogue, 8 warps; warp w owns TMEM lanes 32*(w%4)..+31 (one output row per thread),
+//                 warps 2-5 the low column half of the tile, warps 6-9 the high half
+//
+// Two kernels:
+//   tc_gemm_kernel<BN,EPI>   one CTA per 128 x BN tile.  bf16 outputs are staged through shared memory in
+//                            the TMA swizzle layout and written with cp.async.bulk.tensor stores (coalesced
+//                            and asynchronous: a row-per-thread direct store was the bottleneck,
+//                            profiles/r01a_*); the two small fp32 / row-remapping epilogues store directly.
+//   tc_gemm_ln_kernel        out = LayerNorm(A W^T + bias + residual) for N = 512: a 2-CTA cluster owns a
+//                            128-row block, each CTA 256 of the 512 columns, so every CTA has two
+//                            accumulator stages and the MMAs never wait for the normalisation; the row
+//                            statistics cross the CTA pair through distributed shared memory.
 //
 // Layers served (reference model/mdm_forstyledataset.py):
 //   InputProcess.poseEmbedding (:440) + positional add (:403)       TC_EPI_INPROJ
@@ -32,22 +43,38 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + NUM_EPI_THREADS;  // 320
 constexpr int LN_N = 512;                           // row width the LN epilogue is built for
+constexpr int CHUNK_BYTES = BLOCK_M * 128;          // one staged [128 rows x 64 bf16] box
 
-template <int BN>
+__host__ __device__ constexpr bool epi_is_staged(int epi) { return epi == TC_EPI_BIAS_BF16 || epi == TC_EPI_BIAS_GELU_BF16; }
+
+template <int BN, bool STAGED>
 struct GemmCfg {
-  static constexpr int STAGES = BN >= 256 ? 4 : 6;
+  static constexpr int STAGES = STAGED ? 3 : (BN >= 256 ? 4 : 6);
   static constexpr int A_BYTES = BLOCK_M * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_BYTES = STAGED ? (BN / 64) * CHUNK_BYTES : 0;  // staged output tile
   static constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : (2 * BN >= 128 ? 128 : 64));
   static constexpr int BAR_BYTES = 256;
-  static constexpr int EXCH_BYTES = 2 * 2 * BLOCK_M * 8;  // [buf][group][row] float2
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + EXCH_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
 };
 
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// ---- epilogue of one 32-column chunk held by one thread (= one output row) ----
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding): branch-free,
+// 2 MUFU + 7 FMA-class instructions - the exact-erf GELU epilogue is ALU-bound otherwise.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x|/sqrt2)
+  return 0.5f * x + 0.5f * fabsf(x) * e;          // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+}
+
+// ---- direct (row-per-thread) epilogue of one 32-column chunk: the small fp32 / row-remapping cases ----
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, int n, const uint32_t (&v)[32]) {
   if (row >= p.M) return;
@@ -60,17 +87,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, i
     x[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
     x[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
   }
-  if constexpr (EPI == TC_EPI_BIAS_BF16 || EPI == TC_EPI_BIAS_GELU_BF16) {
-    if constexpr (EPI == TC_EPI_BIAS_GELU_BF16) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
-    }
-    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n);
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      dst[q] = make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
-                          pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
-  } else if constexpr (EPI == TC_EPI_INPROJ) {
+  if constexpr (EPI == TC_EPI_INPROJ) {
     const int b = row / p.T, t = row - b * p.T, S = p.T + 1;
     const float* pe = p.pe + (size_t)(t + 1) * p.N + n;
 #pragma unroll
@@ -103,29 +120,52 @@ __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, i
   }
 }
 
+// ---- producer / MMA roles shared by both kernels -----------------------------------------------------
+struct Ring {
+  uint32_t base, bar_base;
+  int stages, stage_bytes, a_bytes;
+  __device__ __forceinline__ uint32_t a(int st) const { return base + st * stage_bytes; }
+  __device__ __forceinline__ uint32_t b(int st) const { return base + st * stage_bytes + a_bytes; }
+  __device__ __forceinline__ uint32_t full(int st) const { return bar_base + 8 * st; }
+  __device__ __forceinline__ uint32_t empty(int st) const { return bar_base + 8 * (stages + st); }
+  __device__ __forceinline__ uint32_t tfull(int i) const { return bar_base + 8 * (2 * stages + i); }
+  __device__ __forceinline__ uint32_t tempty(int i) const { return bar_base + 8 * (2 * stages + 2 + i); }
+  __device__ __forceinline__ uint32_t extra(int i) const { return bar_base + 8 * (2 * stages + 4 + i); }
+};
+
+template <int BN>
+__device__ __forceinline__ void mma_tile(const Ring& r, uint32_t d_tmem, int k_blks, int& stage, uint32_t& phase) {
+  constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0);
+  for (int kb = 0; kb < k_blks; ++kb) {
+    mbar_wait(r.full(stage), phase);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+      const uint64_t adesc = make_smem_desc_sw128(r.a(stage) + k * (UMMA_K * 2), 0, 1024);
+      const uint64_t bdesc = make_smem_desc_sw128(r.b(stage) + k * (UMMA_K * 2), 0, 1024);
+      mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+    }
+    mma_commit(r.empty(stage));  // frees the smem slot once these MMAs have read it
+    if (++stage == r.stages) { stage = 0; phase ^= 1; }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const TcGemmParams p) {
-  using Cfg = GemmCfg<BN>;
-  constexpr bool IS_LN = (EPI == TC_EPI_BIAS_RES_LN);
-  constexpr int NPT = IS_LN ? 2 : 1;  // accumulator sub-tiles per scheduled tile
-  static_assert(!IS_LN || BN == 256, "LN epilogue is built for 2 x 256 columns");
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ CUtensorMap tmap_out, const TcGemmParams p) {
+  constexpr bool STAGED = epi_is_staged(EPI);
+  using Cfg = GemmCfg<BN, STAGED>;
+  static_assert(!STAGED || BN == 256, "staged epilogue is built for 256-column tiles");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
-  const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  auto a_smem = [&](int st) { return base + st * Cfg::STAGE_BYTES; };
-  auto b_smem = [&](int st) { return base + st * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
-  auto full_bar = [&](int st) { return bar_base + 8 * st; };
-  auto empty_bar = [&](int st) { return bar_base + 8 * (Cfg::STAGES + st); };
-  auto tfull_bar = [&](int i) { return bar_base + 8 * (2 * Cfg::STAGES + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8 * (2 * Cfg::STAGES + 2 + i); };
-  const uint32_t tmem_slot = bar_base + 8 * (2 * Cfg::STAGES + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
-  float2* exch = reinterpret_cast<float2*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+  const uint32_t out_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1024)
+  Ring ring{base, out_smem + Cfg::OUT_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
+  const uint32_t tmem_slot = ring.extra(0);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,13 +173,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && elect_one()) {
     prefetch_tensormap(&tmap_a);
     prefetch_tensormap(&tmap_w);
+    if (STAGED) prefetch_tensormap(&tmap_out);
     for (int st = 0; st < Cfg::STAGES; ++st) {
-      mbar_init(full_bar(st), 1);
-      mbar_init(empty_bar(st), 1);
+      mbar_init(ring.full(st), 1);
+      mbar_init(ring.empty(st), 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), IS_LN ? NUM_EPI_THREADS / 2 : NUM_EPI_THREADS);
+      mbar_init(ring.tfull(i), 1);
+      mbar_init(ring.tempty(i), NUM_EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -152,9 +193,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int n_groups = (p.N / BN) / NPT;
+  const int n_blks = p.N / BN;
   const int m_blks = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int num_tiles = m_blks * n_groups;
+  const int num_tiles = m_blks * n_blks;
   const int k_blks = p.K / BLOCK_K;
 
   if (warp == 0) {
@@ -163,63 +204,92 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_groups, g = tile - m_blk * n_groups;
-        for (int sub = 0; sub < NPT; ++sub) {
-          const int n_blk = g * NPT + sub;
-          for (int kb = 0; kb < k_blks; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-            tma_load_2d(a_smem(stage), &tmap_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
-            tma_load_2d(b_smem(stage), &tmap_w, full_bar(stage), kb * BLOCK_K, n_blk * BN);
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-          }
+        const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(ring.empty(stage), phase ^ 1);
+          mbar_expect_tx(ring.full(stage), Cfg::STAGE_BYTES);
+          tma_load_2d(ring.a(stage), &tmap_a, ring.full(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(ring.b(stage), &tmap_w, ring.full(stage), kb * BLOCK_K, n_blk * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int sub = 0; sub < NPT; ++sub) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-          for (int kb = 0; kb < k_blks; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t adesc = make_smem_desc_sw128(a_smem(stage) + k * (UMMA_K * 2), 0, 1024);
-              const uint64_t bdesc = make_smem_desc_sw128(b_smem(stage) + k * (UMMA_K * 2), 0, 1024);
-              mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-            mma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-          }
-          mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
-        }
+        mbar_wait(ring.tempty(acc), acc_phase ^ 1);
+        tc_fence_after();
+        mma_tile<BN>(ring, tmem_base + (uint32_t)(acc * BN), k_blks, stage, phase);
+        mma_commit(ring.tfull(acc));  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
     // -------------------------------- epilogue --------------------------------
     const int ew = warp - 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp is allowed to access
-    const int half = ew >> 2;   // column half (plain) / accumulator stage (LN)
+    const int half = ew >> 2;   // column half of the tile
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    if constexpr (!IS_LN) {
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_groups, n_blk = tile - m_blk * n_groups;
+    const bool store_thread = (ew & 3) == 0 && lane == 0;
+    int acc = 0, it = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
+      mbar_wait(ring.tfull(acc), acc_phase);
+      tc_fence_after();
+      if constexpr (STAGED) {
+        // the staged tile of the previous iteration must have been read out by its TMA stores
+        if (it > 0) {
+          if (store_thread) bulk_wait_read_all();
+          named_bar_sync(1 + half, NUM_EPI_THREADS / 2);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int chunk = half * 2 + cc;  // 64 columns [64*chunk, 64*chunk+64) of the tile
+          uint32_t v[2][32];
+          tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + chunk * 64), v[0]);
+          tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + chunk * 64 + 32), v[1]);
+          tmem_ld_wait();
+          if (cc == 1) {  // accumulator drained: the MMAs of the tile after next may overwrite it
+            tc_fence_before();
+            mbar_arrive(ring.tempty(acc));
+          }
+          const float* bias = p.bias + n_blk * BN + chunk * 64;
+          const uint32_t row_smem = out_smem + chunk * CHUNK_BYTES + row_in_tile * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // 8 columns -> one 16-byte piece of the swizzled row
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j + 4));
+            const uint32_t* s = &v[j >> 2][(j & 3) * 8];
+            float x0 = __uint_as_float(s[0]) + b0.x, x1 = __uint_as_float(s[1]) + b0.y;
+            float x2 = __uint_as_float(s[2]) + b0.z, x3 = __uint_as_float(s[3]) + b0.w;
+            float x4 = __uint_as_float(s[4]) + b1.x, x5 = __uint_as_float(s[5]) + b1.y;
+            float x6 = __uint_as_float(s[6]) + b1.z, x7 = __uint_as_float(s[7]) + b1.w;
+            if constexpr (EPI == TC_EPI_BIAS_GELU_BF16) {
+              x0 = gelu_fast(x0); x1 = gelu_fast(x1); x2 = gelu_fast(x2); x3 = gelu_fast(x3);
+              x4 = gelu_fast(x4); x5 = gelu_fast(x5); x6 = gelu_fast(x6); x7 = gelu_fast(x7);
+            }
+            sts128(row_smem + ((j ^ (row_in_tile & 7)) << 4),
+                   make_uint4(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3), pack_bf16x2(x4, x5), pack_bf16x2(x6, x7)));
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
+        named_bar_sync(1 + half, NUM_EPI_THREADS / 2);
+        if (store_thread) {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int chunk = half * 2 + cc;
+            tma_store_2d(&tmap_out, out_smem + chunk * CHUNK_BYTES, n_blk * BN + chunk * 64, m_blk * BLOCK_M);
+          }
+          bulk_commit_group();
+        }
+      } else {
         const int row = m_blk * BLOCK_M + row_in_tile;
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BN / 2; c += 32) {
           const int col = half * (BN / 2) + c;
@@ -229,89 +299,237 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           epilogue_chunk<EPI>(p, row, n_blk * BN + col, v);
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        mbar_arrive(ring.tempty(acc));
       }
-    } else {
-      // LN(acc + bias + residual): group `half` owns accumulator stage `half`
-      // (columns [256*half, 256*half+256) of the 512-wide row); row statistics are
-      // exchanged through shared memory between the two groups.
-      uint32_t tile_phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int row = tile * BLOCK_M + row_in_tile;  // n_groups == 1
-        const bool valid = row < p.M;
-        const int ncol0 = half * BN;
-        const uint32_t tcol = tmem_base + lane_addr + (uint32_t)(half * BN);
-        mbar_wait(tfull_bar(half), tile_phase);
-        tc_fence_after();
-        float sum = 0.0f, sq = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tcol + c, v);
-          uint4 r4[4];
-          if (valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * LN_N + ncol0 + c);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) r4[q] = __ldg(rp + q);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) r4[q] = make_uint4(0, 0, 0, 0);
-          }
-          tmem_ld_wait();
-          const uint32_t* ru = reinterpret_cast<const uint32_t*>(r4);
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float2 rr = unpack_bf16x2(ru[j >> 1]);
-            float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + ncol0 + c + j));
-            float x0 = __uint_as_float(v[j]) + bb.x + rr.x;
-            float x1 = __uint_as_float(v[j + 1]) + bb.y + rr.y;
-            sum += x0 + x1;
-            sq = fmaf(x0, x0, fmaf(x1, x1, sq));
-            v[j] = __float_as_uint(x0);
-            v[j + 1] = __float_as_uint(x1);
-          }
-          tmem_st32(tcol + c, v);
-        }
-        tmem_st_wait();
-        float2* ex = exch + (size_t)(it & 1) * 2 * BLOCK_M;
-        ex[half * BLOCK_M + row_in_tile] = make_float2(sum, sq);
-        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
-        const float2 other = ex[(half ^ 1) * BLOCK_M + row_in_tile];
-        const float mean = (sum + other.x) * (1.0f / LN_N);
-        const float var = fmaxf((sq + other.y) * (1.0f / LN_N) - mean * mean, 0.0f);
-        const float rstd = rsqrtf(var + 1e-5f);
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tcol + c, v);
-          tmem_ld_wait();
-          if (valid) {
-            uint32_t o[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float2 g = __ldg(reinterpret_cast<const float2*>(p.ln_g + ncol0 + c + j));
-              float2 b = __ldg(reinterpret_cast<const float2*>(p.ln_b + ncol0 + c + j));
-              float y0 = fmaf((__uint_as_float(v[j]) - mean) * rstd, g.x, b.x);
-              float y1 = fmaf((__uint_as_float(v[j + 1]) - mean) * rstd, g.y, b.y);
-              o[j >> 1] = pack_bf16x2(y0, y1);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row * LN_N + ncol0 + c);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(tempty_bar(half));
-        tile_phase ^= 1;
-      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
+    if (STAGED && store_thread) bulk_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// out = LayerNorm(A W^T + bias + residual) * gamma + beta,  N = 512, bf16 out.
+// Cluster of 2 CTAs per 128-row block; CTA `rank` owns columns [256*rank, +256).
+// ---------------------------------------------------------------------------
+struct LnCfg {
+  static constexpr int BN = 256;
+  static constexpr int STAGES = 3;
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int IO_BYTES = 4 * CHUNK_BYTES;            // residual in / normalised tile out, 4 x [128 x 64]
+  static constexpr int EXCH_BYTES = 2 * 4 * BLOCK_M * 8;      // [parity][source = 2*cta + half][row] float2
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + IO_BYTES + EXCH_BYTES + BAR_BYTES;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
+                  const TcGemmParams p) {
+  using Cfg = LnCfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t io_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t exch_smem = io_smem + Cfg::IO_BYTES;
+  Ring ring{base, exch_smem + Cfg::EXCH_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
+  const uint32_t tmem_slot = ring.extra(0);
+  auto res_full = [&](int h) { return ring.extra(1 + h); };  // residual chunks of column-half h have landed
+  const uint32_t stats_bar = ring.extra(3);                   // 512 arrivals: every epilogue thread of both CTAs
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
+  const float2* exch_ptr = reinterpret_cast<const float2*>(base_ptr + (exch_smem - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_w);
+    prefetch_tensormap(&tmap_res);
+    prefetch_tensormap(&tmap_out);
+    for (int st = 0; st < Cfg::STAGES; ++st) {
+      mbar_init(ring.full(st), 1);
+      mbar_init(ring.empty(st), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(ring.tfull(i), 1);
+      mbar_init(ring.tempty(i), NUM_EPI_THREADS);
+      mbar_init(res_full(i), 1);
+    }
+    mbar_init(stats_bar, 2 * NUM_EPI_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int m_blks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int k_blks = p.K / BLOCK_K;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m_blk = cluster_id; m_blk < m_blks; m_blk += n_clusters) {
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(ring.empty(stage), phase ^ 1);
+          mbar_expect_tx(ring.full(stage), Cfg::STAGE_BYTES);
+          tma_load_2d(ring.a(stage), &tmap_a, ring.full(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(ring.b(stage), &tmap_w, ring.full(stage), kb * BLOCK_K, (int)rank * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int m_blk = cluster_id; m_blk < m_blks; m_blk += n_clusters) {
+        mbar_wait(ring.tempty(acc), acc_phase ^ 1);
+        tc_fence_after();
+        mma_tile<BN>(ring, tmem_base + (uint32_t)(acc * BN), k_blks, stage, phase);
+        mma_commit(ring.tfull(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;  // 128-column half of this CTA's 256 columns
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const bool io_thread = (ew & 3) == 0 && lane == 0;  // issues this half's residual loads and output stores
+    const int col0 = (int)rank * BN + half * 128;      // first global column of this thread's 128
+    const uint32_t peer_exch = map_to_cta(exch_smem, rank ^ 1);
+    const uint32_t peer_stats_bar = map_to_cta(stats_bar, rank ^ 1);
+    const int my_src = (int)rank * 2 + half;
+    if (io_thread && cluster_id < m_blks) {
+      mbar_expect_tx(res_full(half), 2 * CHUNK_BYTES);
+      for (int cc = 0; cc < 2; ++cc)
+        tma_load_2d(io_smem + (half * 2 + cc) * CHUNK_BYTES, &tmap_res, res_full(half), col0 + cc * 64, cluster_id * BLOCK_M);
+    }
+    int acc = 0, it = 0;
+    uint32_t acc_phase = 0;
+    for (int m_blk = cluster_id; m_blk < m_blks; m_blk += n_clusters, ++it) {
+      const uint32_t par = it & 1;
+      mbar_wait(ring.tfull(acc), acc_phase);
+      tc_fence_after();
+      mbar_wait(res_full(half), par);
+      float x[128];
+      float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {  // 32 accumulator columns at a time
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + half * 128 + c4 * 32), v);
+        tmem_ld_wait();
+        if (c4 == 3) {  // accumulator is in registers: release the TMEM stage before the normalisation
+          tc_fence_before();
+          mbar_arrive(ring.tempty(acc));
+        }
+        const uint32_t row_smem = io_smem + (half * 2 + (c4 >> 1)) * CHUNK_BYTES + r * 128;
+        const float* bias = p.bias + col0 + c4 * 32;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = (c4 & 1) * 4 + jj;  // 16-byte piece of the 128-byte staged row
+          const uint4 rr = lds128(row_smem + ((j ^ (r & 7)) << 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * jj));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * jj + 4));
+          const uint32_t* s = &v[jj * 8];
+          const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z), r3 = unpack_bf16x2(rr.w);
+          float* xo = &x[c4 * 32 + jj * 8];
+          xo[0] = __uint_as_float(s[0]) + b0.x + r0.x; xo[1] = __uint_as_float(s[1]) + b0.y + r0.y;
+          xo[2] = __uint_as_float(s[2]) + b0.z + r1.x; xo[3] = __uint_as_float(s[3]) + b0.w + r1.y;
+          xo[4] = __uint_as_float(s[4]) + b1.x + r2.x; xo[5] = __uint_as_float(s[5]) + b1.y + r2.y;
+          xo[6] = __uint_as_float(s[6]) + b1.z + r3.x; xo[7] = __uint_as_float(s[7]) + b1.w + r3.y;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            sum += xo[q];
+            sq = fmaf(xo[q], xo[q], sq);
+          }
+        }
+      }
+      // row statistics: 4 partials per row (2 CTAs x 2 halves), exchanged through (distributed) shared memory
+      const uint32_t slot = (uint32_t)(((par * 4 + my_src) * BLOCK_M + r) * 8);
+      st_cluster_f32x2(map_to_cta(exch_smem, rank) + slot, sum, sq);
+      st_cluster_f32x2(peer_exch + slot, sum, sq);
+      mbar_arrive_cluster(map_to_cta(stats_bar, rank));
+      mbar_arrive_cluster(peer_stats_bar);
+      mbar_wait_cluster(stats_bar, par);
+      float tsum = 0.0f, tsq = 0.0f;
+#pragma unroll
+      for (int src = 0; src < 4; ++src) {
+        const float2 e = exch_ptr[(par * 4 + src) * BLOCK_M + r];
+        tsum += e.x;
+        tsq += e.y;
+      }
+      const float mean = tsum * (1.0f / LN_N);
+      const float var = fmaxf(tsq * (1.0f / LN_N) - mean * mean, 0.0f);
+      const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const uint32_t row_smem = io_smem + (half * 2 + cc) * CHUNK_BYTES + r * 128;
+        const float* g = p.ln_g + col0 + cc * 64;
+        const float* bt = p.ln_b + col0 + cc * 64;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + 8 * j));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 8 * j + 4));
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(bt + 8 * j));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(bt + 8 * j + 4));
+          const float* xi = &x[cc * 64 + j * 8];
+          const float y0 = fmaf((xi[0] - mean) * rstd, g0.x, t0.x), y1 = fmaf((xi[1] - mean) * rstd, g0.y, t0.y);
+          const float y2 = fmaf((xi[2] - mean) * rstd, g0.z, t0.z), y3 = fmaf((xi[3] - mean) * rstd, g0.w, t0.w);
+          const float y4 = fmaf((xi[4] - mean) * rstd, g1.x, t1.x), y5 = fmaf((xi[5] - mean) * rstd, g1.y, t1.y);
+          const float y6 = fmaf((xi[6] - mean) * rstd, g1.z, t1.z), y7 = fmaf((xi[7] - mean) * rstd, g1.w, t1.w);
+          // each thread overwrites exactly the 16-byte pieces of the residual it read itself
+          sts128(row_smem + ((j ^ (r & 7)) << 4),
+                 make_uint4(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7)));
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, NUM_EPI_THREADS / 2);
+      if (io_thread) {
+        for (int cc = 0; cc < 2; ++cc)
+          tma_store_2d(&tmap_out, io_smem + (half * 2 + cc) * CHUNK_BYTES, col0 + cc * 64, m_blk * BLOCK_M);
+        bulk_commit_group();
+        const int next = m_blk + n_clusters;
+        if (next < m_blks) {
+          bulk_wait_read_all();  // the stores have read the tile: the buffers can take the next residual
+          mbar_expect_tx(res_full(half), 2 * CHUNK_BYTES);
+          for (int cc = 0; cc < 2; ++cc)
+            tma_load_2d(io_smem + (half * 2 + cc) * CHUNK_BYTES, &tmap_res, res_full(half), col0 + cc * 64, next * BLOCK_M);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (io_thread) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA exits while its peer may still write statistics into its shared memory
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -392,23 +610,49 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
 
 template <int BN, int EPI>
 static int launch_gemm(const TcGemmParams& p, cudaStream_t s) {
-  using Cfg = GemmCfg<BN>;
-  CUtensorMap ta, tw;
+  constexpr bool STAGED = epi_is_staged(EPI);
+  using Cfg = GemmCfg<BN, STAGED>;
+  CUtensorMap ta, tw, to;
   int rc;
   if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, BN, BLOCK_K))) return rc;
+  if (STAGED) {
+    if ((rc = make_tmap_bf16(&to, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, BLOCK_M, 64))) return rc;
+  } else {
+    to = ta;  // unused
+  }
   static bool attr_set = false;
   if (!attr_set) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int npt = (EPI == TC_EPI_BIAS_RES_LN) ? 2 : 1;
-  const int tiles = ceil_div(p.M, BLOCK_M) * ((p.N / BN) / npt);
+  const int tiles = ceil_div(p.M, BLOCK_M) * (p.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  tc_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, p);
+  tc_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, to, p);
   static const char* const kNames[] = {"tc_gemm_qkv", "tc_gemm_ffn1_gelu", "tc_gemm_res_ln", "tc_gemm_inproj",
                                        "tc_gemm_outproj", "tc_gemm_f32"};
   MST_LAUNCHED(kNames[EPI], s);
+  return MST_OK;
+}
+
+static int launch_gemm_ln(const TcGemmParams& p, cudaStream_t s) {
+  using Cfg = LnCfg;
+  CUtensorMap ta, tw, tr, to;
+  int rc;
+  if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
+  if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN, BLOCK_K))) return rc;
+  if ((rc = make_tmap_bf16(&tr, p.residual, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, BLOCK_M, 64))) return rc;
+  if ((rc = make_tmap_bf16(&to, p.out, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, BLOCK_M, 64))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_blks = ceil_div(p.M, BLOCK_M);
+  const int max_clusters = sm_count() / 2;
+  const int clusters = m_blks < max_clusters ? m_blks : max_clusters;
+  tc_gemm_ln_kernel<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, tr, to, p);
+  MST_LAUNCHED("tc_gemm_res_ln", s);
   return MST_OK;
 }
 
@@ -425,7 +669,7 @@ int tc_gemm(const TcGemmParams& p, cudaStream_t s) {
       return launch_gemm<256, TC_EPI_BIAS_GELU_BF16>(p, s);
     case TC_EPI_BIAS_RES_LN:
       MST_CHECK_ARG(p.N == LN_N && p.residual && p.ln_g && p.ln_b, "LN epilogue needs N == 512 and residual/gamma/beta");
-      return launch_gemm<256, TC_EPI_BIAS_RES_LN>(p, s);
+      return launch_gemm_ln(p, s);
     case TC_EPI_INPROJ:
       MST_CHECK_ARG(p.N % 256 == 0 && p.pe && p.B > 0 && p.T > 0 && p.ldo % 8 == 0, "bad in-projection geometry");
       return launch_gemm<256, TC_EPI_INPROJ>(p, s);

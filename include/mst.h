@@ -260,6 +260,11 @@ int mst_philox_normal(float* out, int32_t batch, int64_t per_sample, uint64_t se
 /* C[M,N] (fp32) = A[M,K](bf16) * W[N,K](bf16)^T + bias[N], tcgen05 path.    */
 int mst_test_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, float* c,
                        int32_t m, int32_t n, int32_t k, void* stream);
+/* bf16-output epilogues of the same GEMM: epi 0 = bias, 1 = bias+GELU,
+ * 2 = LayerNorm(acc + bias + residual)*g + b (n must be 512).  out: bf16 [m,n]. */
+int mst_test_gemm_epi_bf16(int32_t epi, const void* a_bf16, const void* w_bf16, const float* bias,
+                           const void* residual_bf16, const float* ln_g, const float* ln_b, void* out_bf16,
+                           int32_t m, int32_t n, int32_t k, void* stream);
 /* softmax(QK^T/sqrt(dh))V for qkv [n_seqs*S, 3d] bf16 -> out [n_seqs*S, d] bf16 */
 int mst_test_attention_bf16(mst_engine_t e, const void* qkv_bf16, void* out_bf16, int32_t n_seqs,
                             int32_t seq_len, void* workspace, size_t workspace_bytes, void* stream);

@@ -256,6 +256,31 @@ def test_tc_gemm_bf16(L, m, n, k):
     assert relerr(c, want) < 1e-4
 
 
+@pytest.mark.parametrize("epi,m,n,k", [(0, 25216, 1536, 512), (0, 197, 256, 64), (1, 25216, 1024, 512), (1, 300, 256, 512),
+                                       (2, 25216, 512, 512), (2, 25216, 512, 1024), (2, 197, 512, 512), (2, 50, 512, 64),
+                                       (2, 128 * 149, 512, 512)])
+def test_tc_gemm_fused_epilogues(L, epi, m, n, k):
+    """bias / bias+GELU (TMA-store epilogue) and the 2-CTA-cluster residual+LayerNorm GEMM against torch fp32 on the
+    same bf16 inputs.  Output is bf16: tolerance = one bf16 rounding (2^-8 relative) plus accumulation order."""
+    lib = L.load()
+    a = _rand((m, k), 1).to(DEV).bfloat16().contiguous()
+    w = (_rand((n, k), 2) / math.sqrt(k)).to(DEV).bfloat16().contiguous()
+    bias = _rand((n,), 3).to(DEV)
+    res = _rand((m, n), 4).to(DEV).bfloat16().contiguous()
+    g, b = (1 + 0.1 * _rand((n,), 5)).to(DEV), (0.1 * _rand((n,), 6)).to(DEV)
+    out = torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16)
+    L.check(lib.mst_test_gemm_epi_bf16(epi, a.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr(), g.data_ptr(),
+                                       b.data_ptr(), out.data_ptr(), m, n, k, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    want = a.float() @ w.float().T + bias
+    if epi == 1:
+        want = torch.nn.functional.gelu(want)
+    elif epi == 2:
+        want = torch.nn.functional.layer_norm(want + res.float(), (n,), g, b, eps=1e-5)
+    assert torch.isfinite(out.float()).all()
+    assert relerr(out.float(), want) < 6e-3
+
+
 @pytest.mark.parametrize("n_seqs,S", [(1, 197), (5, 197), (3, 77), (2, 61), (4, 21), (2, 128), (2, 129)])
 def test_tc_attention_bf16(K, L, state, n_seqs, S):
     lib = L.load()
