@@ -28,7 +28,7 @@ EXPORTED = [
     "mst_version", "mst_last_error", "mst_launch_count", "mst_profile_begin", "mst_profile_end", "mst_device_info", "mst_abi_sizes", "mst_engine_create", "mst_engine_destroy",
     "mst_engine_packed_weight_bytes", "mst_engine_load_weights", "mst_engine_workspace_bytes", "mst_time_embed",
     "mst_text_embed", "mst_denoiser_forward", "mst_update_step", "mst_q_sample", "mst_cfg_combine",
-    "mst_philox_normal", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_attention_bf16",
+    "mst_philox_normal", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
 ]
 
 
@@ -131,6 +131,7 @@ def _declare(lib):
         "mst_philox_normal": [vp, i32, i64, u64, u64, i32, vp],
         "mst_test_gemm_bf16": [vp, vp, vp, vp, i32, i32, i32, vp],
         "mst_test_gemm_epi_bf16": [i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "mst_test_set_gemm_debug": [vp],
         "mst_test_attention_bf16": [vp, vp, vp, i32, i32, vp, sz, vp],
     }
     for name, args in sigs.items():

@@ -474,6 +474,11 @@ extern "C" int mst_test_gemm_epi_bf16(int32_t epi, const void* a_bf16, const voi
   return tc_gemm(p, (cudaStream_t)stream);
 }
 
+extern "C" int mst_test_set_gemm_debug(void* dev_buf_int64) {
+  set_gemm_debug(static_cast<long long*>(dev_buf_int64));
+  return MST_OK;
+}
+
 extern "C" int mst_test_attention_bf16(mst_engine_t h, const void* qkv_bf16, void* out_bf16, int32_t n_seqs,
                                        int32_t seq_len, void* workspace, size_t workspace_bytes, void* stream) {
   MST_CHECK_ARG(h && qkv_bf16 && out_bf16, "null pointer");

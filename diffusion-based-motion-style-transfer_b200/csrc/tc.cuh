@@ -29,10 +29,12 @@ struct TcGemmParams {
   // in/out projection geometry
   const float* pe = nullptr;
   int B = 0, T = 0, n_pass = 1, n_valid = 0;
+  long long* dbg = nullptr;  // test hook: clock64 timeline of cluster 0 (see mst_test_set_gemm_debug)
   float* out2 = nullptr;  // OUTPROJ: rows of sequences >= B go here (uncond pass)
 };
 
 int tc_gemm(const TcGemmParams& p, cudaStream_t s);
+void set_gemm_debug(long long* dev_buf);  // device buffer of >= 3*2*1024 int64 (or nullptr to switch off)
 
 // x [B,F,T] fp32 -> A operand of the in-projection: bf16 [B*T, f_pad], zero padded
 int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T, int f_pad, cudaStream_t s);

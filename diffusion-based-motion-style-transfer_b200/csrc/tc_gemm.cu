@@ -43,35 +43,54 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + NUM_EPI_THREADS;  // 320
 constexpr int LN_N = 512;                           // row width the LN epilogue is built for
-constexpr int CHUNK_BYTES = BLOCK_M * 128;          // one staged [128 rows x 64 bf16] box
+constexpr int WARP_BOX_BYTES = 32 * 128;            // one staged [32 rows x 64 bf16] box (a warp's rows of a 64-column chunk)
+constexpr int STAGING_BYTES = NUM_EPI_WARPS * 2 * WARP_BOX_BYTES;  // 64 KB: two boxes per epilogue warp
 
-__host__ __device__ constexpr bool epi_is_staged(int epi) { return epi == TC_EPI_BIAS_BF16 || epi == TC_EPI_BIAS_GELU_BF16; }
-
-template <int BN, bool STAGED>
+template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = STAGED ? 3 : (BN >= 256 ? 4 : 6);
+  static constexpr int STAGES = BN >= 256 ? 4 : 6;
   static constexpr int A_BYTES = BLOCK_M * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_BYTES = STAGED ? (BN / 64) * CHUNK_BYTES : 0;  // staged output tile
   static constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : (2 * BN >= 128 ? 128 : 64));
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
 };
 
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding): branch-free,
-// 2 MUFU + 7 FMA-class instructions - the exact-erf GELU epilogue is ALU-bound otherwise.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x|/sqrt2)
-  return 0.5f * x + 0.5f * fabsf(x) * e;          // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+// ---- GELU for the FFN epilogue --------------------------------------------------------------------------
+// 0.5 x (1 + erf(x / sqrt 2)) with erf(z) = z P(z^2) on |z| <= 3 (degree-8 minimax fit, |erf error| < 4.2e-5,
+// |GELU error| < 9e-5 - two orders below the bf16 rounding of the output) and z clamped outside.
+// No MUFU: an exp/rcp based erf needs 2 SFU ops per element = 4096 SFU cycles per 128x256 tile, as long as the
+// tile's MMAs.  The polynomial runs on packed fma.rn.f32x2 (two elements per instruction).
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void gelu2(float& x0, float& x1) {
+  const float kC[9] = {1.1283629389e+00f, -3.7581860120e-01f, 1.1186250267e-01f, -2.5649613612e-02f, 4.4378622868e-03f,
+                       -5.5355724174e-04f, 4.6147291864e-05f, -2.2677306229e-06f, 4.9182760725e-08f};
+  const float z0 = fminf(fmaxf(x0 * 0.70710678118654752440f, -3.0f), 3.0f);
+  const float z1 = fminf(fmaxf(x1 * 0.70710678118654752440f, -3.0f), 3.0f);
+  const uint64_t z = pk2(z0, z1);
+  const uint64_t t = mul2(z, z);
+  uint64_t p = pk2(kC[8], kC[8]);
+#pragma unroll
+  for (int k = 7; k >= 0; --k) p = fma2(p, t, pk2(kC[k], kC[k]));
+  const uint64_t e = mul2(z, p);
+  const uint64_t hx = pk2(0.5f * x0, 0.5f * x1);
+  upk2(fma2(hx, e, hx), x0, x1);
 }
 
 // ---- direct (row-per-thread) epilogue of one 32-column chunk: the small fp32 / row-remapping cases ----
@@ -120,7 +139,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, i
   }
 }
 
-// ---- producer / MMA roles shared by both kernels -----------------------------------------------------
+// ---- smem ring + barrier addresses shared by the kernels ---------------------------------------------
 struct Ring {
   uint32_t base, bar_base;
   int stages, stage_bytes, a_bytes;
@@ -150,20 +169,18 @@ __device__ __forceinline__ void mma_tile(const Ring& r, uint32_t d_tmem, int k_b
   }
 }
 
+// ---------------------------------------------------------------------------
+// Single-CTA kernel: the two small projections (row-remapping / fp32 epilogues) and the fp32 test hook.
+// ---------------------------------------------------------------------------
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-               const __grid_constant__ CUtensorMap tmap_out, const TcGemmParams p) {
-  constexpr bool STAGED = epi_is_staged(EPI);
-  using Cfg = GemmCfg<BN, STAGED>;
-  static_assert(!STAGED || BN == 256, "staged epilogue is built for 256-column tiles");
-
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const TcGemmParams p) {
+  using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
-  const uint32_t out_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1024)
-  Ring ring{base, out_smem + Cfg::OUT_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
+  Ring ring{base, base + Cfg::STAGES * Cfg::STAGE_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
   const uint32_t tmem_slot = ring.extra(0);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
 
@@ -173,7 +190,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && elect_one()) {
     prefetch_tensormap(&tmap_a);
     prefetch_tensormap(&tmap_w);
-    if (STAGED) prefetch_tensormap(&tmap_out);
     for (int st = 0; st < Cfg::STAGES; ++st) {
       mbar_init(ring.full(st), 1);
       mbar_init(ring.empty(st), 1);
@@ -199,7 +215,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int k_blks = p.K / BLOCK_K;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -215,7 +230,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------- MMA issuer -------------------------------
     if (elect_one()) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -229,82 +243,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // -------------------------------- epilogue --------------------------------
     const int ew = warp - 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp is allowed to access
     const int half = ew >> 2;   // column half of the tile
     const int row_in_tile = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const bool store_thread = (ew & 3) == 0 && lane == 0;
-    int acc = 0, it = 0;
+    int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_blks, n_blk = tile - m_blk * n_blks;
+      const int row = m_blk * BLOCK_M + row_in_tile;
       mbar_wait(ring.tfull(acc), acc_phase);
       tc_fence_after();
-      if constexpr (STAGED) {
-        // the staged tile of the previous iteration must have been read out by its TMA stores
-        if (it > 0) {
-          if (store_thread) bulk_wait_read_all();
-          named_bar_sync(1 + half, NUM_EPI_THREADS / 2);
-        }
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int chunk = half * 2 + cc;  // 64 columns [64*chunk, 64*chunk+64) of the tile
-          uint32_t v[2][32];
-          tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + chunk * 64), v[0]);
-          tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + chunk * 64 + 32), v[1]);
-          tmem_ld_wait();
-          if (cc == 1) {  // accumulator drained: the MMAs of the tile after next may overwrite it
-            tc_fence_before();
-            mbar_arrive(ring.tempty(acc));
-          }
-          const float* bias = p.bias + n_blk * BN + chunk * 64;
-          const uint32_t row_smem = out_smem + chunk * CHUNK_BYTES + row_in_tile * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {  // 8 columns -> one 16-byte piece of the swizzled row
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j + 4));
-            const uint32_t* s = &v[j >> 2][(j & 3) * 8];
-            float x0 = __uint_as_float(s[0]) + b0.x, x1 = __uint_as_float(s[1]) + b0.y;
-            float x2 = __uint_as_float(s[2]) + b0.z, x3 = __uint_as_float(s[3]) + b0.w;
-            float x4 = __uint_as_float(s[4]) + b1.x, x5 = __uint_as_float(s[5]) + b1.y;
-            float x6 = __uint_as_float(s[6]) + b1.z, x7 = __uint_as_float(s[7]) + b1.w;
-            if constexpr (EPI == TC_EPI_BIAS_GELU_BF16) {
-              x0 = gelu_fast(x0); x1 = gelu_fast(x1); x2 = gelu_fast(x2); x3 = gelu_fast(x3);
-              x4 = gelu_fast(x4); x5 = gelu_fast(x5); x6 = gelu_fast(x6); x7 = gelu_fast(x7);
-            }
-            sts128(row_smem + ((j ^ (row_in_tile & 7)) << 4),
-                   make_uint4(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3), pack_bf16x2(x4, x5), pack_bf16x2(x6, x7)));
-          }
-        }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
-        named_bar_sync(1 + half, NUM_EPI_THREADS / 2);
-        if (store_thread) {
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int chunk = half * 2 + cc;
-            tma_store_2d(&tmap_out, out_smem + chunk * CHUNK_BYTES, n_blk * BN + chunk * 64, m_blk * BLOCK_M);
-          }
-          bulk_commit_group();
-        }
-      } else {
-        const int row = m_blk * BLOCK_M + row_in_tile;
 #pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 32) {
-          const int col = half * (BN / 2) + c;
-          uint32_t v[32];
-          tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + col), v);
-          tmem_ld_wait();
-          epilogue_chunk<EPI>(p, row, n_blk * BN + col, v);
-        }
-        tc_fence_before();
-        mbar_arrive(ring.tempty(acc));
+      for (int c = 0; c < BN / 2; c += 32) {
+        const int col = half * (BN / 2) + c;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + col), v);
+        tmem_ld_wait();
+        epilogue_chunk<EPI>(p, row, n_blk * BN + col, v);
       }
+      tc_fence_before();
+      mbar_arrive(ring.tempty(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (STAGED && store_thread) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -316,8 +279,216 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------
-// out = LayerNorm(A W^T + bias + residual) * gamma + beta,  N = 512, bf16 out.
-// Cluster of 2 CTAs per 128-row block; CTA `rank` owns columns [256*rank, +256).
+// CTA-pair GEMM (tcgen05 cta_group::2): one 256 x 256 output tile per cluster of two CTAs
+// (QKV projection, FFN linear1 + GELU).  Each CTA stages its own 128 rows of A and HALF of the
+// 256 weight rows, so it pulls 32 KB per k-block through L2 instead of 48 KB.  The leader CTA
+// (rank 0) issues the MMAs for both; both CTAs run the epilogue of their 128 rows.
+// Epilogue: every warp owns its 32 rows: TMEM -> registers -> (+bias, GELU) -> bf16 -> the warp's own
+// 128B-swizzled [32 x 64] staging box -> one TMA store per box.  Two boxes per warp ping-pong, so the only
+// synchronisation is __syncwarp and the bulk-group wait of lane 0 - no CTA-wide barrier in the loop.
+// ---------------------------------------------------------------------------
+struct PairCfg {
+  static constexpr int BN = 256;
+  static constexpr int STAGES = 5;
+  static constexpr int A_BYTES = BLOCK_M * 128;       // 128 rows x 64 k
+  static constexpr int B_BYTES = (BN / 2) * 128;      // this CTA's 128 of the 256 weight rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
+};
+
+#define MST_DBG_STAMP() do { if (dbg && di < 1000) dbg[di++] = clock64(); } while (0)
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_out, const TcGemmParams p) {
+  using Cfg = PairCfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t out_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  Ring ring{base, out_smem + STAGING_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
+  const uint32_t tmem_slot = ring.extra(0);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_w);
+    prefetch_tensormap(&tmap_out);
+    for (int st = 0; st < Cfg::STAGES; ++st) {
+      mbar_init(ring.full(st), 1);   // leader: its own arrive.expect_tx covers the bytes of both CTAs
+      mbar_init(ring.empty(st), 1);  // multicast tcgen05.commit of the leader
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(ring.tfull(i), 1);
+      mbar_init(ring.tempty(i), 2 * NUM_EPI_THREADS);  // leader: epilogue threads of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int n_blks = p.N / BN;
+  const int m_blks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_pairs = (m_blks + 1) / 2;
+  const int num_tiles = m_pairs * n_blks;
+  const int k_blks = p.K / BLOCK_K;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs; completion is signalled on the LEADER's full barrier) ----------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long* dbg = (p.dbg && cluster_id == 0) ? p.dbg + (0 * 2 + rank) * 1024 : nullptr;
+      int di = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        const int mp = tile / n_blks, n_blk = tile - mp * n_blks;
+        const int m_blk = 2 * mp + (int)rank;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(ring.empty(stage), phase ^ 1);
+          MST_DBG_STAMP();
+          const uint32_t full_leader = map_to_cta(ring.full(stage), 0);
+          if (leader) mbar_expect_tx(ring.full(stage), 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2cta(ring.a(stage), &tmap_a, full_leader, kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d_2cta(ring.b(stage), &tmap_w, full_leader, kb * BLOCK_K, n_blk * BN + (int)rank * (BN / 2));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: leader CTA only, one thread for the pair ----------------
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      long long* dbg = (p.dbg && cluster_id == 0) ? p.dbg + (1 * 2 + rank) * 1024 : nullptr;
+      int di = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        MST_DBG_STAMP();
+        mbar_wait_cluster(ring.tempty(acc), acc_phase ^ 1);
+        tc_fence_after();
+        MST_DBG_STAMP();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait_cluster(ring.full(stage), phase);
+          tc_fence_after();
+          MST_DBG_STAMP();
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(ring.a(stage) + k * (UMMA_K * 2), 0, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(ring.b(stage) + k * (UMMA_K * 2), 0, 1024);
+            mma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          mma_commit_2cta(ring.empty(stage), 3);  // both CTAs' producers may refill the slot
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit_2cta(ring.tfull(acc), 3);  // both CTAs' epilogues
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs, each for its own 128 rows) ----------------
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t my_box = out_smem + ew * 2 * WARP_BOX_BYTES;  // this warp's two staging boxes
+    const uint32_t my_row = lane * 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long* dbg = (p.dbg && cluster_id == 0 && warp == 2 && lane == 0) ? p.dbg + (2 * 2 + rank) * 1024 : nullptr;
+    int di = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      const int mp = tile / n_blks, n_blk = tile - mp * n_blks;
+      const int m_blk = 2 * mp + (int)rank;
+      MST_DBG_STAMP();
+      mbar_wait(ring.tfull(acc), acc_phase);
+      tc_fence_after();
+      MST_DBG_STAMP();
+      const uint32_t tempty_leader = map_to_cta(ring.tempty(acc), 0);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = half * 128 + cc * 64;  // first of this step's 64 tile columns
+        uint32_t v[2][32];
+        tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + col), v[0]);
+        tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + col + 32), v[1]);
+        // box cc was handed to a TMA store one tile ago: at most the other box's store may still be reading
+        if (lane == 0) bulk_wait_read_1();
+        __syncwarp();
+        tmem_ld_wait();
+        if (cc == 1) {  // accumulator drained: the MMAs of the tile after next may overwrite it
+          tc_fence_before();
+          mbar_arrive_cluster_relaxed(tempty_leader);
+        }
+        MST_DBG_STAMP();
+        const float* bias = p.bias + n_blk * BN + col;
+        const uint32_t row_smem = my_box + cc * WARP_BOX_BYTES + my_row;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 8 columns -> one 16-byte piece of the swizzled row
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j + 4));
+          const uint32_t* s = &v[j >> 2][(j & 3) * 8];
+          float x0 = __uint_as_float(s[0]) + b0.x, x1 = __uint_as_float(s[1]) + b0.y;
+          float x2 = __uint_as_float(s[2]) + b0.z, x3 = __uint_as_float(s[3]) + b0.w;
+          float x4 = __uint_as_float(s[4]) + b1.x, x5 = __uint_as_float(s[5]) + b1.y;
+          float x6 = __uint_as_float(s[6]) + b1.z, x7 = __uint_as_float(s[7]) + b1.w;
+          if constexpr (EPI == TC_EPI_BIAS_GELU_BF16) {
+            gelu2(x0, x1); gelu2(x2, x3); gelu2(x4, x5); gelu2(x6, x7);
+          }
+          sts128(row_smem + ((j ^ (lane & 7)) << 4),
+                 make_uint4(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3), pack_bf16x2(x4, x5), pack_bf16x2(x6, x7)));
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        MST_DBG_STAMP();
+        if (lane == 0) {
+          tma_store_2d(&tmap_out, my_box + cc * WARP_BOX_BYTES, n_blk * BN + col, m_blk * BLOCK_M + quad * 32);
+          bulk_commit_group();
+        }
+      }
+      MST_DBG_STAMP();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// out = LayerNorm(A W^T + bias + residual) * gamma + beta,  N = 512, bf16 out
+// (self_attn.out_proj + norm1, linear2 + norm2).
+// Cluster of 2 CTAs per 128-row block; CTA `rank` owns columns [256*rank, +256), so each CTA has two
+// accumulator stages and the MMAs of the next block overlap the normalisation.  Per epilogue warp: its
+// 32 rows x 128 columns; the residual arrives by TMA in the warp's two [32 x 64] boxes, the sum
+// acc + bias + residual stays in registers (fp32), the four partial (sum, sum of squares) of a row -
+// 2 CTAs x 2 column halves - meet through shared memory: local st.shared + mbarrier arrive, remote
+// st.async with transaction bytes on the peer's mbarrier (no cluster-scope fence anywhere).
 // ---------------------------------------------------------------------------
 struct LnCfg {
   static constexpr int BN = 256;
@@ -325,11 +496,10 @@ struct LnCfg {
   static constexpr int A_BYTES = BLOCK_M * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int IO_BYTES = 4 * CHUNK_BYTES;            // residual in / normalised tile out, 4 x [128 x 64]
   static constexpr int EXCH_BYTES = 2 * 4 * BLOCK_M * 8;      // [parity][source = 2*cta + half][row] float2
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + IO_BYTES + EXCH_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + EXCH_BYTES + BAR_BYTES;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -343,11 +513,11 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
   const uint32_t io_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t exch_smem = io_smem + Cfg::IO_BYTES;
+  const uint32_t exch_smem = io_smem + STAGING_BYTES;
   Ring ring{base, exch_smem + Cfg::EXCH_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
   const uint32_t tmem_slot = ring.extra(0);
-  auto res_full = [&](int h) { return ring.extra(1 + h); };  // residual chunks of column-half h have landed
-  const uint32_t stats_bar = ring.extra(3);                   // 512 arrivals: every epilogue thread of both CTAs
+  const uint32_t stats_bar = ring.extra(1);                   // 256 local arrivals + 2048 transaction bytes from the peer
+  auto res_full = [&](int e) { return ring.extra(2 + e); };  // residual boxes of epilogue warp e have landed
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
   const float2* exch_ptr = reinterpret_cast<const float2*>(base_ptr + (exch_smem - base));
 
@@ -368,9 +538,9 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int i = 0; i < 2; ++i) {
       mbar_init(ring.tfull(i), 1);
       mbar_init(ring.tempty(i), NUM_EPI_THREADS);
-      mbar_init(res_full(i), 1);
     }
-    mbar_init(stats_bar, 2 * NUM_EPI_THREADS);
+    mbar_init(stats_bar, NUM_EPI_THREADS);
+    for (int e = 0; e < NUM_EPI_WARPS; ++e) mbar_init(res_full(e), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -379,7 +549,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  cluster_sync_all();  // the peer's barriers are initialised before anything is signalled on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -419,15 +589,16 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int half = ew >> 2;  // 128-column half of this CTA's 256 columns
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const bool io_thread = (ew & 3) == 0 && lane == 0;  // issues this half's residual loads and output stores
-    const int col0 = (int)rank * BN + half * 128;      // first global column of this thread's 128
+    const int col0 = (int)rank * BN + half * 128;  // first global column of this thread's 128
+    const uint32_t my_box = io_smem + ew * 2 * WARP_BOX_BYTES;
+    const uint32_t my_row = lane * 128;
     const uint32_t peer_exch = map_to_cta(exch_smem, rank ^ 1);
     const uint32_t peer_stats_bar = map_to_cta(stats_bar, rank ^ 1);
     const int my_src = (int)rank * 2 + half;
-    if (io_thread && cluster_id < m_blks) {
-      mbar_expect_tx(res_full(half), 2 * CHUNK_BYTES);
+    if (lane == 0 && cluster_id < m_blks) {
+      mbar_expect_tx(res_full(ew), 2 * WARP_BOX_BYTES);
       for (int cc = 0; cc < 2; ++cc)
-        tma_load_2d(io_smem + (half * 2 + cc) * CHUNK_BYTES, &tmap_res, res_full(half), col0 + cc * 64, cluster_id * BLOCK_M);
+        tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64, cluster_id * BLOCK_M + quad * 32);
     }
     int acc = 0, it = 0;
     uint32_t acc_phase = 0;
@@ -435,7 +606,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t par = it & 1;
       mbar_wait(ring.tfull(acc), acc_phase);
       tc_fence_after();
-      mbar_wait(res_full(half), par);
+      mbar_wait(res_full(ew), par);
       float x[128];
       float sum = 0.0f, sq = 0.0f;
 #pragma unroll
@@ -447,12 +618,12 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tc_fence_before();
           mbar_arrive(ring.tempty(acc));
         }
-        const uint32_t row_smem = io_smem + (half * 2 + (c4 >> 1)) * CHUNK_BYTES + r * 128;
+        const uint32_t row_smem = my_box + (c4 >> 1) * WARP_BOX_BYTES + my_row;
         const float* bias = p.bias + col0 + c4 * 32;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int j = (c4 & 1) * 4 + jj;  // 16-byte piece of the 128-byte staged row
-          const uint4 rr = lds128(row_smem + ((j ^ (r & 7)) << 4));
+          const uint4 rr = lds128(row_smem + ((j ^ (lane & 7)) << 4));
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * jj));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * jj + 4));
           const uint32_t* s = &v[jj * 8];
@@ -469,12 +640,14 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
       }
-      // row statistics: 4 partials per row (2 CTAs x 2 halves), exchanged through (distributed) shared memory
+      // row statistics: 4 partials per row (2 CTAs x 2 halves)
       const uint32_t slot = (uint32_t)(((par * 4 + my_src) * BLOCK_M + r) * 8);
-      st_cluster_f32x2(map_to_cta(exch_smem, rank) + slot, sum, sq);
-      st_cluster_f32x2(peer_exch + slot, sum, sq);
-      mbar_arrive_cluster(map_to_cta(stats_bar, rank));
-      mbar_arrive_cluster(peer_stats_bar);
+      st_async_f32x2(peer_exch + slot, sum, sq, peer_stats_bar);
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(exch_smem + slot), "f"(sum), "f"(sq) : "memory");
+      if (ew == 0 && lane == 0)
+        mbar_expect_tx(stats_bar, NUM_EPI_THREADS * 8);  // arrive + the peer's 256 x 8 bytes of this phase
+      else
+        mbar_arrive(stats_bar);
       mbar_wait_cluster(stats_bar, par);
       float tsum = 0.0f, tsq = 0.0f;
 #pragma unroll
@@ -488,7 +661,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const float rstd = rsqrtf(var + 1e-5f);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        const uint32_t row_smem = io_smem + (half * 2 + cc) * CHUNK_BYTES + r * 128;
+        const uint32_t row_smem = my_box + cc * WARP_BOX_BYTES + my_row;
         const float* g = p.ln_g + col0 + cc * 64;
         const float* bt = p.ln_b + col0 + cc * 64;
 #pragma unroll
@@ -503,28 +676,29 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const float y4 = fmaf((xi[4] - mean) * rstd, g1.x, t1.x), y5 = fmaf((xi[5] - mean) * rstd, g1.y, t1.y);
           const float y6 = fmaf((xi[6] - mean) * rstd, g1.z, t1.z), y7 = fmaf((xi[7] - mean) * rstd, g1.w, t1.w);
           // each thread overwrites exactly the 16-byte pieces of the residual it read itself
-          sts128(row_smem + ((j ^ (r & 7)) << 4),
+          sts128(row_smem + ((j ^ (lane & 7)) << 4),
                  make_uint4(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7)));
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(1 + half, NUM_EPI_THREADS / 2);
-      if (io_thread) {
+      __syncwarp();
+      if (lane == 0) {
         for (int cc = 0; cc < 2; ++cc)
-          tma_store_2d(&tmap_out, io_smem + (half * 2 + cc) * CHUNK_BYTES, col0 + cc * 64, m_blk * BLOCK_M);
+          tma_store_2d(&tmap_out, my_box + cc * WARP_BOX_BYTES, col0 + cc * 64, m_blk * BLOCK_M + quad * 32);
         bulk_commit_group();
         const int next = m_blk + n_clusters;
         if (next < m_blks) {
-          bulk_wait_read_all();  // the stores have read the tile: the buffers can take the next residual
-          mbar_expect_tx(res_full(half), 2 * CHUNK_BYTES);
+          bulk_wait_read_all();  // the stores have read the boxes: they can take the next block's residual
+          mbar_expect_tx(res_full(ew), 2 * WARP_BOX_BYTES);
           for (int cc = 0; cc < 2; ++cc)
-            tma_load_2d(io_smem + (half * 2 + cc) * CHUNK_BYTES, &tmap_res, res_full(half), col0 + cc * 64, next * BLOCK_M);
+            tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64, next * BLOCK_M + quad * 32);
         }
       }
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (io_thread) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -610,17 +784,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
 
 template <int BN, int EPI>
 static int launch_gemm(const TcGemmParams& p, cudaStream_t s) {
-  constexpr bool STAGED = epi_is_staged(EPI);
-  using Cfg = GemmCfg<BN, STAGED>;
-  CUtensorMap ta, tw, to;
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tw;
   int rc;
   if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, BN, BLOCK_K))) return rc;
-  if (STAGED) {
-    if ((rc = make_tmap_bf16(&to, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, BLOCK_M, 64))) return rc;
-  } else {
-    to = ta;  // unused
-  }
   static bool attr_set = false;
   if (!attr_set) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -628,10 +796,31 @@ static int launch_gemm(const TcGemmParams& p, cudaStream_t s) {
   }
   const int tiles = ceil_div(p.M, BLOCK_M) * (p.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  tc_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, to, p);
+  tc_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, p);
   static const char* const kNames[] = {"tc_gemm_qkv", "tc_gemm_ffn1_gelu", "tc_gemm_res_ln", "tc_gemm_inproj",
                                        "tc_gemm_outproj", "tc_gemm_f32"};
   MST_LAUNCHED(kNames[EPI], s);
+  return MST_OK;
+}
+
+template <int EPI>
+static int launch_gemm_pair(const TcGemmParams& p, cudaStream_t s) {
+  using Cfg = PairCfg;
+  CUtensorMap ta, tw, to;
+  int rc;
+  if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
+  if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN / 2, BLOCK_K))) return rc;
+  if ((rc = make_tmap_bf16(&to, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 32, 64))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(ceil_div(p.M, BLOCK_M), 2) * (p.N / Cfg::BN);
+  const int max_clusters = sm_count() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  tc_gemm_pair_kernel<EPI><<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, to, p);
+  MST_LAUNCHED(EPI == TC_EPI_BIAS_BF16 ? "tc_gemm_qkv" : "tc_gemm_ffn1_gelu", s);
   return MST_OK;
 }
 
@@ -641,8 +830,8 @@ static int launch_gemm_ln(const TcGemmParams& p, cudaStream_t s) {
   int rc;
   if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN, BLOCK_K))) return rc;
-  if ((rc = make_tmap_bf16(&tr, p.residual, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, BLOCK_M, 64))) return rc;
-  if ((rc = make_tmap_bf16(&to, p.out, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, BLOCK_M, 64))) return rc;
+  if ((rc = make_tmap_bf16(&tr, p.residual, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, 32, 64))) return rc;
+  if ((rc = make_tmap_bf16(&to, p.out, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, 32, 64))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -656,17 +845,22 @@ static int launch_gemm_ln(const TcGemmParams& p, cudaStream_t s) {
   return MST_OK;
 }
 
-int tc_gemm(const TcGemmParams& p, cudaStream_t s) {
+static long long* g_gemm_dbg = nullptr;
+void set_gemm_debug(long long* dev_buf) { g_gemm_dbg = dev_buf; }
+
+int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
+  TcGemmParams p = p_in;
+  p.dbg = g_gemm_dbg;
   MST_CHECK_ARG(p.a && p.w && p.bias && p.out, "null pointer");
   MST_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0, "empty problem");
   MST_CHECK_ARG(p.K % BLOCK_K == 0, "K must be a multiple of 64");
   switch (p.epi) {
     case TC_EPI_BIAS_BF16:
       MST_CHECK_ARG(p.N % 256 == 0 && p.ldo % 8 == 0, "N must be a multiple of 256");
-      return launch_gemm<256, TC_EPI_BIAS_BF16>(p, s);
+      return launch_gemm_pair<TC_EPI_BIAS_BF16>(p, s);
     case TC_EPI_BIAS_GELU_BF16:
       MST_CHECK_ARG(p.N % 256 == 0 && p.ldo % 8 == 0, "N must be a multiple of 256");
-      return launch_gemm<256, TC_EPI_BIAS_GELU_BF16>(p, s);
+      return launch_gemm_pair<TC_EPI_BIAS_GELU_BF16>(p, s);
     case TC_EPI_BIAS_RES_LN:
       MST_CHECK_ARG(p.N == LN_N && p.residual && p.ln_g && p.ln_b, "LN epilogue needs N == 512 and residual/gamma/beta");
       return launch_gemm_ln(p, s);

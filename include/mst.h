@@ -265,6 +265,9 @@ int mst_test_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias
 int mst_test_gemm_epi_bf16(int32_t epi, const void* a_bf16, const void* w_bf16, const float* bias,
                            const void* residual_bf16, const float* ln_g, const float* ln_b, void* out_bf16,
                            int32_t m, int32_t n, int32_t k, void* stream);
+/* Developer hook: when set to a device buffer of >= 6*1024 int64, cluster 0 of the pair GEMM records clock64()
+ * timelines of its producer / MMA / epilogue roles there (tools/gemm_timeline.py).  NULL switches it off.  */
+int mst_test_set_gemm_debug(void* dev_buf_int64);
 /* softmax(QK^T/sqrt(dh))V for qkv [n_seqs*S, 3d] bf16 -> out [n_seqs*S, d] bf16 */
 int mst_test_attention_bf16(mst_engine_t e, const void* qkv_bf16, void* out_bf16, int32_t n_seqs,
                             int32_t seq_len, void* workspace, size_t workspace_bytes, void* stream);

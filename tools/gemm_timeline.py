@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""clock64 timeline of cluster 0 of the pair GEMM (QKV shape by default): where do the producer, the MMA
+issuer and the epilogue spend their cycles?   python tools/gemm_timeline.py [epi m n k]"""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mst_b200 import _lib as L  # noqa: E402
+
+epi, m, n, k = (int(v) for v in sys.argv[1:5]) if len(sys.argv) >= 5 else (0, 25216, 1536, 512)
+dev = "cuda:0"
+lib = L.load()
+g = torch.Generator().manual_seed(1)
+a = torch.randn(m, k, generator=g).to(dev).bfloat16()
+w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(dev).bfloat16()
+bias = torch.randn(n, generator=g).to(dev)
+res = torch.randn(m, n, generator=g).to(dev).bfloat16()
+out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+s = torch.cuda.current_stream().cuda_stream
+
+
+def run():
+    L.check(lib.mst_test_gemm_epi_bf16(epi, a.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr(), bias.data_ptr(),
+                                       bias.data_ptr(), out.data_ptr(), m, n, k, s))
+
+
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    run()
+e1.record()
+torch.cuda.synchronize()
+print(f"epi={epi} m={m} n={n} k={k}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch")
+dbg = torch.zeros(6 * 1024, dtype=torch.int64, device=dev)
+lib.mst_test_set_gemm_debug(dbg.data_ptr())
+run()
+torch.cuda.synchronize()
+lib.mst_test_set_gemm_debug(None)
+d = dbg.cpu().view(3, 2, 1024)
+kb = k // 64
+t0 = int(d[1, 0, 0])
+rel = lambda v: int(v) - t0
+prod = [[rel(v) for v in d[0, r] if v != 0] for r in range(2)]
+mma = [rel(v) for v in d[1, 0] if v != 0]
+epi_t = [[rel(v) for v in d[2, r] if v != 0] for r in range(2)]
+per = 2 + kb
+print("MMA issuer (leader): per tile [start, after tempty wait, after full wait of each k-block]")
+for i in range(0, len(mma), per):
+    row = mma[i:i + per]
+    print(f"  tile {i // per}: start {row[0]:7d} tempty+{row[1] - row[0]:5d} kblocks " + " ".join(f"{b - a_:4d}" for a_, b in zip(row[1:], row[2:])),
+          f"| tile total {row[-1] - row[0]:6d}")
+print("epilogue (warp 2 lane 0) per tile: top | tfull wait | box0 free+ldtm | math0+sts | store0+box1 free+ldtm (tmem released) | math1+sts | store1 | total after tfull")
+for r in range(2):
+    e = epi_t[r]
+    for i in range(0, len(e), 7):
+        q = e[i:i + 7]
+        if len(q) == 7:
+            print(f"  cta{r} tile {i // 7}: top {q[0]:7d} | " + " | ".join(f"{b - a_:5d}" for a_, b in zip(q, q[1:])) + f" | total {q[6] - q[1]:5d}")
+print("producer: time after each empty wait (per k-block), deltas")
+for r in range(2):
+    pr = prod[r]
+    print(f"  cta{r}: first {pr[0]}", " ".join(str(b - a_) for a_, b in zip(pr[:40], pr[1:41])))
