@@ -1,17 +1,20 @@
-// Self-attention of one (sequence, head) per CTA on tcgen05 tensor cores:
+// Self-attention on tcgen05 tensor cores, persistent and software-pipelined:
 //   O = softmax(Q K^T / sqrt(dh)) V,   S = T+1 <= 208 tokens, dh = 128, no mask
-// (torch.nn.MultiheadAttention as used by nn.TransformerEncoderLayer in the
-// reference, model/mdm_forstyledataset.py:231-238 / :346).
+// (torch.nn.MultiheadAttention as used by nn.TransformerEncoderLayer in the reference,
+// model/mdm_forstyledataset.py:231-238 / :346).
 //
-// The whole key range fits one tile, so there is no online-softmax rescaling:
-//   1. TMA: K, V ([s_pad x 128] each) and one 128-row Q tile -> 128B-swizzled smem
-//   2. tcgen05.mma  S[128 x s_pad] = Q K^T            (fp32 in TMEM cols [0, s_pad))
-//   3. 128 threads, one query row each: tcgen05.ld the row, max, exp2, sum;
-//      write P (bf16) to shared memory in the K-major swizzled operand layout
-//   4. tcgen05.mma  O[128 x 128] = P V   (V consumed MN-major straight from the
-//      QKV buffer's layout - no transpose pass)        (TMEM cols [256, 384))
-//   5. O * (1/rowsum) -> bf16 -> global
-// Steps 2-5 repeat for the second Q tile (rows 128..S-1) with K/V resident.
+// Work item = (sequence, head, 128-query tile).  The whole key range of a sequence fits one tile, so there is
+// no online-softmax rescaling.  Every CTA owns a contiguous range of items and runs three roles:
+//   warp 0          TMA producer: K and V of a (sequence, head) once, Q per item (two Q buffers), straight out of
+//                   the packed QKV activation through a 3-D tensor map [sequence][token][column] - rows past
+//                   the end of a sequence are out of bounds (zero-filled), never the next sequence's data
+//   warp 1          tcgen05.mma issuer:  S = Q K^T  (fp32, TMEM)  and  O = P V  with P read from TMEM
+//   warps 4-7, 8-11 two softmax groups of 128 threads (one query row each) that alternate items, so the
+//                   row max / exp2 / sum of item i overlaps the Q K^T of item i+1 and the P V of item i-1.
+//                   P (bf16) is written back into TMEM over the S columns it was computed from - it never
+//                   touches shared memory - and O leaves through per-warp [32 x 32] staging boxes and TMA stores.
+// TMEM slot (2 slots, 256 columns apart): S fp32 in [0, s_pad), P bf16x2 in [0, s_pad/2),
+// O fp32 in [s_pad/2, s_pad/2 + 128) (the tail of S is dead once the softmax has read it).
 #include "tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -21,49 +24,75 @@ using namespace ptx;
 
 constexpr int ATT_DH = 128;
 constexpr int ATT_MAX_SPAD = 208;
-constexpr int ATT_THREADS = 160;  // warps 0-3: softmax/epilogue (one row per thread); warp 4: TMA + MMA issue
-constexpr int ATT_Q_BYTES = 2 * 128 * 128;
-constexpr int ATT_KV_BYTES = 2 * ATT_MAX_SPAD * 128;
-constexpr int ATT_P_BYTES = 4 * 128 * 128;
-constexpr int ATT_SMEM_BYTES = 1024 + ATT_Q_BYTES + 2 * ATT_KV_BYTES + ATT_P_BYTES + 64;
+constexpr int ATT_THREADS = 384;
+constexpr int ATT_Q_BYTES = 2 * 128 * 128;             // one Q tile: two 64-column halves of 128 rows
+constexpr int ATT_KV_BYTES = 2 * ATT_MAX_SPAD * 128;   // K (or V): two 64-column halves of s_pad rows
+constexpr int ATT_OBOX_BYTES = 32 * 64;                // [32 rows x 32 bf16], 64B swizzle
+constexpr int ATT_STAGING_BYTES = 8 * 2 * ATT_OBOX_BYTES;
+constexpr int ATT_SMEM_BYTES = 1024 + 2 * ATT_Q_BYTES + 2 * ATT_KV_BYTES + ATT_STAGING_BYTES + 256;
 constexpr int ATT_TMEM_COLS = 512;
-constexpr int ATT_O_COL = 256;
+constexpr int ATT_SLOT_COLS = 256;
+
+struct AttnGeom {
+  int S, s_pad, n_qt, n_heads, n_items, d_model;
+  float scale_log2e;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    __nv_bfloat16* __restrict__ out, int S, int s_pad, int d_model, float scale_log2e) {
+                    const __grid_constant__ CUtensorMap tmap_o, const AttnGeom g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
-  const uint32_t kv_box = (uint32_t)s_pad * 128u;  // bytes of one [s_pad x 64] box
-  const uint32_t q_smem = base;
-  const uint32_t k_smem = q_smem + ATT_Q_BYTES;
+  const uint32_t kv_box = (uint32_t)g.s_pad * 128u;  // bytes of one [s_pad x 64] box
+  const uint32_t q_smem = base;                       // 2 buffers
+  const uint32_t k_smem = q_smem + 2 * ATT_Q_BYTES;
   const uint32_t v_smem = k_smem + ATT_KV_BYTES;
-  const uint32_t p_smem = v_smem + ATT_KV_BYTES;
-  const uint32_t bar_base = p_smem + ATT_P_BYTES;
-  const uint32_t kv_bar = bar_base, q_bar = bar_base + 8, s_full = bar_base + 16, p_ready = bar_base + 24,
-                 o_full = bar_base + 32, tmem_slot = bar_base + 40;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + ATT_Q_BYTES + 2 * ATT_KV_BYTES + ATT_P_BYTES + 40);
-  uint8_t* p_ptr = base_ptr + ATT_Q_BYTES + 2 * ATT_KV_BYTES;
+  const uint32_t o_smem = v_smem + ATT_KV_BYTES;
+  const uint32_t bar_base = o_smem + ATT_STAGING_BYTES;
+  const uint32_t k_full = bar_base, k_free = bar_base + 8, v_full = bar_base + 16, v_free = bar_base + 24;
+  auto q_full = [&](int b) { return bar_base + 32 + 8 * b; };
+  auto q_free = [&](int b) { return bar_base + 48 + 8 * b; };
+  auto s_full = [&](int s) { return bar_base + 64 + 8 * s; };
+  auto p_ready = [&](int s) { return bar_base + 80 + 8 * s; };
+  auto o_full = [&](int s) { return bar_base + 96 + 8 * s; };
+  auto slot_free = [&](int s) { return bar_base + 112 + 8 * s; };
+  const uint32_t tmem_slot = bar_base + 128;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.x, seq = blockIdx.y;
-  const int row0 = seq * S;
-  const int n_qt = (S + 127) / 128;
 
-  if (warp == 4 && elect_one()) {
+  // contiguous, balanced range of work items of this CTA
+  const int per = g.n_items / (int)gridDim.x, extra = g.n_items % (int)gridDim.x;
+  const int i0 = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
+  const int i1 = i0 + per + ((int)blockIdx.x < extra ? 1 : 0);
+
+  if (warp == 0 && elect_one()) {
     prefetch_tensormap(&tmap_q);
     prefetch_tensormap(&tmap_kv);
-    mbar_init(kv_bar, 1);
-    mbar_init(q_bar, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
-    mbar_init(o_full, 1);
+    prefetch_tensormap(&tmap_o);
+    mbar_init(k_full, 1);
+    mbar_init(k_free, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_free, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(q_full(b), 1);
+      mbar_init(q_free(b), 1);
+      mbar_init(s_full(b), 1);
+      mbar_init(p_ready(b), 128);
+      mbar_init(o_full(b), 1);
+      mbar_init(slot_free(b), 128);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == 1) {
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
     tmem_relinquish();
   }
@@ -71,114 +100,211 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const int p_cols = g.s_pad / 2;  // P: two bf16 per 32-bit column; O starts right behind it
 
-  if (warp == 4) {
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
     if (elect_one()) {
-      // K and V: two 64-column boxes each
-      mbar_expect_tx(kv_bar, 4 * kv_box);
-      for (int kc = 0; kc < 2; ++kc) {
-        tma_load_2d(k_smem + kc * kv_box, &tmap_kv, kv_bar, d_model + head * ATT_DH + kc * 64, row0);
-        tma_load_2d(v_smem + kc * kv_box, &tmap_kv, kv_bar, 2 * d_model + head * ATT_DH + kc * 64, row0);
-      }
-      const uint32_t idesc_qk = make_idesc_bf16(128, s_pad, 0);
-      const uint32_t idesc_pv = make_idesc_bf16(128, ATT_DH, 1);
-      for (int qt = 0; qt < n_qt; ++qt) {
-        const uint32_t par = qt & 1;
-        // the previous tile's QK^T has been consumed (p_ready implies s_full), Q smem is free
-        mbar_expect_tx(q_bar, ATT_Q_BYTES);
+      int n_units = 0;
+      auto load_q = [&](int it) {
+        const int j = it - i0, qb = j & 1;
+        const int unit = it / g.n_qt, qt = it - unit * g.n_qt;
+        const int seq = unit / g.n_heads, head = unit - seq * g.n_heads;
+        mbar_wait(q_free(qb), ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(q_full(qb), ATT_Q_BYTES);
         for (int kc = 0; kc < 2; ++kc)
-          tma_load_2d(q_smem + kc * 16384, &tmap_q, q_bar, head * ATT_DH + kc * 64, row0 + qt * 128);
-        if (qt == 0) mbar_wait(kv_bar, 0);
-        mbar_wait(q_bar, par);
+          tma_load_3d(q_smem + qb * ATT_Q_BYTES + kc * 16384, &tmap_q, q_full(qb), head * ATT_DH + kc * 64, qt * 128, seq);
+      };
+      int q_loaded = i0;  // items < q_loaded have their Q load issued
+      for (int it = i0; it < i1; ++it) {
+        const int unit = it / g.n_qt, qt = it - unit * g.n_qt;
+        const int seq = unit / g.n_heads, head = unit - seq * g.n_heads;
+        const bool new_unit = (it == i0) || qt == 0;
+        if (new_unit) {
+          mbar_wait(k_free, (n_units & 1) ^ 1);
+          mbar_expect_tx(k_full, 2 * kv_box);
+          for (int kc = 0; kc < 2; ++kc)
+            tma_load_3d(k_smem + kc * kv_box, &tmap_kv, k_full, g.d_model + head * ATT_DH + kc * 64, 0, seq);
+        }
+        if (q_loaded <= it) load_q(q_loaded++);
+        if (new_unit) {
+          // the second query tile of this unit does not depend on V's buffer: issue it before waiting for v_free
+          if (q_loaded == it + 1 && it + 1 < i1 && qt + 1 < g.n_qt) load_q(q_loaded++);
+          mbar_wait(v_free, (n_units & 1) ^ 1);
+          mbar_expect_tx(v_full, 2 * kv_box);
+          for (int kc = 0; kc < 2; ++kc)
+            tma_load_3d(v_smem + kc * kv_box, &tmap_kv, v_full, 2 * g.d_model + head * ATT_DH + kc * 64, 0, seq);
+          ++n_units;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc_qk = make_idesc_bf16(128, g.s_pad, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, ATT_DH, 1);
+      int k_units = 0, v_units = 0;  // units whose K / V has been waited for
+      auto is_new_unit = [&](int it) { return it == i0 || (it % g.n_qt) == 0; };
+      auto is_last_of_unit = [&](int it) { return it == i1 - 1 || ((it + 1) % g.n_qt) == 0; };
+      auto issue_qk = [&](int it) {
+        const int j = it - i0, slot = j & 1, qb = j & 1;
+        if (is_new_unit(it)) {
+          mbar_wait(k_full, k_units & 1);
+          ++k_units;
+        }
+        mbar_wait(q_full(qb), (j >> 1) & 1);
+        mbar_wait(slot_free(slot), ((j >> 1) & 1) ^ 1);  // O of item j-2 has been read out of this slot
         tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(slot * ATT_SLOT_COLS);
 #pragma unroll
         for (int ks = 0; ks < ATT_DH / 16; ++ks) {
           const int kc = ks >> 2, k4 = ks & 3;
-          const uint64_t adesc = make_smem_desc_sw128(q_smem + kc * 16384 + k4 * 32, 0, 1024);
+          const uint64_t adesc = make_smem_desc_sw128(q_smem + qb * ATT_Q_BYTES + kc * 16384 + k4 * 32, 0, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(k_smem + kc * kv_box + k4 * 32, 0, 1024);
-          mma_bf16_ss(tmem_base, adesc, bdesc, idesc_qk, ks != 0 ? 1u : 0u);
+          mma_bf16_ss(d, adesc, bdesc, idesc_qk, ks != 0 ? 1u : 0u);
         }
-        mma_commit(s_full);
-        // P V once the softmax threads have published P
-        mbar_wait(p_ready, par);
+        mma_commit(s_full(slot));
+        mma_commit(q_free(qb));
+        if (is_last_of_unit(it)) mma_commit(k_free);
+      };
+      auto issue_pv = [&](int it) {
+        const int j = it - i0, slot = j & 1;
+        mbar_wait(p_ready(slot), (j >> 1) & 1);
+        if (is_new_unit(it)) {
+          mbar_wait(v_full, v_units & 1);
+          ++v_units;
+        }
         tc_fence_after();
-        const int n_ks = s_pad / 16;
+        const uint32_t slot_base = tmem_base + (uint32_t)(slot * ATT_SLOT_COLS);
+        const int n_ks = g.s_pad / 16;
         for (int ks = 0; ks < n_ks; ++ks) {
-          const int kc = ks >> 2, k4 = ks & 3;
-          const uint64_t adesc = make_smem_desc_sw128(p_smem + kc * 16384 + k4 * 32, 0, 1024);
-          // V is [keys][dh]: N (=dh) contiguous -> MN-major B; 16 keys = 2 groups of 8 rows (SBO),
-          // the second 64 dh columns live in the next box (LBO)
+          // V is [keys][dh]: N (= dh) contiguous -> MN-major B; 16 keys = 2 groups of 8 rows (SBO), the second
+          // 64 dh columns live in the next box (LBO).  A = P: 16 keys = 8 packed columns per step.
           const uint64_t bdesc = make_smem_desc_sw128(v_smem + ks * 2048, kv_box, 1024);
-          mma_bf16_ss(tmem_base + ATT_O_COL, adesc, bdesc, idesc_pv, ks != 0 ? 1u : 0u);
+          mma_bf16_ts(slot_base + (uint32_t)p_cols, slot_base + (uint32_t)(ks * 8), bdesc, idesc_pv, ks != 0 ? 1u : 0u);
         }
-        mma_commit(o_full);
-        // Q smem is rewritten next iteration: QK^T of this tile completed long ago
-        // (s_full fired before p_ready), so no extra wait is needed.
+        mma_commit(o_full(slot));
+        if (is_last_of_unit(it)) mma_commit(v_free);
+      };
+      if (i0 < i1) issue_qk(i0);
+      for (int it = i0; it < i1; ++it) {
+        if (it + 1 < i1) issue_qk(it + 1);
+        issue_pv(it);
       }
     }
-  } else {
-    const int r = threadIdx.x;  // query row inside the tile, also the TMEM lane
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    for (int qt = 0; qt < n_qt; ++qt) {
-      const uint32_t par = qt & 1;
-      mbar_wait(s_full, par);
+  } else if (warp >= 4) {
+    // ------------------------------------------------ softmax / output groups
+    const int grp = (warp - 4) >> 2;  // 0: even items, 1: odd items
+    const int quad = warp & 3;
+    const int ew = warp - 4;
+    const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t my_box = o_smem + ew * 2 * ATT_OBOX_BYTES;
+    for (int it = i0 + grp; it < i1; it += 2) {
+      const int j = it - i0, slot = j & 1;
+      const uint32_t par = (j >> 1) & 1;
+      const int unit = it / g.n_qt, qt = it - unit * g.n_qt;
+      const int seq = unit / g.n_heads, head = unit - seq * g.n_heads;
+      const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(slot * ATT_SLOT_COLS);
+      const bool row_valid = qt * 128 + r < g.S;
+      const bool warp_valid = qt * 128 + quad * 32 < g.S;  // any valid row in this warp
+      mbar_wait(s_full(slot), par);
       tc_fence_after();
-      float mx = -INFINITY;
-      for (int c = 0; c < s_pad; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + lane_addr + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c + j < S) mx = fmaxf(mx, __uint_as_float(v[j]));
-      }
       float sum = 0.0f;
-      for (int c = 0; c < s_pad; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + lane_addr + c, v);
-        tmem_ld_wait();
-        float e[16];
+      if (warp_valid) {
+        float mx = -INFINITY;
+        for (int c = 0; c < g.s_pad; c += 32) {
+          if (c + 32 <= g.s_pad) {
+            uint32_t v[32];
+            tmem_ld32(s_addr + c, v);
+            tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          e[j] = (c + j < S) ? exp2f((__uint_as_float(v[j]) - mx) * scale_log2e) : 0.0f;
-          sum += e[j];
+            for (int k = 0; k < 32; ++k)
+              if (c + k < g.S) mx = fmaxf(mx, __uint_as_float(v[k]));
+          } else {
+            uint32_t v[16];
+            tmem_ld16(s_addr + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              if (c + k < g.S) mx = fmaxf(mx, __uint_as_float(v[k]));
+          }
         }
-        // two 16-byte chunks (8 keys each) of row r in key-chunk buffer kc, 128B-swizzled
-        const int kc = c >> 6, chunk = (c & 63) >> 3;
-        uint8_t* rowp = p_ptr + kc * 16384 + r * 128;
-        uint4 lo = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-        uint4 hi = make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
-        *reinterpret_cast<uint4*>(rowp + (((chunk) ^ (r & 7)) << 4)) = lo;
-        *reinterpret_cast<uint4*>(rowp + (((chunk + 1) ^ (r & 7)) << 4)) = hi;
+        const float moff = mx * g.scale_log2e;
+        for (int c = 0; c < g.s_pad; c += 32) {
+          if (c + 32 <= g.s_pad) {
+            uint32_t v[32];
+            tmem_ld32(s_addr + c, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+              const float e0 = (c + k < g.S) ? fast_exp2(fmaf(__uint_as_float(v[k]), g.scale_log2e, -moff)) : 0.0f;
+              const float e1 = (c + k + 1 < g.S) ? fast_exp2(fmaf(__uint_as_float(v[k + 1]), g.scale_log2e, -moff)) : 0.0f;
+              sum += e0 + e1;
+              pk[k >> 1] = pack_bf16x2(e0, e1);
+            }
+            tmem_st16(s_addr + (c >> 1), pk);
+          } else {
+            uint32_t v[16];
+            tmem_ld16(s_addr + c, v);
+            tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+              const float e0 = (c + k < g.S) ? fast_exp2(fmaf(__uint_as_float(v[k]), g.scale_log2e, -moff)) : 0.0f;
+              const float e1 = (c + k + 1 < g.S) ? fast_exp2(fmaf(__uint_as_float(v[k + 1]), g.scale_log2e, -moff)) : 0.0f;
+              sum += e0 + e1;
+              pk[k >> 1] = pack_bf16x2(e0, e1);
+            }
+            tmem_st8(s_addr + (c >> 1), pk);
+          }
+        }
+        tmem_st_wait();
       }
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      // a warp without any valid query row leaves S (all zeros: its Q rows are out of bounds) as "P"; its O rows are
+      // never stored
       tc_fence_before();
-      mbar_arrive(p_ready);
-      mbar_wait(o_full, par);
+      mbar_arrive(p_ready(slot));
+      mbar_wait(o_full(slot), par);
       tc_fence_after();
-      const float inv = 1.0f / sum;
-      const int q = qt * 128 + r;
-      for (int c = 0; c < ATT_DH; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_addr + ATT_O_COL + c, v);
-        tmem_ld_wait();
-        if (q < S) {
-          uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row0 + q) * d_model + head * ATT_DH + c);
+      if (warp_valid) {
+        const float inv = row_valid ? 1.0f / sum : 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < ATT_DH; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(s_addr + (uint32_t)(p_cols + c), v);
+          const int bx = (c >> 5) & 1;
+          if (lane == 0) bulk_wait_read_1();  // the store that last used this box has read it
+          __syncwarp();
+          tmem_ld_wait();
+          const uint32_t row_smem = my_box + bx * ATT_OBOX_BYTES + lane * 64;
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            dst[g] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
-                                pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
-                                pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
-                                pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
+          for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16-byte piece; 64B swizzle: piece ^ ((row >> 1) & 3)
+            const uint32_t* s = &v[q * 8];
+            sts128(row_smem + ((q ^ ((lane >> 1) & 3)) << 4),
+                   make_uint4(pack_bf16x2(__uint_as_float(s[0]) * inv, __uint_as_float(s[1]) * inv),
+                              pack_bf16x2(__uint_as_float(s[2]) * inv, __uint_as_float(s[3]) * inv),
+                              pack_bf16x2(__uint_as_float(s[4]) * inv, __uint_as_float(s[5]) * inv),
+                              pack_bf16x2(__uint_as_float(s[6]) * inv, __uint_as_float(s[7]) * inv)));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_o, my_box + bx * ATT_OBOX_BYTES, head * ATT_DH + c, qt * 128 + quad * 32, seq);
+            bulk_commit_group();
+          }
         }
       }
       tc_fence_before();
+      mbar_arrive(slot_free(slot));
     }
+    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
@@ -191,19 +317,28 @@ int tc_attention(const TcAttnParams& p, cudaStream_t s) {
   const int s_pad = (p.S + 15) / 16 * 16;
   if (s_pad > ATT_MAX_SPAD)
     return fail(MST_ERR_UNSUPPORTED, "tc_attention: sequences longer than 208 tokens (T > 207) are not supported");
-  const uint64_t M = (uint64_t)p.n_seqs * p.S;
-  CUtensorMap tq, tkv;
+  const uint64_t ld = 3 * (uint64_t)p.d_model;
+  CUtensorMap tq, tkv, to;
   int rc;
-  if ((rc = make_tmap_bf16(&tq, p.qkv, M, 3 * (uint64_t)p.d_model, 3 * (uint64_t)p.d_model, 128, 64))) return rc;
-  if ((rc = make_tmap_bf16(&tkv, p.qkv, M, 3 * (uint64_t)p.d_model, 3 * (uint64_t)p.d_model, (uint32_t)s_pad, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tq, p.qkv, p.n_seqs, p.S, ld, ld, (uint64_t)p.S * ld, 128, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tkv, p.qkv, p.n_seqs, p.S, ld, ld, (uint64_t)p.S * ld, (uint32_t)s_pad, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_3d(&to, p.out, p.n_seqs, p.S, p.d_model, p.d_model, (uint64_t)p.S * p.d_model, 32, 32, 64)))
+    return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     attr_set = true;
   }
-  const float scale_log2e = 1.4426950408889634f / sqrtf((float)ATT_DH);
-  dim3 grid(p.n_heads, p.n_seqs);
-  tc_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tkv, p.out, p.S, s_pad, p.d_model, scale_log2e);
+  AttnGeom g;
+  g.S = p.S;
+  g.s_pad = s_pad;
+  g.n_qt = (p.S + 127) / 128;
+  g.n_heads = p.n_heads;
+  g.n_items = p.n_seqs * p.n_heads * g.n_qt;
+  g.d_model = p.d_model;
+  g.scale_log2e = 1.4426950408889634f / sqrtf((float)ATT_DH);
+  const int grid = g.n_items < sm_count() ? g.n_items : sm_count();
+  tc_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tkv, to, g);
   MST_LAUNCHED("tc_attention", s);
   return MST_OK;
 }

@@ -29,8 +29,11 @@
 #include "tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <string.h>
+
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 namespace mst {
 
@@ -777,6 +780,52 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
   {
     std::lock_guard<std::mutex> lk(mu);
     cache[key] = m;
+  }
+  *out = m;
+  return MST_OK;
+}
+
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t n_outer, uint64_t rows, uint64_t cols,
+                      uint64_t row_stride_elems, uint64_t outer_stride_elems, uint32_t box_rows, uint32_t box_cols,
+                      int swizzle_bytes) {
+  static std::mutex mu;
+  struct Key3 {
+    const void* base;
+    uint64_t v[5];
+    uint32_t b[3];
+    bool operator==(const Key3& o) const {
+      return base == o.base && !memcmp(v, o.v, sizeof(v)) && !memcmp(b, o.b, sizeof(b));
+    }
+  };
+  static std::vector<std::pair<Key3, CUtensorMap>> cache;  // a handful of entries per process
+  Key3 key{base, {n_outer, rows, cols, row_stride_elems, outer_stride_elems}, {box_rows, box_cols, (uint32_t)swizzle_bytes}};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& kv : cache)
+      if (kv.first == key) {
+        *out = kv.second;
+        return MST_OK;
+      }
+  }
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return fail(MST_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride_elems * 2) % 16 != 0 || (outer_stride_elems * 2) % 16 != 0)
+    return fail(MST_ERR_INVALID, "make_tmap_bf16_3d: base and strides must be 16-byte aligned");
+  if (!((swizzle_bytes == 128 && box_cols == 64) || (swizzle_bytes == 64 && box_cols == 32)))
+    return fail(MST_ERR_INVALID, "make_tmap_bf16_3d: box width must equal the swizzle span");
+  cuuint64_t dims[3] = {cols, rows, n_outer};
+  cuuint64_t strides[2] = {row_stride_elems * 2, outer_stride_elems * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MST_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with code " + std::to_string((int)r));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 256) cache.clear();
+    cache.emplace_back(key, m);
   }
   *out = m;
   return MST_OK;
