@@ -81,6 +81,18 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+// two bf16 (packed in 32 bits) -> two fp32 (packed in 64 bits): shift / mask, no conversion instruction
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t u) { return pk2u(u << 16, u & 0xffff0000u); }
 __device__ __forceinline__ void gelu2(float& x0, float& x1) {
   const float kC[9] = {1.1283629389e+00f, -3.7581860120e-01f, 1.1186250267e-01f, -2.5649613612e-02f, 4.4378622868e-03f,
                        -5.5355724174e-04f, 4.6147291864e-05f, -2.2677306229e-06f, 4.9182760725e-08f};
@@ -486,26 +498,28 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ---------------------------------------------------------------------------
 // out = LayerNorm(A W^T + bias + residual) * gamma + beta,  N = 512, bf16 out
 // (self_attn.out_proj + norm1, linear2 + norm2).
-// Cluster of 2 CTAs per 128-row block; CTA `rank` owns columns [256*rank, +256), so each CTA has two
-// accumulator stages and the MMAs of the next block overlap the normalisation.  Per epilogue warp: its
-// 32 rows x 128 columns; the residual arrives by TMA in the warp's two [32 x 64] boxes, the sum
-// acc + bias + residual stays in registers (fp32), the four partial (sum, sum of squares) of a row -
-// 2 CTAs x 2 column halves - meet through shared memory: local st.shared + mbarrier arrive, remote
-// st.async with transaction bytes on the peer's mbarrier (no cluster-scope fence anywhere).
+// Cluster of 4 CTAs per 256-row block: two cta_group::2 pairs, pair p = ranks {2p, 2p+1} owns columns
+// [256p, 256p+256) of all 256 rows, so every CTA holds a 128 x 256 fp32 accumulator twice (two TMEM stages: the
+// MMAs of the next block overlap the normalisation) and pulls only 32 KB per k-block through L2.
+// Per epilogue warp: its 32 rows x 128 columns; the residual arrives by TMA in the warp's two [32 x 64] boxes,
+// acc + bias + residual stays in registers (fp32), and the four partial (sum, sum of squares) of a row -
+// 2 pairs x 2 column halves - meet through shared memory: local st.shared + mbarrier arrive, remote st.async with
+// transaction bytes on the partner CTA's mbarrier (rank ^ 2 holds the same rows; no cluster-scope fence anywhere).
 // ---------------------------------------------------------------------------
 struct LnCfg {
   static constexpr int BN = 256;
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = 4;
   static constexpr int A_BYTES = BLOCK_M * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = (BN / 2) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EXCH_BYTES = 2 * 4 * BLOCK_M * 8;      // [parity][source = 2*cta + half][row] float2
+  static constexpr int EXCH_BYTES = 2 * 4 * BLOCK_M * 8;      // [parity][source = 2*pair + half][row] float2
+  static constexpr int PARAM_BYTES = 3 * BN * 4;              // bias | gamma | beta of this CTA's 256 columns
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + EXCH_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + EXCH_BYTES + PARAM_BYTES + BAR_BYTES;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                   const TcGemmParams p) {
@@ -517,9 +531,10 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
   const uint32_t io_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;
   const uint32_t exch_smem = io_smem + STAGING_BYTES;
-  Ring ring{base, exch_smem + Cfg::EXCH_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
+  const uint32_t par_smem = exch_smem + Cfg::EXCH_BYTES;
+  Ring ring{base, par_smem + Cfg::PARAM_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
   const uint32_t tmem_slot = ring.extra(0);
-  const uint32_t stats_bar = ring.extra(1);                   // 256 local arrivals + 2048 transaction bytes from the peer
+  const uint32_t stats_bar = ring.extra(1);                   // 256 local arrivals + 2048 transaction bytes from the partner
   auto res_full = [&](int e) { return ring.extra(2 + e); };  // residual boxes of epilogue warp e have landed
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
   const float2* exch_ptr = reinterpret_cast<const float2*>(base_ptr + (exch_smem - base));
@@ -527,7 +542,10 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const uint32_t pair = rank >> 1, mrank = rank & 1;  // column half / row half of the 256 x 512 block
+  const uint32_t leader_rank = rank & ~1u;
+  const bool leader = mrank == 0;
+  const int cluster_id = blockIdx.x >> 2, n_clusters = gridDim.x >> 2;
 
   if (warp == 0 && elect_one()) {
     prefetch_tensormap(&tmap_a);
@@ -540,48 +558,77 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(ring.tfull(i), 1);
-      mbar_init(ring.tempty(i), NUM_EPI_THREADS);
+      mbar_init(ring.tempty(i), 2 * NUM_EPI_THREADS);
     }
     mbar_init(stats_bar, NUM_EPI_THREADS);
     for (int e = 0; e < NUM_EPI_WARPS; ++e) mbar_init(res_full(e), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  if (threadIdx.x < BN) {  // the epilogue reads its per-column parameters from shared memory (broadcast LDS.128)
+    float* par = reinterpret_cast<float*>(base_ptr + (par_smem - base));
+    const int c = (int)pair * BN + (int)threadIdx.x;
+    par[threadIdx.x] = p.bias[c];
+    par[BN + threadIdx.x] = p.ln_g[c];
+    par[2 * BN + threadIdx.x] = p.ln_b[c];
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // the peer's barriers are initialised before anything is signalled on them remotely
+  cluster_sync_all();  // every CTA's barriers are initialised before anything is signalled on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int m_blks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_pairs = (m_blks + 1) / 2;
   const int k_blks = p.K / BLOCK_K;
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int m_blk = cluster_id; m_blk < m_blks; m_blk += n_clusters) {
+      for (int mp = cluster_id; mp < m_pairs; mp += n_clusters) {
+        const int m_blk = 2 * mp + (int)mrank;
         for (int kb = 0; kb < k_blks; ++kb) {
           mbar_wait(ring.empty(stage), phase ^ 1);
-          mbar_expect_tx(ring.full(stage), Cfg::STAGE_BYTES);
-          tma_load_2d(ring.a(stage), &tmap_a, ring.full(stage), kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(ring.b(stage), &tmap_w, ring.full(stage), kb * BLOCK_K, (int)rank * BN);
+          const uint32_t full_leader = map_to_cta(ring.full(stage), leader_rank);
+          if (leader) mbar_expect_tx(ring.full(stage), 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2cta(ring.a(stage), &tmap_a, full_leader, kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d_2cta(ring.b(stage), &tmap_w, full_leader, kb * BLOCK_K, (int)pair * BN + (int)mrank * (BN / 2));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN, 0);
+      const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int m_blk = cluster_id; m_blk < m_blks; m_blk += n_clusters) {
-        mbar_wait(ring.tempty(acc), acc_phase ^ 1);
+      long long* dbg = (p.dbg && cluster_id == 0 && rank == 0) ? p.dbg + (1 * 2 + 0) * 1024 : nullptr;
+      int di = 0;
+      for (int mp = cluster_id; mp < m_pairs; mp += n_clusters) {
+        MST_DBG_STAMP();
+        mbar_wait_cluster(ring.tempty(acc), acc_phase ^ 1);
         tc_fence_after();
-        mma_tile<BN>(ring, tmem_base + (uint32_t)(acc * BN), k_blks, stage, phase);
-        mma_commit(ring.tfull(acc));
+        MST_DBG_STAMP();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait_cluster(ring.full(stage), phase);
+          tc_fence_after();
+          MST_DBG_STAMP();
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(ring.a(stage) + k * (UMMA_K * 2), 0, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(ring.b(stage) + k * (UMMA_K * 2), 0, 1024);
+            mma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          mma_commit_2cta(ring.empty(stage), pair_mask);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit_2cta(ring.tfull(acc), pair_mask);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -592,66 +639,89 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int half = ew >> 2;  // 128-column half of this CTA's 256 columns
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const int col0 = (int)rank * BN + half * 128;  // first global column of this thread's 128
+    const int col0 = (int)pair * BN + half * 128;  // first global column of this thread's 128
     const uint32_t my_box = io_smem + ew * 2 * WARP_BOX_BYTES;
     const uint32_t my_row = lane * 128;
-    const uint32_t peer_exch = map_to_cta(exch_smem, rank ^ 1);
-    const uint32_t peer_stats_bar = map_to_cta(stats_bar, rank ^ 1);
-    const int my_src = (int)rank * 2 + half;
-    if (lane == 0 && cluster_id < m_blks) {
+    const uint32_t partner = rank ^ 2u;  // the CTA holding the other 256 columns of the same rows
+    const uint32_t peer_exch = map_to_cta(exch_smem, partner);
+    const uint32_t peer_stats_bar = map_to_cta(stats_bar, partner);
+    const int my_src = (int)pair * 2 + half;
+    const int first_blk = 2 * cluster_id + (int)mrank;
+    if (lane == 0 && cluster_id < m_pairs) {
       mbar_expect_tx(res_full(ew), 2 * WARP_BOX_BYTES);
       for (int cc = 0; cc < 2; ++cc)
-        tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64, cluster_id * BLOCK_M + quad * 32);
+        tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64, first_blk * BLOCK_M + quad * 32);
     }
     int acc = 0, it = 0;
     uint32_t acc_phase = 0;
-    for (int m_blk = cluster_id; m_blk < m_blks; m_blk += n_clusters, ++it) {
+    long long* dbg = (p.dbg && cluster_id == 0 && warp == 2 && lane == 0 && rank < 2) ? p.dbg + (2 * 2 + rank) * 1024 : nullptr;
+    int di = 0;
+    for (int mp = cluster_id; mp < m_pairs; mp += n_clusters, ++it) {
+      const int m_blk = 2 * mp + (int)mrank;
       const uint32_t par = it & 1;
+      MST_DBG_STAMP();
       mbar_wait(ring.tfull(acc), acc_phase);
       tc_fence_after();
+      MST_DBG_STAMP();
       mbar_wait(res_full(ew), par);
-      float x[128];
-      float sum = 0.0f, sq = 0.0f;
+      MST_DBG_STAMP();
+      const uint32_t tempty_leader = map_to_cta(ring.tempty(acc), leader_rank);
+      // pass 1: x = acc + bias + residual (kept in registers as packed fp32 pairs), row sum and sum of squares on
+      // four independent packed accumulators (fma.rn.f32x2: two elements per instruction)
+      uint64_t x2[64];
+      uint64_t s2a = 0, s2b = 0, q2a = 0, q2b = 0;
+      const uint32_t bias_smem = par_smem + (uint32_t)(half * 128) * 4;
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {  // 32 accumulator columns at a time
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + half * 128 + c4 * 32), v);
-        tmem_ld_wait();
-        if (c4 == 3) {  // accumulator is in registers: release the TMEM stage before the normalisation
-          tc_fence_before();
-          mbar_arrive(ring.tempty(acc));
-        }
         const uint32_t row_smem = my_box + (c4 >> 1) * WARP_BOX_BYTES + my_row;
-        const float* bias = p.bias + col0 + c4 * 32;
+        uint4 rr[4], bb[8];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int j = (c4 & 1) * 4 + jj;  // 16-byte piece of the 128-byte staged row
-          const uint4 rr = lds128(row_smem + ((j ^ (lane & 7)) << 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * jj));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * jj + 4));
-          const uint32_t* s = &v[jj * 8];
-          const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z), r3 = unpack_bf16x2(rr.w);
-          float* xo = &x[c4 * 32 + jj * 8];
-          xo[0] = __uint_as_float(s[0]) + b0.x + r0.x; xo[1] = __uint_as_float(s[1]) + b0.y + r0.y;
-          xo[2] = __uint_as_float(s[2]) + b0.z + r1.x; xo[3] = __uint_as_float(s[3]) + b0.w + r1.y;
-          xo[4] = __uint_as_float(s[4]) + b1.x + r2.x; xo[5] = __uint_as_float(s[5]) + b1.y + r2.y;
-          xo[6] = __uint_as_float(s[6]) + b1.z + r3.x; xo[7] = __uint_as_float(s[7]) + b1.w + r3.y;
+          rr[jj] = lds128(row_smem + ((j ^ (lane & 7)) << 4));
+          bb[2 * jj] = lds128(bias_smem + (uint32_t)(c4 * 32 + jj * 8) * 4);
+          bb[2 * jj + 1] = lds128(bias_smem + (uint32_t)(c4 * 32 + jj * 8 + 4) * 4);
+        }
+        tmem_ld_wait();
+        if (c4 == 3) {  // accumulator is in registers: release the TMEM stage before the normalisation
+          tc_fence_before();
+          mbar_arrive_cluster_relaxed(tempty_leader);
+        }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            sum += xo[q];
-            sq = fmaf(xo[q], xo[q], sq);
-          }
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint32_t* a = &v[jj * 8];
+          uint64_t* xo = &x2[c4 * 16 + jj * 4];
+          xo[0] = add2(add2(pk2u(a[0], a[1]), pk2u(bb[2 * jj].x, bb[2 * jj].y)), bf16x2_to_f32x2(rr[jj].x));
+          xo[1] = add2(add2(pk2u(a[2], a[3]), pk2u(bb[2 * jj].z, bb[2 * jj].w)), bf16x2_to_f32x2(rr[jj].y));
+          xo[2] = add2(add2(pk2u(a[4], a[5]), pk2u(bb[2 * jj + 1].x, bb[2 * jj + 1].y)), bf16x2_to_f32x2(rr[jj].z));
+          xo[3] = add2(add2(pk2u(a[6], a[7]), pk2u(bb[2 * jj + 1].z, bb[2 * jj + 1].w)), bf16x2_to_f32x2(rr[jj].w));
+          s2a = add2(s2a, xo[0]); q2a = fma2(xo[0], xo[0], q2a);
+          s2b = add2(s2b, xo[1]); q2b = fma2(xo[1], xo[1], q2b);
+          s2a = add2(s2a, xo[2]); q2a = fma2(xo[2], xo[2], q2a);
+          s2b = add2(s2b, xo[3]); q2b = fma2(xo[3], xo[3], q2b);
         }
       }
-      // row statistics: 4 partials per row (2 CTAs x 2 halves)
+      float sum, sq;
+      {
+        float a0, a1, b0, b1;
+        upk2(add2(s2a, s2b), a0, a1);
+        upk2(add2(q2a, q2b), b0, b1);
+        sum = a0 + a1;
+        sq = b0 + b1;
+      }
+      MST_DBG_STAMP();
+      // row statistics: 4 partials per row (2 pairs x 2 halves)
       const uint32_t slot = (uint32_t)(((par * 4 + my_src) * BLOCK_M + r) * 8);
       st_async_f32x2(peer_exch + slot, sum, sq, peer_stats_bar);
       asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(exch_smem + slot), "f"(sum), "f"(sq) : "memory");
       if (ew == 0 && lane == 0)
-        mbar_expect_tx(stats_bar, NUM_EPI_THREADS * 8);  // arrive + the peer's 256 x 8 bytes of this phase
+        mbar_expect_tx(stats_bar, NUM_EPI_THREADS * 8);  // arrive + the partner's 256 x 8 bytes of this phase
       else
         mbar_arrive(stats_bar);
       mbar_wait_cluster(stats_bar, par);
+      MST_DBG_STAMP();
       float tsum = 0.0f, tsq = 0.0f;
 #pragma unroll
       for (int src = 0; src < 4; ++src) {
@@ -662,42 +732,50 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const float mean = tsum * (1.0f / LN_N);
       const float var = fmaxf(tsq * (1.0f / LN_N) - mean * mean, 0.0f);
       const float rstd = rsqrtf(var + 1e-5f);
+      // pass 2: y = x * (rstd*g) + (b - mean*rstd*g), packed; each thread overwrites exactly the 16-byte pieces of the
+      // residual it read itself
+      const uint64_t rstd2 = pk2(rstd, rstd), nmean2 = pk2(-mean, -mean);
+      const uint32_t g_smem = par_smem + (uint32_t)(BN + half * 128) * 4, b_smem = par_smem + (uint32_t)(2 * BN + half * 128) * 4;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const uint32_t row_smem = my_box + cc * WARP_BOX_BYTES + my_row;
-        const float* g = p.ln_g + col0 + cc * 64;
-        const float* bt = p.ln_b + col0 + cc * 64;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + 8 * j));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 8 * j + 4));
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(bt + 8 * j));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(bt + 8 * j + 4));
-          const float* xi = &x[cc * 64 + j * 8];
-          const float y0 = fmaf((xi[0] - mean) * rstd, g0.x, t0.x), y1 = fmaf((xi[1] - mean) * rstd, g0.y, t0.y);
-          const float y2 = fmaf((xi[2] - mean) * rstd, g0.z, t0.z), y3 = fmaf((xi[3] - mean) * rstd, g0.w, t0.w);
-          const float y4 = fmaf((xi[4] - mean) * rstd, g1.x, t1.x), y5 = fmaf((xi[5] - mean) * rstd, g1.y, t1.y);
-          const float y6 = fmaf((xi[6] - mean) * rstd, g1.z, t1.z), y7 = fmaf((xi[7] - mean) * rstd, g1.w, t1.w);
-          // each thread overwrites exactly the 16-byte pieces of the residual it read itself
-          sts128(row_smem + ((j ^ (lane & 7)) << 4),
-                 make_uint4(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7)));
+          const uint4 g0 = lds128(g_smem + (uint32_t)(cc * 64 + j * 8) * 4), g1 = lds128(g_smem + (uint32_t)(cc * 64 + j * 8 + 4) * 4);
+          const uint4 t0 = lds128(b_smem + (uint32_t)(cc * 64 + j * 8) * 4), t1 = lds128(b_smem + (uint32_t)(cc * 64 + j * 8 + 4) * 4);
+          const uint64_t* xi = &x2[cc * 32 + j * 4];
+          const uint64_t gg[4] = {pk2u(g0.x, g0.y), pk2u(g0.z, g0.w), pk2u(g1.x, g1.y), pk2u(g1.z, g1.w)};
+          const uint64_t tt[4] = {pk2u(t0.x, t0.y), pk2u(t0.z, t0.w), pk2u(t1.x, t1.y), pk2u(t1.z, t1.w)};
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint64_t a = mul2(gg[q], rstd2);
+            const uint64_t y = fma2(xi[q], a, fma2(a, nmean2, tt[q]));
+            float y0, y1;
+            upk2(y, y0, y1);
+            o[q] = pack_bf16x2(y0, y1);
+          }
+          sts128(row_smem + ((j ^ (lane & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
+      MST_DBG_STAMP();
       if (lane == 0) {
         for (int cc = 0; cc < 2; ++cc)
           tma_store_2d(&tmap_out, my_box + cc * WARP_BOX_BYTES, col0 + cc * 64, m_blk * BLOCK_M + quad * 32);
         bulk_commit_group();
-        const int next = m_blk + n_clusters;
-        if (next < m_blks) {
+        const int next_mp = mp + n_clusters;
+        if (next_mp < m_pairs) {
           bulk_wait_read_all();  // the stores have read the boxes: they can take the next block's residual
           mbar_expect_tx(res_full(ew), 2 * WARP_BOX_BYTES);
           for (int cc = 0; cc < 2; ++cc)
-            tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64, next * BLOCK_M + quad * 32);
+            tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64,
+                        (2 * next_mp + (int)mrank) * BLOCK_M + quad * 32);
         }
       }
       __syncwarp();
+      MST_DBG_STAMP();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -706,10 +784,10 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // no CTA exits while its peer may still write statistics into its shared memory
+  cluster_sync_all();  // no CTA exits while a partner may still write statistics into its shared memory
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -878,7 +956,7 @@ static int launch_gemm_ln(const TcGemmParams& p, cudaStream_t s) {
   CUtensorMap ta, tw, tr, to;
   int rc;
   if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
-  if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN, BLOCK_K))) return rc;
+  if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN / 2, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tr, p.residual, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, 32, 64))) return rc;
   if ((rc = make_tmap_bf16(&to, p.out, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, 32, 64))) return rc;
   static bool attr_set = false;
@@ -886,10 +964,10 @@ static int launch_gemm_ln(const TcGemmParams& p, cudaStream_t s) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int m_blks = ceil_div(p.M, BLOCK_M);
-  const int max_clusters = sm_count() / 2;
-  const int clusters = m_blks < max_clusters ? m_blks : max_clusters;
-  tc_gemm_ln_kernel<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, tr, to, p);
+  const int m_pairs = ceil_div(ceil_div(p.M, BLOCK_M), 2);
+  const int max_clusters = sm_count() / 4;
+  const int clusters = m_pairs < max_clusters ? m_pairs : max_clusters;
+  tc_gemm_ln_kernel<<<4 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, tr, to, p);
   MST_LAUNCHED("tc_gemm_res_ln", s);
   return MST_OK;
 }

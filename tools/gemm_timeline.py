@@ -36,7 +36,28 @@ for _ in range(10):
     run()
 e1.record()
 torch.cuda.synchronize()
-print(f"epi={epi} m={m} n={n} k={k}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch")
+eager_us = e0.elapsed_time(e1) / 10 * 1e3
+# the same launches replayed from a CUDA graph: no host launch cost between kernels
+gr = torch.cuda.CUDAGraph()
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    s = side.cuda_stream
+    run()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(gr, stream=side):
+        for _ in range(20):
+            run()
+s = torch.cuda.current_stream().cuda_stream
+gr.replay()
+torch.cuda.synchronize()
+e0.record()
+gr.replay()
+e1.record()
+torch.cuda.synchronize()
+flops = 2.0 * m * n * k
+graph_us = e0.elapsed_time(e1) / 20 * 1e3
+print(f"epi={epi} m={m} n={n} k={k}: eager {eager_us:.1f} us, graph {graph_us:.1f} us per launch = {flops / graph_us / 1e6:.0f} TFLOP/s")
 dbg = torch.zeros(6 * 1024, dtype=torch.int64, device=dev)
 lib.mst_test_set_gemm_debug(dbg.data_ptr())
 run()
@@ -55,6 +76,15 @@ for i in range(0, len(mma), per):
     row = mma[i:i + per]
     print(f"  tile {i // per}: start {row[0]:7d} tempty+{row[1] - row[0]:5d} kblocks " + " ".join(f"{b - a_:4d}" for a_, b in zip(row[1:], row[2:])),
           f"| tile total {row[-1] - row[0]:6d}")
+if epi == 2:
+    print("LN epilogue (warp 2 lane 0) per tile: top | tfull wait | res wait | pass1 | stats exchange | pass2+fence | store+drain+next residual issue")
+    for r in range(2):
+        e = epi_t[r]
+        for i in range(0, len(e), 7):
+            q = e[i:i + 7]
+            if len(q) == 7:
+                print(f"  cta{r} tile {i // 7}: top {q[0]:7d} | " + " | ".join(f"{b - a_:5d}" for a_, b in zip(q, q[1:])) + f" | total {q[6] - q[1]:5d}")
+    sys.exit(0)
 print("epilogue (warp 2 lane 0) per tile: top | tfull wait | box0 free+ldtm | math0+sts | store0+box1 free+ldtm (tmem released) | math1+sts | store1 | total after tfull")
 for r in range(2):
     e = epi_t[r]
