@@ -123,8 +123,8 @@ def cpu_port_step_seconds(B, T, n_denoise, threads=None):
     p_sample update, B sequences of T frames, timed over `n_denoise` steps after one untimed step."""
     from oracle import denoiser as OD, sampler as OS, schedule as OSch
     from oracle.weights import mdm_state_dict
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores (torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is a single process)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     state = mdm_state_dict(F_FEATS, seed=0)
     g = torch.Generator().manual_seed(1)
     shape = (B, F_FEATS, 1, T)
@@ -327,9 +327,10 @@ def main():
         dist.destroy_process_group()
 
 
-def roofline_leg(K, model, dev, B, T, pk, ms_denoise_in_graph):
-    """Per-launch CUDA-event timing of one eager denoise step (forward with cond+uncond batched, then the fused
-    update) -> roofline of the dominant kernel family + the per-kernel table."""
+def roofline_leg(K, model, dev, B, T, pk, ms_denoise_in_graph, steady=True):
+    """Per-launch CUDA-event timing of one denoise step (forward with cond+uncond batched, then the fused update),
+    captured as a CUDA graph with an event after every kernel and replayed in steady state -> roofline of the
+    dominant kernel family + the per-kernel table (each entry = kernel time + the in-graph gap to the next one)."""
     from mst_b200 import _lib as L
     eng = model.mst_engine(dev)
     shape = (B, F_FEATS, 1, T)
@@ -352,12 +353,31 @@ def roofline_leg(K, model, dev, B, T, pk, ms_denoise_in_graph):
     for _ in range(3):
         step()
     torch.cuda.synchronize(dev)
+    # capture the step with an event-record node after every kernel, replay it long enough to reach the
+    # steady (power-capped) state of a real trajectory, then read the per-launch times of the last replays
     agg = {}
     reps = 5
-    for _ in range(reps):
-        with K.profile() as p:
-            step()
-        for name, ms in p.records:
+    if not steady:  # eager variant (for runs under ncu): events between eager launches
+        for _ in range(reps):
+            with K.profile() as p:
+                step()
+            for name, ms in p.records:
+                n, tot = agg.get(name, (0, 0.0))
+                agg[name] = (n + 1, tot + ms)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            with K.profile(deferred=True) as p:
+                step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for _ in range(300 if steady else 0):
+        graph.replay()
+    for _ in range(reps if steady else 0):
+        graph.replay()
+        torch.cuda.synchronize(dev)
+        for name, ms in p.collect():
             n, tot = agg.get(name, (0, 0.0))
             agg[name] = (n + 1, tot + ms)
     S, M = T + 1, 2 * B * (T + 1)
@@ -386,7 +406,7 @@ def roofline_leg(K, model, dev, B, T, pk, ms_denoise_in_graph):
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel<BN,EPI> (all epilogues)", "achieved": achieved,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
                 "peak_kind": f"{pk['src']} sustained cuBLAS bf16 (kernel timed inside a long step)", "traffic": None,
-                "share_of_step": ms / total, "eager_step_ms": total, "graph_step_ms": ms_denoise_in_graph}
+                "share_of_step": ms / total, "profiled_step_ms": total, "graph_step_ms": ms_denoise_in_graph}
     upd = [s for s in stages if s["kernel"] == "update"]
     if upd and roof is not None:
         by = 20 * B * F_FEATS * T  # out_c, out_u, x_t, x_inp read + x_{t-1} write, [F] mask, in-kernel Philox

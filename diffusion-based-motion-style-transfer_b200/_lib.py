@@ -25,7 +25,7 @@ MASK_NONE, MASK_FULL, MASK_FT, MASK_F = 0, 1, 2, 3
 
 # every symbol include/mst.h declares
 EXPORTED = [
-    "mst_version", "mst_last_error", "mst_launch_count", "mst_profile_begin", "mst_profile_end", "mst_device_info", "mst_abi_sizes", "mst_engine_create", "mst_engine_destroy",
+    "mst_version", "mst_last_error", "mst_launch_count", "mst_profile_begin", "mst_profile_end", "mst_profile_collect", "mst_device_info", "mst_abi_sizes", "mst_engine_create", "mst_engine_destroy",
     "mst_engine_packed_weight_bytes", "mst_engine_load_weights", "mst_engine_workspace_bytes", "mst_time_embed",
     "mst_text_embed", "mst_denoiser_forward", "mst_update_step", "mst_q_sample", "mst_cfg_combine",
     "mst_philox_normal", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
@@ -116,6 +116,7 @@ def _declare(lib):
         "mst_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "mst_profile_begin": [vp],
         "mst_profile_end": [C.POINTER(C.c_float), C.c_char_p, i32, sz, C.POINTER(i32)],
+        "mst_profile_collect": [C.POINTER(C.c_float), C.c_char_p, i32, sz, C.POINTER(i32)],
         "mst_abi_sizes": [C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)],
         "mst_engine_create": [C.POINTER(ModelDesc), C.POINTER(vp)],
         "mst_engine_destroy": [vp],

@@ -7,6 +7,7 @@
 #include "simt.cuh"
 #include "tc.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -32,16 +33,33 @@ struct Profile {
 };
 static thread_local Profile g_prof;
 
+// During stream capture an ordinary record is swallowed into the graph's internal dependencies; an EXTERNAL
+// record becomes an event-record node that updates the real event on every replay.
+static cudaError_t record_event(cudaEvent_t e, cudaStream_t s) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+    return cudaEventRecordWithFlags(e, s, cudaEventRecordExternal);
+  return cudaEventRecord(e, s);
+}
+
 void note_launch(const char* name, cudaStream_t s) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (g_prof.open && s == g_prof.stream) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) == cudaSuccess) {
-      cudaEventRecord(e, s);
+      record_event(e, s);
       g_prof.ev.push_back(e);
       g_prof.names.push_back(name);
     }
   }
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MST_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 int sm_count() {
@@ -140,26 +158,21 @@ extern "C" uint64_t mst_launch_count(void) { return g_launches.load(std::memory_
 
 extern "C" int mst_profile_begin(void* stream) {
   MST_CHECK_ARG(!g_prof.open, "a profile is already open on this thread");
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  MST_CUDA_OK(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
-  MST_CHECK_ARG(cs == cudaStreamCaptureStatusNone, "cannot profile inside CUDA-graph capture");
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
   g_prof.stream = (cudaStream_t)stream;
   g_prof.ev.clear();
   g_prof.names.clear();
   cudaEvent_t e;
   MST_CUDA_OK(cudaEventCreate(&e));
-  MST_CUDA_OK(cudaEventRecord(e, g_prof.stream));
+  MST_CUDA_OK(record_event(e, g_prof.stream));  // during stream capture: an external event-record node
   g_prof.ev.push_back(e);
   g_prof.open = true;
   return MST_OK;
 }
 
-extern "C" int mst_profile_end(float* ms, char* names, int32_t cap, size_t names_cap, int32_t* n_out) {
-  MST_CHECK_ARG(g_prof.open, "no profile is open on this thread");
-  MST_CHECK_ARG(n_out != nullptr, "null n_out");
-  g_prof.open = false;
+static int profile_collect(float* ms, char* names, int32_t cap, size_t names_cap, int32_t* n_out) {
   const int n = (int)g_prof.names.size();
-  cudaError_t err = cudaEventSynchronize(g_prof.ev.back());
+  cudaError_t err = g_prof.ev.empty() ? cudaSuccess : cudaEventSynchronize(g_prof.ev.back());
   size_t off = 0;
   if (names && names_cap) names[0] = 0;
   for (int i = 0; i < n && err == cudaSuccess; ++i) {
@@ -176,12 +189,26 @@ extern "C" int mst_profile_end(float* ms, char* names, int32_t cap, size_t names
       }
     }
   }
-  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
-  g_prof.ev.clear();
-  g_prof.names.clear();
   *n_out = n;
-  if (err != cudaSuccess) return fail(MST_ERR_CUDA, std::string("mst_profile_end: ") + cudaGetErrorString(err));
+  if (err != cudaSuccess) return fail(MST_ERR_CUDA, std::string("mst_profile: ") + cudaGetErrorString(err));
   return MST_OK;
+}
+
+extern "C" int mst_profile_end(float* ms, char* names, int32_t cap, size_t names_cap, int32_t* n_out) {
+  MST_CHECK_ARG(g_prof.open, "no profile is open on this thread");
+  g_prof.open = false;
+  if (!ms && !names) {  // deferred: the launches were captured into a CUDA graph; read after replaying it
+    if (n_out) *n_out = (int)g_prof.names.size();
+    return MST_OK;
+  }
+  MST_CHECK_ARG(n_out != nullptr, "null n_out");
+  return profile_collect(ms, names, cap, names_cap, n_out);
+}
+
+extern "C" int mst_profile_collect(float* ms, char* names, int32_t cap, size_t names_cap, int32_t* n_out) {
+  MST_CHECK_ARG(!g_prof.open, "close the profile with mst_profile_end first");
+  MST_CHECK_ARG(n_out != nullptr, "null n_out");
+  return profile_collect(ms, names, cap, names_cap, n_out);
 }
 
 extern "C" int mst_device_info(int* sm, int* cc_major, int* cc_minor) {

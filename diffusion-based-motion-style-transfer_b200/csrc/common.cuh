@@ -38,6 +38,34 @@ void note_launch(const char* name, cudaStream_t s);
     ::mst::note_launch((name), (stream));                                     \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every kernel of the denoise step is launched with programmaticStreamSerialization: its CTAs may be scheduled
+// (and run their prologue: barrier init, TMEM allocation, tensor-map prefetch) as soon as SMs drain from the
+// previous kernel; pdl_wait() then blocks until that kernel has completed and flushed its memory.  Without it
+// ~7 us of launch latency sat between consecutive kernels of the captured step (profiles/r01c_*).
+bool pdl_enabled();  // MST_PDL=0 switches it off
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

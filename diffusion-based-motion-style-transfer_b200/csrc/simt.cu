@@ -124,6 +124,8 @@ int gemm_f32(const GemmF32Params& p, cudaStream_t s) {
 // (mdm_forstyledataset.py:322-327, :344-345).  Writes fp32 and/or bf16.
 // ---------------------------------------------------------------------------
 __global__ void token0_kernel(Token0Params p) {
+  pdl_launch_dependents();
+  pdl_wait();  // *temb_row_dev is decremented by the previous step's update kernel
   const int seq = blockIdx.x;
   const int b = seq % p.B;
   const bool uncond = p.cfg ? (seq >= p.B) : (p.uncond != 0);
@@ -140,7 +142,7 @@ __global__ void token0_kernel(Token0Params p) {
 }
 
 int token0(const Token0Params& p, int n_seqs, cudaStream_t s) {
-  token0_kernel<<<n_seqs, 128, 0, s>>>(p);
+  MST_CUDA_OK(launch_pdl(token0_kernel, dim3(n_seqs), dim3(128), 0, s, p));
   MST_LAUNCHED("token0", s);
   return MST_OK;
 }

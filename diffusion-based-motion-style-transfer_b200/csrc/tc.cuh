@@ -29,6 +29,7 @@ struct TcGemmParams {
   // in/out projection geometry
   const float* pe = nullptr;
   int B = 0, T = 0, n_pass = 1, n_valid = 0;
+  int td_mode = 0;           // experiment knob (MST_TEARDOWN)
   long long* dbg = nullptr;  // test hook: clock64 timeline of cluster 0 (see mst_test_set_gemm_debug)
   float* out2 = nullptr;  // OUTPROJ: rows of sequences >= B go here (uncond pass)
 };

@@ -47,6 +47,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const __grid_constant__ CUtensorMap tmap_o, const AttnGeom g) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -99,6 +100,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // the QKV projection has completed
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int p_cols = g.s_pad / 2;  // P: two bf16 per 32-bit column; O starts right behind it
 
@@ -338,7 +340,7 @@ int tc_attention(const TcAttnParams& p, cudaStream_t s) {
   g.d_model = p.d_model;
   g.scale_log2e = 1.4426950408889634f / sqrtf((float)ATT_DH);
   const int grid = g.n_items < sm_count() ? g.n_items : sm_count();
-  tc_attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tq, tkv, to, g);
+  MST_CUDA_OK(launch_pdl(tc_attention_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, s, tq, tkv, to, g));
   MST_LAUNCHED("tc_attention", s);
   return MST_OK;
 }

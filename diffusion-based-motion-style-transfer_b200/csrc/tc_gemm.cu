@@ -29,6 +29,7 @@
 #include "tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -48,6 +49,35 @@ constexpr int GEMM_THREADS = 64 + NUM_EPI_THREADS;  // 320
 constexpr int LN_N = 512;                           // row width the LN epilogue is built for
 constexpr int WARP_BOX_BYTES = 32 * 128;            // one staged [32 rows x 64 bf16] box (a warp's rows of a 64-column chunk)
 constexpr int STAGING_BYTES = NUM_EPI_WARPS * 2 * WARP_BOX_BYTES;  // 64 KB: two boxes per epilogue warp
+
+#define MST_DBG_STAMP() do { if (dbg && di < 1000) dbg[di++] = clock64(); } while (0)
+// wall-clock (ns) of CTA entry (slot 0), end of work (slot 1) and last instruction (slot 2), per CTA
+#define MST_DBG_WALL(slot)                                                      \
+  do {                                                                          \
+    if (p.dbg && threadIdx.x == 0) {                                            \
+      unsigned long long gt_;                                                   \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                   \
+      p.dbg[6 * 1024 + 3 * blockIdx.x + (slot)] = (long long)gt_;               \
+    }                                                                           \
+  } while (0)
+// true end of a warp's work (no barrier in between: a timer read right after BAR.SYNC sees the ISSUE time of the
+// barrier, not its release) - atomicMax over the warps of the CTA
+#define MST_DBG_WALL_END()                                                      \
+  do {                                                                          \
+    if (p.dbg && lane == 0) {                                                   \
+      unsigned long long gt_;                                                   \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                   \
+      atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 6 * 1024 + 3 * blockIdx.x + 1), gt_); \
+    }                                                                           \
+  } while (0)
+#define MST_DBG_WALL_W1(slot)                                                   \
+  do {                                                                          \
+    if (p.dbg && threadIdx.x == 32) {                                           \
+      unsigned long long gt_;                                                   \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                   \
+      p.dbg[7 * 1024 + 2 * blockIdx.x + (slot)] = (long long)gt_;               \
+    }                                                                           \
+  } while (0)
 
 template <int BN>
 struct GemmCfg {
@@ -191,6 +221,8 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const TcGemmParams p) {
   using Cfg = GemmCfg<BN>;
+  pdl_launch_dependents();
+  MST_DBG_WALL(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -222,6 +254,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_blks = p.N / BN;
@@ -283,14 +316,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    MST_DBG_WALL_END();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (p.td_mode == 0) tc_fence_after();
+    MST_DBG_WALL_W1(0);
+    if (p.td_mode != 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    MST_DBG_WALL_W1(1);
   }
+  if (p.td_mode == 2 && warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  __syncthreads();
+  MST_DBG_WALL(2);
 }
 
 // ---------------------------------------------------------------------------
@@ -313,7 +352,6 @@ struct PairCfg {
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
 };
 
-#define MST_DBG_STAMP() do { if (dbg && di < 1000) dbg[di++] = clock64(); } while (0)
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -321,6 +359,8 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_out, const TcGemmParams p) {
   using Cfg = PairCfg;
   constexpr int BN = Cfg::BN;
+  pdl_launch_dependents();
+  MST_DBG_WALL(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -358,6 +398,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_blks = p.N / BN;
@@ -484,6 +525,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (acc == 0) acc_phase ^= 1;
     }
     if (lane == 0) bulk_wait_all();
+    MST_DBG_WALL_END();
   }
 
   tc_fence_before();
@@ -493,6 +535,8 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
   }
+  __syncthreads();
+  MST_DBG_WALL(2);
 }
 
 // ---------------------------------------------------------------------------
@@ -508,15 +552,18 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ---------------------------------------------------------------------------
 struct LnCfg {
   static constexpr int BN = 256;
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = 3;
   static constexpr int A_BYTES = BLOCK_M * 128;
   static constexpr int B_BYTES = (BN / 2) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EXCH_BYTES = 2 * 4 * BLOCK_M * 8;      // [parity][source = 2*pair + half][row] float2
   static constexpr int PARAM_BYTES = 3 * BN * 4;              // bias | gamma | beta of this CTA's 256 columns
+  static constexpr int OBOX_BYTES = 32 * 64;                  // output staging: [32 rows x 32 bf16], 64B swizzle
+  static constexpr int OUT_BYTES = NUM_EPI_WARPS * 2 * OBOX_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + EXCH_BYTES + PARAM_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES =
+      1024 + STAGES * STAGE_BYTES + STAGING_BYTES + OUT_BYTES + EXCH_BYTES + PARAM_BYTES + BAR_BYTES;
 };
 
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -525,12 +572,15 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const TcGemmParams p) {
   using Cfg = LnCfg;
   constexpr int BN = Cfg::BN;
+  pdl_launch_dependents();
+  MST_DBG_WALL(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
   const uint32_t io_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t exch_smem = io_smem + STAGING_BYTES;
+  const uint32_t out_smem = io_smem + STAGING_BYTES;  // residual boxes first, then the output boxes
+  const uint32_t exch_smem = out_smem + Cfg::OUT_BYTES;
   const uint32_t par_smem = exch_smem + Cfg::EXCH_BYTES;
   Ring ring{base, par_smem + Cfg::PARAM_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
   const uint32_t tmem_slot = ring.extra(0);
@@ -579,6 +629,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   cluster_sync_all();  // every CTA's barriers are initialised before anything is signalled on them remotely
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int m_blks = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -640,7 +691,8 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int col0 = (int)pair * BN + half * 128;  // first global column of this thread's 128
-    const uint32_t my_box = io_smem + ew * 2 * WARP_BOX_BYTES;
+    const uint32_t my_box = io_smem + ew * 2 * WARP_BOX_BYTES;   // residual: two [32 x 64] boxes
+    const uint32_t my_obox = out_smem + ew * 2 * Cfg::OBOX_BYTES;  // output: two [32 x 32] boxes, ping-pong
     const uint32_t my_row = lane * 128;
     const uint32_t partner = rank ^ 2u;  // the CTA holding the other 256 columns of the same rows
     const uint32_t peer_exch = map_to_cta(exch_smem, partner);
@@ -703,6 +755,18 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           s2b = add2(s2b, xo[3]); q2b = fma2(xo[3], xo[3], q2b);
         }
       }
+      // the residual boxes have been read: fetch the next block's residual now, it lands during the statistics
+      // exchange and the normalisation
+      __syncwarp();
+      if (lane == 0) {
+        const int next_mp = mp + n_clusters;
+        if (next_mp < m_pairs) {
+          mbar_expect_tx(res_full(ew), 2 * WARP_BOX_BYTES);
+          for (int cc = 0; cc < 2; ++cc)
+            tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64,
+                        (2 * next_mp + (int)mrank) * BLOCK_M + quad * 32);
+        }
+      }
       float sum, sq;
       {
         float a0, a1, b0, b1;
@@ -732,18 +796,20 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const float mean = tsum * (1.0f / LN_N);
       const float var = fmaxf(tsq * (1.0f / LN_N) - mean * mean, 0.0f);
       const float rstd = rsqrtf(var + 1e-5f);
-      // pass 2: y = x * (rstd*g) + (b - mean*rstd*g), packed; each thread overwrites exactly the 16-byte pieces of the
-      // residual it read itself
+      // pass 2: y = x * (rstd*g) + (b - mean*rstd*g), packed; 32 columns at a time through the two output boxes
       const uint64_t rstd2 = pk2(rstd, rstd), nmean2 = pk2(-mean, -mean);
       const uint32_t g_smem = par_smem + (uint32_t)(BN + half * 128) * 4, b_smem = par_smem + (uint32_t)(2 * BN + half * 128) * 4;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const uint32_t row_smem = my_box + cc * WARP_BOX_BYTES + my_row;
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const uint32_t box = my_obox + (c4 & 1) * Cfg::OBOX_BYTES;
+        if (lane == 0) bulk_wait_read_1();  // the store that last used this box has read it
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint4 g0 = lds128(g_smem + (uint32_t)(cc * 64 + j * 8) * 4), g1 = lds128(g_smem + (uint32_t)(cc * 64 + j * 8 + 4) * 4);
-          const uint4 t0 = lds128(b_smem + (uint32_t)(cc * 64 + j * 8) * 4), t1 = lds128(b_smem + (uint32_t)(cc * 64 + j * 8 + 4) * 4);
-          const uint64_t* xi = &x2[cc * 32 + j * 4];
+        for (int jj = 0; jj < 4; ++jj) {
+          const int col = c4 * 32 + jj * 8;
+          const uint4 g0 = lds128(g_smem + (uint32_t)col * 4), g1 = lds128(g_smem + (uint32_t)(col + 4) * 4);
+          const uint4 t0 = lds128(b_smem + (uint32_t)col * 4), t1 = lds128(b_smem + (uint32_t)(col + 4) * 4);
+          const uint64_t* xi = &x2[c4 * 16 + jj * 4];
           const uint64_t gg[4] = {pk2u(g0.x, g0.y), pk2u(g0.z, g0.w), pk2u(g1.x, g1.y), pk2u(g1.z, g1.w)};
           const uint64_t tt[4] = {pk2u(t0.x, t0.y), pk2u(t0.z, t0.w), pk2u(t1.x, t1.y), pk2u(t1.z, t1.w)};
           uint32_t o[4];
@@ -755,31 +821,23 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             upk2(y, y0, y1);
             o[q] = pack_bf16x2(y0, y1);
           }
-          sts128(row_smem + ((j ^ (lane & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(box + lane * 64 + ((jj ^ ((lane >> 1) & 3)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmap_out, box, col0 + c4 * 32, m_blk * BLOCK_M + quad * 32, 0);
+          bulk_commit_group();
         }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
       MST_DBG_STAMP();
-      if (lane == 0) {
-        for (int cc = 0; cc < 2; ++cc)
-          tma_store_2d(&tmap_out, my_box + cc * WARP_BOX_BYTES, col0 + cc * 64, m_blk * BLOCK_M + quad * 32);
-        bulk_commit_group();
-        const int next_mp = mp + n_clusters;
-        if (next_mp < m_pairs) {
-          bulk_wait_read_all();  // the stores have read the boxes: they can take the next block's residual
-          mbar_expect_tx(res_full(ew), 2 * WARP_BOX_BYTES);
-          for (int cc = 0; cc < 2; ++cc)
-            tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64,
-                        (2 * next_mp + (int)mrank) * BLOCK_M + quad * 32);
-        }
-      }
       __syncwarp();
       MST_DBG_STAMP();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (lane == 0) bulk_wait_all();
+    MST_DBG_WALL_END();
   }
 
   tc_fence_before();
@@ -789,6 +847,8 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
   }
+  __syncthreads();
+  MST_DBG_WALL(2);
 }
 
 // ---------------------------------------------------------------------------
@@ -923,11 +983,35 @@ static int launch_gemm(const TcGemmParams& p, cudaStream_t s) {
   }
   const int tiles = ceil_div(p.M, BLOCK_M) * (p.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  tc_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, p);
+  MST_CUDA_OK(launch_pdl(tc_gemm_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tw, p));
   static const char* const kNames[] = {"tc_gemm_qkv", "tc_gemm_ffn1_gelu", "tc_gemm_res_ln", "tc_gemm_inproj",
                                        "tc_gemm_outproj", "tc_gemm_f32"};
   MST_LAUNCHED(kNames[EPI], s);
   return MST_OK;
+}
+
+// Largest number of clusters of `cluster_size` CTAs that can be co-resident: with 4-CTA clusters only 132 of the
+// 148 SMs can be covered (GPC granularity), and a persistent kernel launched with more clusters than that runs
+// the surplus as a second wave - which doubled the LN GEMM's time before this cap (profiles/r01c_*).
+template <typename Kernel>
+static int max_active_clusters(Kernel kernel, int cluster_size, int threads, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster_size * (sm_count() / cluster_size));
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = cluster_size;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = (sm_count() / cluster_size) * 7 / 8;  // conservative fallback
+  }
+  return n;
 }
 
 template <int EPI>
@@ -944,9 +1028,9 @@ static int launch_gemm_pair(const TcGemmParams& p, cudaStream_t s) {
     attr_set = true;
   }
   const int tiles = ceil_div(ceil_div(p.M, BLOCK_M), 2) * (p.N / Cfg::BN);
-  const int max_clusters = sm_count() / 2;
+  static const int max_clusters = max_active_clusters(tc_gemm_pair_kernel<EPI>, 2, GEMM_THREADS, Cfg::SMEM_BYTES);
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  tc_gemm_pair_kernel<EPI><<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, to, p);
+  MST_CUDA_OK(launch_pdl(tc_gemm_pair_kernel<EPI>, dim3(2 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tw, to, p));
   MST_LAUNCHED(EPI == TC_EPI_BIAS_BF16 ? "tc_gemm_qkv" : "tc_gemm_ffn1_gelu", s);
   return MST_OK;
 }
@@ -958,16 +1042,17 @@ static int launch_gemm_ln(const TcGemmParams& p, cudaStream_t s) {
   if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN / 2, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tr, p.residual, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, 32, 64))) return rc;
-  if ((rc = make_tmap_bf16(&to, p.out, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, 32, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&to, p.out, 1, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, (uint64_t)p.M * LN_N, 32, 32, 64)))
+    return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int m_pairs = ceil_div(ceil_div(p.M, BLOCK_M), 2);
-  const int max_clusters = sm_count() / 4;
+  static const int max_clusters = max_active_clusters(tc_gemm_ln_kernel, 4, GEMM_THREADS, Cfg::SMEM_BYTES);
   const int clusters = m_pairs < max_clusters ? m_pairs : max_clusters;
-  tc_gemm_ln_kernel<<<4 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tw, tr, to, p);
+  MST_CUDA_OK(launch_pdl(tc_gemm_ln_kernel, dim3(4 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tw, tr, to, p));
   MST_LAUNCHED("tc_gemm_res_ln", s);
   return MST_OK;
 }
@@ -978,6 +1063,10 @@ void set_gemm_debug(long long* dev_buf) { g_gemm_dbg = dev_buf; }
 int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
   TcGemmParams p = p_in;
   p.dbg = g_gemm_dbg;
+  {
+    const char* e = getenv("MST_TEARDOWN");
+    p.td_mode = e ? atoi(e) : 0;
+  }
   MST_CHECK_ARG(p.a && p.w && p.bias && p.out, "null pointer");
   MST_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0, "empty problem");
   MST_CHECK_ARG(p.K % BLOCK_K == 0, "K must be a multiple of 64");
@@ -1012,6 +1101,8 @@ int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
 // x[b][f][t] fp32 -> a[(b*T + t)][f] bf16, columns [F, f_pad) zero.  32x32 smem transpose.
 __global__ void __launch_bounds__(256) motion_to_tokens_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a,
                                                                int F, int T, int f_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, f0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -1028,7 +1119,7 @@ __global__ void __launch_bounds__(256) motion_to_tokens_kernel(const float* __re
 
 int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T, int f_pad, cudaStream_t s) {
   dim3 grid(ceil_div(T, 32), ceil_div(f_pad, 32), B);
-  motion_to_tokens_kernel<<<grid, 256, 0, s>>>(x, a, F, T, f_pad);
+  MST_CUDA_OK(launch_pdl(motion_to_tokens_kernel, grid, dim3(256), 0, s, x, a, F, T, f_pad));
   MST_LAUNCHED("motion_to_tokens", s);
   return MST_OK;
 }

@@ -94,6 +94,8 @@ __device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(rei
 
 template <int SAMPLER, int NOISE, bool VEC4>
 __global__ void __launch_bounds__(256) update_kernel(mst_update_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t per = (int64_t)a.n_feats * a.n_frames;  // elements per sample
   const int T = a.n_frames;
   const bool has_u = a.out_uncond != nullptr;
@@ -200,9 +202,9 @@ static int launch_update(const mst_update_args& a, cudaStream_t s) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (vec)
-    update_kernel<SAMPLER, NOISE, true><<<(unsigned)blocks, threads, 0, s>>>(a);
+    MST_CUDA_OK(launch_pdl(update_kernel<SAMPLER, NOISE, true>, dim3((unsigned)blocks), dim3(threads), 0, s, a));
   else
-    update_kernel<SAMPLER, NOISE, false><<<(unsigned)blocks, threads, 0, s>>>(a);
+    MST_CUDA_OK(launch_pdl(update_kernel<SAMPLER, NOISE, false>, dim3((unsigned)blocks), dim3(threads), 0, s, a));
   MST_LAUNCHED("update", s);
   return MST_OK;
 }

@@ -274,18 +274,31 @@ class profile:
     """``with profile() as p: ...`` -> ``p.records`` = [(kernel name, ms)] for every launch the block made
     through the library on the current stream (CUDA events between launches; synchronises on exit)."""
 
-    def __init__(self, cap: int = 4096):
-        self.cap, self.records = cap, []
+    def __init__(self, cap: int = 4096, deferred: bool = False):
+        """deferred=True: the block is being captured into a CUDA graph; call ``collect()`` after replaying it."""
+        self.cap, self.records, self.deferred = cap, [], deferred
 
     def __enter__(self):
         L.check(L.load().mst_profile_begin(_stream_ptr()), "mst_profile_begin")
         return self
 
-    def __exit__(self, *exc):
+    def _read(self, fn, what):
         ms = (C.c_float * self.cap)()
         names = C.create_string_buffer(self.cap * 32)
         n = C.c_int32()
-        L.check(L.load().mst_profile_end(ms, names, self.cap, len(names), C.byref(n)), "mst_profile_end")
+        L.check(fn(ms, names, self.cap, len(names), C.byref(n)), what)
         nm = names.value.decode().split("\n")[:-1]
         self.records = [(nm[i] if i < len(nm) else "?", float(ms[i])) for i in range(min(n.value, self.cap))]
+        return self.records
+
+    def __exit__(self, *exc):
+        if self.deferred:
+            n = C.c_int32()
+            L.check(L.load().mst_profile_end(None, None, 0, 0, C.byref(n)), "mst_profile_end")
+        else:
+            self._read(L.load().mst_profile_end, "mst_profile_end")
         return False
+
+    def collect(self):
+        """per-launch times of the most recent replay of the graph the block was captured into"""
+        return self._read(L.load().mst_profile_collect, "mst_profile_collect")

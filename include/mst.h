@@ -80,6 +80,11 @@ uint64_t mst_launch_count(void);
  * This is the live source of bench.py's roofline numbers.                   */
 int mst_profile_begin(void* stream);
 int mst_profile_end(float* ms, char* names, int32_t cap, size_t names_cap, int32_t* n);
+/* Deferred form for CUDA graphs: begin/end may bracket launches that are being CAPTURED (the events become
+ * event-record nodes); call mst_profile_end(NULL, NULL, 0, 0, &n), replay the graph as often as wanted, then
+ * mst_profile_collect reads the per-launch times of the LAST replay - kernel time plus the in-graph gap to
+ * the next kernel, in the thermal / power state of a long run.                                              */
+int mst_profile_collect(float* ms, char* names, int32_t cap, size_t names_cap, int32_t* n);
 
 /* sizeof() of the argument structs as this library was compiled - lets a
  * foreign-language binding verify its own struct layout (no GPU needed).   */

@@ -58,12 +58,42 @@ torch.cuda.synchronize()
 flops = 2.0 * m * n * k
 graph_us = e0.elapsed_time(e1) / 20 * 1e3
 print(f"epi={epi} m={m} n={n} k={k}: eager {eager_us:.1f} us, graph {graph_us:.1f} us per launch = {flops / graph_us / 1e6:.0f} TFLOP/s")
-dbg = torch.zeros(6 * 1024, dtype=torch.int64, device=dev)
+if epi == 2:
+    # gap between two consecutive launches inside one graph: wall-clock exit of launch 1 vs entry of launch 2
+    bufs = [torch.zeros(7 * 1024, dtype=torch.int64, device=dev) for _ in range(3)]
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        s = side.cuda_stream
+        with torch.cuda.graph(g2, stream=side):
+            for b in bufs:
+                lib.mst_test_set_gemm_debug(b.data_ptr())
+                run()
+        lib.mst_test_set_gemm_debug(None)
+    s = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        g2.replay()
+    torch.cuda.synchronize()
+    ws = []
+    for b in bufs:
+        w = b.cpu()[6 * 1024:6 * 1024 + 3 * 148].view(148, 3)
+        ws.append(w[w[:, 0] > 0])
+    t0g = int(ws[0][:, 0].min())
+    for i, w in enumerate(ws):
+        print(f"  launch {i}: first entry {int(w[:,0].min()) - t0g} ns, last entry {int(w[:,0].max()) - t0g}, first exit {int(w[:,1].min()) - t0g}, last exit {int(w[:,1].max()) - t0g}")
+dbg = torch.zeros(7 * 1024, dtype=torch.int64, device=dev)
 lib.mst_test_set_gemm_debug(dbg.data_ptr())
 run()
 torch.cuda.synchronize()
 lib.mst_test_set_gemm_debug(None)
-d = dbg.cpu().view(3, 2, 1024)
+if epi == 2:
+    w = dbg.cpu()[6 * 1024:6 * 1024 + 3 * 148].view(148, 3)
+    w = w[w[:, 0] > 0]
+    t_first = int(w[:, 0].min())
+    print(f"CTA wall-clock (ns since first CTA entry): entries min/median/max = {int(w[:,0].min()) - t_first}/{int(w[:,0].median()) - t_first}/{int(w[:,0].max()) - t_first}; "
+          f"exits min/median/max = {int(w[:,1].min()) - t_first}/{int(w[:,1].median()) - t_first}/{int(w[:,1].max()) - t_first}")
+    dur = (w[:, 1] - w[:, 0]).float()
+    print(f"  per-CTA duration ns: min {dur.min():.0f} median {dur.median():.0f} max {dur.max():.0f}; CTA0 {int(w[0,1]-w[0,0])}")
+d = dbg.cpu()[:6 * 1024 - 1024 * 0][:3 * 2 * 1024].view(3, 2, 1024)
 kb = k // 64
 t0 = int(d[1, 0, 0])
 rel = lambda v: int(v) - t0

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--frames", type=int, default=196)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--eager", action="store_true", help="eager launches only (use under ncu)")
     a = ap.parse_args()
     from mst_b200 import engine as K
     from mst_b200.model.mdm_forstyledataset import MDM
@@ -29,7 +30,7 @@ def main():
     model = MDM(load_clip=False, **mu.get_transfer_args(bench.Args()))
     model.mst_precision = a.precision
     model.to(dev).eval()
-    roof, stages = bench.roofline_leg(K, model, dev, a.batch, a.frames, bench.peaks(), 0.0)
+    roof, stages = bench.roofline_leg(K, model, dev, a.batch, a.frames, bench.peaks(), 0.0, steady=not a.eager)
     for s in stages:
         print(s)
     print(roof)
