@@ -36,7 +36,10 @@ constexpr int ATT_SLOT_COLS = 256;
 struct AttnGeom {
   int S, s_pad, n_qt, n_heads, n_items, d_model;
   float scale_log2e;
+  long long* dbg;  // developer hook (mst_test_set_gemm_debug): clock64 timeline of CTA 0
 };
+
+#define ATT_STAMP() do { if (dbg && di < 1000) dbg[di++] = clock64(); } while (0)
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -146,6 +149,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const uint32_t idesc_qk = make_idesc_bf16(128, g.s_pad, 0);
       const uint32_t idesc_pv = make_idesc_bf16(128, ATT_DH, 1);
       int k_units = 0, v_units = 0;  // units whose K / V has been waited for
+      long long* dbg = (g.dbg && blockIdx.x == 0) ? g.dbg + 1024 : nullptr;
+      int di = 0;
       auto is_new_unit = [&](int it) { return it == i0 || (it % g.n_qt) == 0; };
       auto is_last_of_unit = [&](int it) { return it == i1 - 1 || ((it + 1) % g.n_qt) == 0; };
       auto issue_qk = [&](int it) {
@@ -157,6 +162,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         mbar_wait(q_full(qb), (j >> 1) & 1);
         mbar_wait(slot_free(slot), ((j >> 1) & 1) ^ 1);  // O of item j-2 has been read out of this slot
         tc_fence_after();
+        ATT_STAMP();
         const uint32_t d = tmem_base + (uint32_t)(slot * ATT_SLOT_COLS);
 #pragma unroll
         for (int ks = 0; ks < ATT_DH / 16; ++ks) {
@@ -177,6 +183,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           ++v_units;
         }
         tc_fence_after();
+        ATT_STAMP();
         const uint32_t slot_base = tmem_base + (uint32_t)(slot * ATT_SLOT_COLS);
         const int n_ks = g.s_pad / 16;
         for (int ks = 0; ks < n_ks; ++ks) {
@@ -202,6 +209,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t my_box = o_smem + ew * 2 * ATT_OBOX_BYTES;
+    long long* dbg = (g.dbg && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0) ? g.dbg + (2 + grp) * 1024 : nullptr;
+    int di = 0;
     for (int it = i0 + grp; it < i1; it += 2) {
       const int j = it - i0, slot = j & 1;
       const uint32_t par = (j >> 1) & 1;
@@ -210,66 +219,123 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(slot * ATT_SLOT_COLS);
       const bool row_valid = qt * 128 + r < g.S;
       const bool warp_valid = qt * 128 + quad * 32 < g.S;  // any valid row in this warp
+      ATT_STAMP();
       mbar_wait(s_full(slot), par);
       tc_fence_after();
+      ATT_STAMP();
       float sum = 0.0f;
       if (warp_valid) {
-        float mx = -INFINITY;
-        for (int c = 0; c < g.s_pad; c += 32) {
-          if (c + 32 <= g.s_pad) {
-            uint32_t v[32];
-            tmem_ld32(s_addr + c, v);
-            tmem_ld_wait();
+        // Row softmax in two passes over the S row held in TMEM.  The chain LDTM -> wait -> math is latency-bound with
+        // one warp per scheduler, so: loads are double-buffered (the next 32 columns are in flight while the current
+        // 32 are processed), the running max / sum use four independent accumulators, and only the last (partial)
+        // chunk pays for the key mask.
+        const int n_full = g.S >> 5;                 // chunks of 32 keys that are entirely valid
+        const int tail0 = n_full << 5;               // first key of the masked tail
+        const int tail_w = g.s_pad - tail0;          // 0, 16 or 32 columns
+        uint32_t va[32], vb[32];
+        // ---- pass 1: row maximum
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        auto max32 = [&](const uint32_t (&v)[32]) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (c + k < g.S) mx = fmaxf(mx, __uint_as_float(v[k]));
-          } else {
-            uint32_t v[16];
-            tmem_ld16(s_addr + c, v);
+          for (int k = 0; k < 32; k += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[k]));
+            m1 = fmaxf(m1, __uint_as_float(v[k + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[k + 2]));
+            m3 = fmaxf(m3, __uint_as_float(v[k + 3]));
+          }
+        };
+        if (n_full > 0) tmem_ld32(s_addr, va);
+        for (int i = 0; i < n_full; i += 2) {
+          tmem_ld_wait();
+          if (i + 1 < n_full) tmem_ld32(s_addr + (i + 1) * 32, vb);
+          max32(va);
+          if (i + 1 < n_full) {
             tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-              if (c + k < g.S) mx = fmaxf(mx, __uint_as_float(v[k]));
+            if (i + 2 < n_full) tmem_ld32(s_addr + (i + 2) * 32, va);
+            max32(vb);
           }
         }
+        if (tail_w == 32) {
+          tmem_ld32(s_addr + tail0, va);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (tail0 + k < g.S) m0 = fmaxf(m0, __uint_as_float(va[k]));
+        } else if (tail_w == 16) {
+          uint32_t vt[16];
+          tmem_ld16(s_addr + tail0, vt);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (tail0 + k < g.S) m0 = fmaxf(m0, __uint_as_float(vt[k]));
+        }
+        ATT_STAMP();
+        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         const float moff = mx * g.scale_log2e;
-        for (int c = 0; c < g.s_pad; c += 32) {
-          if (c + 32 <= g.s_pad) {
-            uint32_t v[32];
-            tmem_ld32(s_addr + c, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
+        // ---- pass 2: p = exp2((s - max) * scale), row sum, bf16 P written back over S
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        auto exp32 = [&](const uint32_t (&v)[32], int c) {
+          uint32_t pk[16];
 #pragma unroll
-            for (int k = 0; k < 32; k += 2) {
-              const float e0 = (c + k < g.S) ? fast_exp2(fmaf(__uint_as_float(v[k]), g.scale_log2e, -moff)) : 0.0f;
-              const float e1 = (c + k + 1 < g.S) ? fast_exp2(fmaf(__uint_as_float(v[k + 1]), g.scale_log2e, -moff)) : 0.0f;
-              sum += e0 + e1;
-              pk[k >> 1] = pack_bf16x2(e0, e1);
-            }
-            tmem_st16(s_addr + (c >> 1), pk);
-          } else {
-            uint32_t v[16];
-            tmem_ld16(s_addr + c, v);
+          for (int k = 0; k < 32; k += 4) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[k]), g.scale_log2e, -moff));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[k + 1]), g.scale_log2e, -moff));
+            const float e2 = fast_exp2(fmaf(__uint_as_float(v[k + 2]), g.scale_log2e, -moff));
+            const float e3 = fast_exp2(fmaf(__uint_as_float(v[k + 3]), g.scale_log2e, -moff));
+            s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+            pk[k >> 1] = pack_bf16x2(e0, e1);
+            pk[(k >> 1) + 1] = pack_bf16x2(e2, e3);
+          }
+          tmem_st16(s_addr + (c >> 1), pk);
+        };
+        if (n_full > 0) tmem_ld32(s_addr, va);
+        for (int i = 0; i < n_full; i += 2) {
+          tmem_ld_wait();
+          if (i + 1 < n_full) tmem_ld32(s_addr + (i + 1) * 32, vb);
+          exp32(va, i * 32);
+          if (i + 1 < n_full) {
             tmem_ld_wait();
-            uint32_t pk[8];
-#pragma unroll
-            for (int k = 0; k < 16; k += 2) {
-              const float e0 = (c + k < g.S) ? fast_exp2(fmaf(__uint_as_float(v[k]), g.scale_log2e, -moff)) : 0.0f;
-              const float e1 = (c + k + 1 < g.S) ? fast_exp2(fmaf(__uint_as_float(v[k + 1]), g.scale_log2e, -moff)) : 0.0f;
-              sum += e0 + e1;
-              pk[k >> 1] = pack_bf16x2(e0, e1);
-            }
-            tmem_st8(s_addr + (c >> 1), pk);
+            if (i + 2 < n_full) tmem_ld32(s_addr + (i + 2) * 32, va);
+            exp32(vb, (i + 1) * 32);
           }
         }
+        if (tail_w == 32) {
+          tmem_ld32(s_addr + tail0, va);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const float e0 = (tail0 + k < g.S) ? fast_exp2(fmaf(__uint_as_float(va[k]), g.scale_log2e, -moff)) : 0.0f;
+            const float e1 = (tail0 + k + 1 < g.S) ? fast_exp2(fmaf(__uint_as_float(va[k + 1]), g.scale_log2e, -moff)) : 0.0f;
+            s0 += e0; s1 += e1;
+            pk[k >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st16(s_addr + (tail0 >> 1), pk);
+        } else if (tail_w == 16) {
+          uint32_t vt[16];
+          tmem_ld16(s_addr + tail0, vt);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int k = 0; k < 16; k += 2) {
+            const float e0 = (tail0 + k < g.S) ? fast_exp2(fmaf(__uint_as_float(vt[k]), g.scale_log2e, -moff)) : 0.0f;
+            const float e1 = (tail0 + k + 1 < g.S) ? fast_exp2(fmaf(__uint_as_float(vt[k + 1]), g.scale_log2e, -moff)) : 0.0f;
+            s0 += e0; s1 += e1;
+            pk[k >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st8(s_addr + (tail0 >> 1), pk);
+        }
+        sum = (s0 + s1) + (s2 + s3);
         tmem_st_wait();
       }
       // a warp without any valid query row leaves S (all zeros: its Q rows are out of bounds) as "P"; its O rows are
       // never stored
       tc_fence_before();
       mbar_arrive(p_ready(slot));
+      ATT_STAMP();
       mbar_wait(o_full(slot), par);
       tc_fence_after();
+      ATT_STAMP();
       if (warp_valid) {
         const float inv = row_valid ? 1.0f / sum : 0.0f;
 #pragma unroll 1
@@ -300,6 +366,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       tc_fence_before();
       mbar_arrive(slot_free(slot));
+      ATT_STAMP();
     }
     if (lane == 0) bulk_wait_all();
   }
@@ -311,6 +378,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
 }
+
+long long* attn_debug_ptr();  // tc_gemm.cu: the buffer set by mst_test_set_gemm_debug
 
 int tc_attention(const TcAttnParams& p, cudaStream_t s) {
   MST_CHECK_ARG(p.qkv && p.out, "null pointer");
@@ -339,6 +408,7 @@ int tc_attention(const TcAttnParams& p, cudaStream_t s) {
   g.n_items = p.n_seqs * p.n_heads * g.n_qt;
   g.d_model = p.d_model;
   g.scale_log2e = 1.4426950408889634f / sqrtf((float)ATT_DH);
+  g.dbg = attn_debug_ptr();
   const int grid = g.n_items < sm_count() ? g.n_items : sm_count();
   MST_CUDA_OK(launch_pdl(tc_attention_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, s, tq, tkv, to, g));
   MST_LAUNCHED("tc_attention", s);

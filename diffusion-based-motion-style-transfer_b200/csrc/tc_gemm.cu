@@ -1059,6 +1059,7 @@ static int launch_gemm_ln(const TcGemmParams& p, cudaStream_t s) {
 
 static long long* g_gemm_dbg = nullptr;
 void set_gemm_debug(long long* dev_buf) { g_gemm_dbg = dev_buf; }
+long long* attn_debug_ptr() { return g_gemm_dbg; }
 
 int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
   TcGemmParams p = p_in;

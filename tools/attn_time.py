@@ -35,3 +35,19 @@ torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / 20 * 1e3
 flops = n_seqs * 4 * 4.0 * S * S * 128
 print(f"attention n_seqs={n_seqs} S={S}: {us:.1f} us per launch = {flops / us / 1e6:.0f} TFLOP/s")
+
+dbg = torch.zeros(8 * 1024, dtype=torch.int64, device=dev)
+lib.mst_test_set_gemm_debug(dbg.data_ptr())
+L.check(lib.mst_test_attention_bf16(eng._h, qkv.data_ptr(), out.data_ptr(), n_seqs, S, None, 0, torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+lib.mst_test_set_gemm_debug(None)
+d = dbg.cpu().view(8, 1024)
+mma = [int(v) for v in d[1] if v != 0]
+t0 = mma[0]
+print("MMA thread stamps (QK issue / PV issue, in issue order), cycles since first:", [v - t0 for v in mma[:24]])
+for grp in range(2):
+    e = [int(v) - t0 for v in d[2 + grp] if v != 0]
+    print(f"softmax group {grp} (warp quad 0 lane 0): per item: top | s_full wait | pass1 (max) | pass2 (exp, P) | o_full wait | O drain+store")
+    for i in range(0, len(e) - 6, 7):
+        q = e[i:i + 7]
+        print(f"   item {i // 7}: top {q[0]:7d} | " + " | ".join(f"{b - a:5d}" for a, b in zip(q, q[1:])) + f" | total {q[6] - q[0]:6d}")
