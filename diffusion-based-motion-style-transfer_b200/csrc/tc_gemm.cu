@@ -552,7 +552,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ---------------------------------------------------------------------------
 struct LnCfg {
   static constexpr int BN = 256;
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = 5;  // ring slots shared by the k-blocks AND the two residual blocks of every tile
   static constexpr int A_BYTES = BLOCK_M * 128;
   static constexpr int B_BYTES = (BN / 2) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -562,8 +562,7 @@ struct LnCfg {
   static constexpr int OUT_BYTES = NUM_EPI_WARPS * 2 * OBOX_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES =
-      1024 + STAGES * STAGE_BYTES + STAGING_BYTES + OUT_BYTES + EXCH_BYTES + PARAM_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + EXCH_BYTES + PARAM_BYTES + BAR_BYTES;
 };
 
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -578,14 +577,17 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
-  const uint32_t io_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t out_smem = io_smem + STAGING_BYTES;  // residual boxes first, then the output boxes
+  const uint32_t out_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;  // per-warp output boxes
   const uint32_t exch_smem = out_smem + Cfg::OUT_BYTES;
   const uint32_t par_smem = exch_smem + Cfg::EXCH_BYTES;
   Ring ring{base, par_smem + Cfg::PARAM_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
   const uint32_t tmem_slot = ring.extra(0);
   const uint32_t stats_bar = ring.extra(1);                   // 256 local arrivals + 2048 transaction bytes from the partner
-  auto res_full = [&](int e) { return ring.extra(2 + e); };  // residual boxes of epilogue warp e have landed
+  // The residual tile of a block (128 rows x 256 columns = two ring slots of [128 x 64 | 128 x 64]) travels through the
+  // SAME ring as the k-blocks, right behind the block's last k-block: it is in flight while the MMAs finish and costs
+  // no dedicated staging memory.  Slot h of the two holds the columns of epilogue half h.
+  auto res_full = [&](int h) { return ring.extra(2 + h); };  // residual slot h has landed (local CTA, tx bytes)
+  auto res_free = [&](int h) { return ring.extra(4 + h); };  // ... and has been read by the 128 threads of half h
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
   const float2* exch_ptr = reinterpret_cast<const float2*>(base_ptr + (exch_smem - base));
 
@@ -611,7 +613,10 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_init(ring.tempty(i), 2 * NUM_EPI_THREADS);
     }
     mbar_init(stats_bar, NUM_EPI_THREADS);
-    for (int e = 0; e < NUM_EPI_WARPS; ++e) mbar_init(res_full(e), 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(res_full(h), 1);
+      mbar_init(res_free(h), NUM_EPI_THREADS / 2);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -640,16 +645,37 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      int owner[Cfg::STAGES] = {};  // h+1 while the slot holds residual half h that has not been waited free yet
+      int res_loads = 0;            // tiles whose residual has been issued
+      auto acquire = [&]() {        // the slot is free for a new load
+        if (owner[stage]) {
+          // its last occupant was a residual block: the epilogue (not the MMA) consumed it; this thread completes the
+          // slot's "empty" phase itself so that the ring's phase bookkeeping stays uniform
+          mbar_wait(res_free(owner[stage] - 1), (uint32_t)((res_loads - 1) & 1));
+          mbar_arrive(ring.empty(stage));
+          owner[stage] = 0;
+        }
+        mbar_wait(ring.empty(stage), phase ^ 1);
+      };
       for (int mp = cluster_id; mp < m_pairs; mp += n_clusters) {
         const int m_blk = 2 * mp + (int)mrank;
         for (int kb = 0; kb < k_blks; ++kb) {
-          mbar_wait(ring.empty(stage), phase ^ 1);
+          acquire();
           const uint32_t full_leader = map_to_cta(ring.full(stage), leader_rank);
           if (leader) mbar_expect_tx(ring.full(stage), 2 * Cfg::STAGE_BYTES);
           tma_load_2d_2cta(ring.a(stage), &tmap_a, full_leader, kb * BLOCK_K, m_blk * BLOCK_M);
           tma_load_2d_2cta(ring.b(stage), &tmap_w, full_leader, kb * BLOCK_K, (int)pair * BN + (int)mrank * (BN / 2));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
+        for (int h = 0; h < 2; ++h) {  // residual columns [256*pair + 128*h, +128) of this CTA's 128 rows
+          acquire();
+          mbar_expect_tx(res_full(h), Cfg::STAGE_BYTES);
+          tma_load_2d(ring.a(stage), &tmap_res, res_full(h), (int)pair * BN + h * 128, m_blk * BLOCK_M);
+          tma_load_2d(ring.b(stage), &tmap_res, res_full(h), (int)pair * BN + h * 128 + 64, m_blk * BLOCK_M);
+          owner[stage] = h + 1;
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        ++res_loads;
       }
     }
   } else if (warp == 1) {
@@ -657,7 +683,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN, 0);
       const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
       int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      uint32_t full_phase = 0, acc_phase = 0;  // bit s of full_phase: parity the next k-block in slot s completes
       long long* dbg = (p.dbg && cluster_id == 0 && rank == 0) ? p.dbg + (1 * 2 + 0) * 1024 : nullptr;
       int di = 0;
       for (int mp = cluster_id; mp < m_pairs; mp += n_clusters) {
@@ -667,7 +693,8 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         MST_DBG_STAMP();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < k_blks; ++kb) {
-          mbar_wait_cluster(ring.full(stage), phase);
+          mbar_wait_cluster(ring.full(stage), (full_phase >> stage) & 1u);
+          full_phase ^= 1u << stage;
           tc_fence_after();
           MST_DBG_STAMP();
 #pragma unroll
@@ -677,8 +704,10 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             mma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           mma_commit_2cta(ring.empty(stage), pair_mask);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == Cfg::STAGES) stage = 0;
         }
+        for (int h = 0; h < 2; ++h)  // the two residual slots of the tile: nothing to multiply
+          if (++stage == Cfg::STAGES) stage = 0;
         mma_commit_2cta(ring.tfull(acc), pair_mask);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -691,19 +720,12 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int col0 = (int)pair * BN + half * 128;  // first global column of this thread's 128
-    const uint32_t my_box = io_smem + ew * 2 * WARP_BOX_BYTES;   // residual: two [32 x 64] boxes
     const uint32_t my_obox = out_smem + ew * 2 * Cfg::OBOX_BYTES;  // output: two [32 x 32] boxes, ping-pong
-    const uint32_t my_row = lane * 128;
     const uint32_t partner = rank ^ 2u;  // the CTA holding the other 256 columns of the same rows
     const uint32_t peer_exch = map_to_cta(exch_smem, partner);
     const uint32_t peer_stats_bar = map_to_cta(stats_bar, partner);
     const int my_src = (int)pair * 2 + half;
-    const int first_blk = 2 * cluster_id + (int)mrank;
-    if (lane == 0 && cluster_id < m_pairs) {
-      mbar_expect_tx(res_full(ew), 2 * WARP_BOX_BYTES);
-      for (int cc = 0; cc < 2; ++cc)
-        tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64, first_blk * BLOCK_M + quad * 32);
-    }
+    const uint32_t my_row = (uint32_t)r * 128;  // this thread's row inside a [128 x 64] residual box
     int acc = 0, it = 0;
     uint32_t acc_phase = 0;
     long long* dbg = (p.dbg && cluster_id == 0 && warp == 2 && lane == 0 && rank < 2) ? p.dbg + (2 * 2 + rank) * 1024 : nullptr;
@@ -715,8 +737,10 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(ring.tfull(acc), acc_phase);
       tc_fence_after();
       MST_DBG_STAMP();
-      mbar_wait(res_full(ew), par);
+      mbar_wait(res_full(half), par);
       MST_DBG_STAMP();
+      // ring slot that holds this half's residual: the tile's k-blocks come first, then residual half 0, half 1
+      const uint32_t res_smem = ring.a((it * (k_blks + 2) + k_blks + half) % Cfg::STAGES);
       const uint32_t tempty_leader = map_to_cta(ring.tempty(acc), leader_rank);
       // pass 1: x = acc + bias + residual (kept in registers as packed fp32 pairs), row sum and sum of squares on
       // four independent packed accumulators (fma.rn.f32x2: two elements per instruction)
@@ -727,12 +751,12 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int c4 = 0; c4 < 4; ++c4) {  // 32 accumulator columns at a time
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + half * 128 + c4 * 32), v);
-        const uint32_t row_smem = my_box + (c4 >> 1) * WARP_BOX_BYTES + my_row;
+        const uint32_t row_smem = res_smem + (c4 >> 1) * Cfg::A_BYTES + my_row;  // columns 0-63 | 64-127 of the half
         uint4 rr[4], bb[8];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int j = (c4 & 1) * 4 + jj;  // 16-byte piece of the 128-byte staged row
-          rr[jj] = lds128(row_smem + ((j ^ (lane & 7)) << 4));
+          rr[jj] = lds128(row_smem + ((j ^ (r & 7)) << 4));
           bb[2 * jj] = lds128(bias_smem + (uint32_t)(c4 * 32 + jj * 8) * 4);
           bb[2 * jj + 1] = lds128(bias_smem + (uint32_t)(c4 * 32 + jj * 8 + 4) * 4);
         }
@@ -755,18 +779,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           s2b = add2(s2b, xo[3]); q2b = fma2(xo[3], xo[3], q2b);
         }
       }
-      // the residual boxes have been read: fetch the next block's residual now, it lands during the statistics
-      // exchange and the normalisation
-      __syncwarp();
-      if (lane == 0) {
-        const int next_mp = mp + n_clusters;
-        if (next_mp < m_pairs) {
-          mbar_expect_tx(res_full(ew), 2 * WARP_BOX_BYTES);
-          for (int cc = 0; cc < 2; ++cc)
-            tma_load_2d(my_box + cc * WARP_BOX_BYTES, &tmap_res, res_full(ew), col0 + cc * 64,
-                        (2 * next_mp + (int)mrank) * BLOCK_M + quad * 32);
-        }
-      }
+      mbar_arrive(res_free(half));  // the residual slot may be refilled
       float sum, sq;
       {
         float a0, a1, b0, b1;
@@ -1041,7 +1054,7 @@ static int launch_gemm_ln(const TcGemmParams& p, cudaStream_t s) {
   int rc;
   if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN / 2, BLOCK_K))) return rc;
-  if ((rc = make_tmap_bf16(&tr, p.residual, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, 32, 64))) return rc;
+  if ((rc = make_tmap_bf16(&tr, p.residual, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, BLOCK_M, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&to, p.out, 1, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, (uint64_t)p.M * LN_N, 32, 32, 64)))
     return rc;
   static bool attr_set = false;

@@ -248,6 +248,16 @@ __device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const CUtens
       : "memory");
 }
 
+// ... additionally written into the same shared-memory offset of every CTA in `cta_mask` (L2 is read once)
+__device__ __forceinline__ void tma_load_2d_2cta_mc(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                    int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+      "{%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
