@@ -47,8 +47,6 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + NUM_EPI_THREADS;  // 320
 constexpr int LN_N = 512;                           // row width the LN epilogue is built for
-constexpr int WARP_BOX_BYTES = 32 * 128;            // one staged [32 rows x 64 bf16] box (a warp's rows of a 64-column chunk)
-constexpr int STAGING_BYTES = NUM_EPI_WARPS * 2 * WARP_BOX_BYTES;  // 64 KB: two boxes per epilogue warp
 
 #define MST_DBG_STAMP() do { if (dbg && di < 1000) dbg[di++] = clock64(); } while (0)
 // wall-clock (ns) of CTA entry (slot 0), end of work (slot 1) and last instruction (slot 2), per CTA
@@ -123,19 +121,21 @@ __device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
 }
 // two bf16 (packed in 32 bits) -> two fp32 (packed in 64 bits): shift / mask, no conversion instruction
 __device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t u) { return pk2u(u << 16, u & 0xffff0000u); }
-__device__ __forceinline__ void gelu2(float& x0, float& x1) {
-  const float kC[9] = {1.1283629389e+00f, -3.7581860120e-01f, 1.1186250267e-01f, -2.5649613612e-02f, 4.4378622868e-03f,
-                       -5.5355724174e-04f, 4.6147291864e-05f, -2.2677306229e-06f, 4.9182760725e-08f};
-  const float z0 = fminf(fmaxf(x0 * 0.70710678118654752440f, -3.0f), 3.0f);
-  const float z1 = fminf(fmaxf(x1 * 0.70710678118654752440f, -3.0f), 3.0f);
+// gelu(x) = x * (0.5 + z q(z^2)),  z = clamp(x / sqrt 2, +-2.8),  q = degree-6 minimax fit of erf(z) / (2z)
+// (|relative error| < 2e-4, an order below the bf16 rounding of the output).  Two elements per instruction.
+__device__ __forceinline__ uint64_t gelu2(uint64_t x) {
+  const float kC[7] = {5.6408941812e-01f, -1.8671857437e-01f, 5.3391947352e-02f, -1.0763958331e-02f,
+                       1.4033610804e-03f, -1.0399474066e-04f, 3.2816237409e-06f};
+  float x0, x1;
+  upk2(x, x0, x1);
+  const float z0 = fminf(fmaxf(x0 * 0.70710678118654752440f, -2.8f), 2.8f);
+  const float z1 = fminf(fmaxf(x1 * 0.70710678118654752440f, -2.8f), 2.8f);
   const uint64_t z = pk2(z0, z1);
   const uint64_t t = mul2(z, z);
-  uint64_t p = pk2(kC[8], kC[8]);
+  uint64_t q = pk2(kC[6], kC[6]);
 #pragma unroll
-  for (int k = 7; k >= 0; --k) p = fma2(p, t, pk2(kC[k], kC[k]));
-  const uint64_t e = mul2(z, p);
-  const uint64_t hx = pk2(0.5f * x0, 0.5f * x1);
-  upk2(fma2(hx, e, hx), x0, x1);
+  for (int k = 5; k >= 0; --k) q = fma2(q, t, pk2(kC[k], kC[k]));
+  return mul2(x, fma2(z, q, pk2(0.5f, 0.5f)));
 }
 
 // ---- direct (row-per-thread) epilogue of one 32-column chunk: the small fp32 / row-remapping cases ----
@@ -341,23 +341,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // 128B-swizzled [32 x 64] staging box -> one TMA store per box.  Two boxes per warp ping-pong, so the only
 // synchronisation is __syncwarp and the bulk-group wait of lane 0 - no CTA-wide barrier in the loop.
 // ---------------------------------------------------------------------------
+template <int EPI>
 struct PairCfg {
   static constexpr int BN = 256;
-  static constexpr int STAGES = 5;
+  // The GELU epilogue is issue/latency-bound with two warps per scheduler (5.6k cycles per tile against 4.1k of MMAs):
+  // it gets 16 epilogue warps (4 per scheduler, 64 columns each) and pays with one ring stage; the plain-bias
+  // epilogue keeps 8 warps and a 6-deep ring (~190 KB in flight: the L2 -> SM latency is ~2k cycles under load).
+  static constexpr int EPI_WARPS = EPI == TC_EPI_BIAS_GELU_BF16 ? 16 : 8;
+  static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = 64 + EPI_THREADS;
+  static constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
+  static constexpr int STAGES = EPI == TC_EPI_BIAS_GELU_BF16 ? 5 : 6;
   static constexpr int A_BYTES = BLOCK_M * 128;       // 128 rows x 64 k
   static constexpr int B_BYTES = (BN / 2) * 128;      // this CTA's 128 of the 256 weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OBOX_BYTES = 32 * 64;          // output staging: [32 rows x 32 bf16], 64B swizzle
+  static constexpr int OUT_BYTES = EPI_WARPS * 2 * OBOX_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
 };
 
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EPI>::THREADS, 1)
 tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_out, const TcGemmParams p) {
-  using Cfg = PairCfg;
+  using Cfg = PairCfg<EPI>;
   constexpr int BN = Cfg::BN;
   pdl_launch_dependents();
   MST_DBG_WALL(0);
@@ -366,7 +376,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
   const uint32_t out_smem = base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  Ring ring{base, out_smem + STAGING_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
+  Ring ring{base, out_smem + Cfg::OUT_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
   const uint32_t tmem_slot = ring.extra(0);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
 
@@ -386,7 +396,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(ring.tfull(i), 1);
-      mbar_init(ring.tempty(i), 2 * NUM_EPI_THREADS);  // leader: epilogue threads of both CTAs
+      mbar_init(ring.tempty(i), 2 * Cfg::EPI_THREADS);  // leader: epilogue threads of both CTAs
     }
     fence_barrier_init();
   }
@@ -464,10 +474,10 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ---------------- epilogue (both CTAs, each for its own 128 rows) ----------------
     const int ew = warp - 2;
     const int quad = warp & 3;
-    const int half = ew >> 2;
+    const int cgrp = ew >> 2;  // column group of the tile: COLS_PER_WARP columns per warp
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const uint32_t my_box = out_smem + ew * 2 * WARP_BOX_BYTES;  // this warp's two staging boxes
-    const uint32_t my_row = lane * 128;
+    const uint32_t my_box = out_smem + ew * 2 * Cfg::OBOX_BYTES;  // this warp's two staging boxes (ping-pong)
+    const uint32_t my_row = lane * 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     long long* dbg = (p.dbg && cluster_id == 0 && warp == 2 && lane == 0) ? p.dbg + (2 * 2 + rank) * 1024 : nullptr;
@@ -480,43 +490,51 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_after();
       MST_DBG_STAMP();
       const uint32_t tempty_leader = map_to_cta(ring.tempty(acc), 0);
+      constexpr int STEPS = Cfg::COLS_PER_WARP / 32;
+      const uint32_t acc_addr = tmem_base + lane_addr + (uint32_t)(acc * BN + cgrp * Cfg::COLS_PER_WARP);
+      // this warp's 32 rows x COLS_PER_WARP columns, 32 columns at a time; the next 32 are in flight while these are
+      // processed
+      uint32_t v[2][32];
+      tmem_ld32(acc_addr, v[0]);
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col = half * 128 + cc * 64;  // first of this step's 64 tile columns
-        uint32_t v[2][32];
-        tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + col), v[0]);
-        tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + col + 32), v[1]);
-        // box cc was handed to a TMA store one tile ago: at most the other box's store may still be reading
+      for (int c4 = 0; c4 < STEPS; ++c4) {
+        const int col = cgrp * Cfg::COLS_PER_WARP + c4 * 32;  // first tile column of this step
+        // the box was handed to a TMA store two steps ago: at most the other box's store may still be reading
         if (lane == 0) bulk_wait_read_1();
         __syncwarp();
         tmem_ld_wait();
-        if (cc == 1) {  // accumulator drained: the MMAs of the tile after next may overwrite it
+        if (c4 < STEPS - 1) tmem_ld32(acc_addr + (uint32_t)((c4 + 1) * 32), v[(c4 + 1) & 1]);
+        if (c4 == STEPS - 1) {  // accumulator drained: the MMAs of the tile after next may overwrite it
           tc_fence_before();
           mbar_arrive_cluster_relaxed(tempty_leader);
+          MST_DBG_STAMP();
         }
-        MST_DBG_STAMP();
         const float* bias = p.bias + n_blk * BN + col;
-        const uint32_t row_smem = my_box + cc * WARP_BOX_BYTES + my_row;
+        const uint32_t row_smem = my_box + (c4 & 1) * Cfg::OBOX_BYTES + my_row;
+        const uint32_t* a = v[c4 & 1];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // 8 columns -> one 16-byte piece of the swizzled row
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j + 4));
-          const uint32_t* s = &v[j >> 2][(j & 3) * 8];
-          float x0 = __uint_as_float(s[0]) + b0.x, x1 = __uint_as_float(s[1]) + b0.y;
-          float x2 = __uint_as_float(s[2]) + b0.z, x3 = __uint_as_float(s[3]) + b0.w;
-          float x4 = __uint_as_float(s[4]) + b1.x, x5 = __uint_as_float(s[5]) + b1.y;
-          float x6 = __uint_as_float(s[6]) + b1.z, x7 = __uint_as_float(s[7]) + b1.w;
-          if constexpr (EPI == TC_EPI_BIAS_GELU_BF16) {
-            gelu2(x0, x1); gelu2(x2, x3); gelu2(x4, x5); gelu2(x6, x7);
+        for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16-byte piece of the 64-byte swizzled row
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * q));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * q + 4));
+          uint64_t x[4];
+          x[0] = add2(pk2u(a[8 * q + 0], a[8 * q + 1]), pk2(b0.x, b0.y));
+          x[1] = add2(pk2u(a[8 * q + 2], a[8 * q + 3]), pk2(b0.z, b0.w));
+          x[2] = add2(pk2u(a[8 * q + 4], a[8 * q + 5]), pk2(b1.x, b1.y));
+          x[3] = add2(pk2u(a[8 * q + 6], a[8 * q + 7]), pk2(b1.z, b1.w));
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if constexpr (EPI == TC_EPI_BIAS_GELU_BF16) x[e] = gelu2(x[e]);
+            float y0, y1;
+            upk2(x[e], y0, y1);
+            o[e] = pack_bf16x2(y0, y1);
           }
-          sts128(row_smem + ((j ^ (lane & 7)) << 4),
-                 make_uint4(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3), pack_bf16x2(x4, x5), pack_bf16x2(x6, x7)));
+          sts128(row_smem + ((q ^ ((lane >> 1) & 3)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
         __syncwarp();
-        MST_DBG_STAMP();
         if (lane == 0) {
-          tma_store_2d(&tmap_out, my_box + cc * WARP_BOX_BYTES, n_blk * BN + col, m_blk * BLOCK_M + quad * 32);
+          tma_store_3d(&tmap_out, my_box + (c4 & 1) * Cfg::OBOX_BYTES, n_blk * BN + col, m_blk * BLOCK_M + quad * 32, 0);
           bulk_commit_group();
         }
       }
@@ -1029,21 +1047,22 @@ static int max_active_clusters(Kernel kernel, int cluster_size, int threads, siz
 
 template <int EPI>
 static int launch_gemm_pair(const TcGemmParams& p, cudaStream_t s) {
-  using Cfg = PairCfg;
+  using Cfg = PairCfg<EPI>;
   CUtensorMap ta, tw, to;
   int rc;
   if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN / 2, BLOCK_K))) return rc;
-  if ((rc = make_tmap_bf16(&to, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 32, 64))) return rc;
+  if ((rc = make_tmap_bf16_3d(&to, p.out, 1, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, (uint64_t)p.M * p.ldo, 32, 32, 64)))
+    return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = ceil_div(ceil_div(p.M, BLOCK_M), 2) * (p.N / Cfg::BN);
-  static const int max_clusters = max_active_clusters(tc_gemm_pair_kernel<EPI>, 2, GEMM_THREADS, Cfg::SMEM_BYTES);
+  static const int max_clusters = max_active_clusters(tc_gemm_pair_kernel<EPI>, 2, Cfg::THREADS, Cfg::SMEM_BYTES);
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  MST_CUDA_OK(launch_pdl(tc_gemm_pair_kernel<EPI>, dim3(2 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tw, to, p));
+  MST_CUDA_OK(launch_pdl(tc_gemm_pair_kernel<EPI>, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, ta, tw, to, p));
   MST_LAUNCHED(EPI == TC_EPI_BIAS_BF16 ? "tc_gemm_qkv" : "tc_gemm_ffn1_gelu", s);
   return MST_OK;
 }

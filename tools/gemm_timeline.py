@@ -115,13 +115,13 @@ if epi == 2:
             if len(q) == 7:
                 print(f"  cta{r} tile {i // 7}: top {q[0]:7d} | " + " | ".join(f"{b - a_:5d}" for a_, b in zip(q, q[1:])) + f" | total {q[6] - q[1]:5d}")
     sys.exit(0)
-print("epilogue (warp 2 lane 0) per tile: top | tfull wait | box0 free+ldtm | math0+sts | store0+box1 free+ldtm (tmem released) | math1+sts | store1 | total after tfull")
+print("epilogue (warp 2 lane 0) per tile: top | tfull wait | first 3 column steps (tmem released) | last step + stores | total after tfull")
 for r in range(2):
     e = epi_t[r]
-    for i in range(0, len(e), 7):
-        q = e[i:i + 7]
-        if len(q) == 7:
-            print(f"  cta{r} tile {i // 7}: top {q[0]:7d} | " + " | ".join(f"{b - a_:5d}" for a_, b in zip(q, q[1:])) + f" | total {q[6] - q[1]:5d}")
+    for i in range(0, len(e), 4):
+        q = e[i:i + 4]
+        if len(q) == 4:
+            print(f"  cta{r} tile {i // 4}: top {q[0]:7d} | " + " | ".join(f"{b - a_:5d}" for a_, b in zip(q, q[1:])) + f" | total {q[3] - q[1]:5d}")
 print("producer: time after each empty wait (per k-block), deltas")
 for r in range(2):
     pr = prod[r]
