@@ -6,6 +6,7 @@ valid Python identifier; ``mst_b200/__init__.py`` at the repo root aliases it).
 Sub-packages mirror the reference's module paths so that its scripts can bind to them unchanged:
 
     mst_b200.diffusion.gaussian_diffusion / .respace / .inpainting_gaussian_diffusion
+    mst_b200.diffusion.resample / .fp16_util,  mst_b200.train.training_loop   (finetune step)
     mst_b200.model.mdm_forstyledataset / .cfg_sampler
     mst_b200.utils.model_util
     mst_b200.data_loaders.{stylexia_posrot,bandai_posrot,humanml}_utils / .tensors
@@ -23,6 +24,9 @@ _OVERLAY = {
     "diffusion.gaussian_diffusion": "diffusion.gaussian_diffusion",
     "diffusion.respace": "diffusion.respace",
     "diffusion.inpainting_gaussian_diffusion": "diffusion.inpainting_gaussian_diffusion",
+    "diffusion.resample": "diffusion.resample",
+    "diffusion.fp16_util": "diffusion.fp16_util",
+    "train.training_loop": "train.training_loop",
     "model.cfg_sampler": "model.cfg_sampler",
     "model.mdm_forstyledataset": "model.mdm_forstyledataset",
     "utils.model_util": "utils.model_util",

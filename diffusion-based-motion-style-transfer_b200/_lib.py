@@ -14,7 +14,7 @@ import threading
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libmst_b200.so")
-SOURCES = ["api.cu", "update.cu", "simt.cu", "tc_gemm.cu", "tc_attn.cu"]
+SOURCES = ["api.cu", "update.cu", "simt.cu", "tc_gemm.cu", "tc_attn.cu", "train.cu"]
 HEADERS = ["common.cuh", "simt.cuh", "tc.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "mst.h")]
 
 MAX_LAYERS = 32
@@ -28,7 +28,9 @@ EXPORTED = [
     "mst_version", "mst_last_error", "mst_launch_count", "mst_profile_begin", "mst_profile_end", "mst_profile_collect", "mst_device_info", "mst_abi_sizes", "mst_engine_create", "mst_engine_destroy",
     "mst_engine_packed_weight_bytes", "mst_engine_load_weights", "mst_engine_workspace_bytes", "mst_time_embed",
     "mst_text_embed", "mst_denoiser_forward", "mst_update_step", "mst_q_sample", "mst_cfg_combine",
-    "mst_philox_normal", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
+    "mst_philox_normal", "mst_train_sizes", "mst_denoiser_forward_train", "mst_denoiser_backward", "mst_abi_sizes_train",
+    "mst_motion_encoder_forward", "mst_motion_encoder_backward", "mst_masked_l2", "mst_update_step_backward",
+    "mst_adamw_step", "mst_sumsq2", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
 ]
 
 
@@ -72,6 +74,18 @@ class UpdateArgs(C.Structure):
         ("recipm1", C.c_void_p),
         ("noise_kind", C.c_int32), ("noise", C.c_void_p), ("const_noise", C.c_int32),
         ("philox_seed", C.c_uint64), ("philox_sample_offset", C.c_uint64),
+    ]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("n_frames", C.c_int32), ("d_out", C.c_void_p), ("d_x", C.c_void_p),
+        ("layer_grads", C.POINTER(LayerGrads)), ("tape", C.c_void_p), ("tape_bytes", C.c_size_t),
+        ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
     ]
 
 
@@ -130,6 +144,16 @@ def _declare(lib):
         "mst_q_sample": [vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp],
         "mst_cfg_combine": [vp, vp, vp, vp, i32, i64, vp],
         "mst_philox_normal": [vp, i32, i64, u64, u64, i32, vp],
+        "mst_train_sizes": [vp, i32, i32, C.POINTER(sz), C.POINTER(sz)],
+        "mst_denoiser_forward_train": [vp, C.POINTER(ForwardArgs), vp, sz, vp],
+        "mst_denoiser_backward": [vp, C.POINTER(BackwardArgs), vp],
+        "mst_abi_sizes_train": [C.POINTER(sz), C.POINTER(sz)],
+        "mst_motion_encoder_forward": [vp, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp],
+        "mst_motion_encoder_backward": [vp, vp, i32, i32, vp, vp, sz, vp, sz, vp],
+        "mst_masked_l2": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "mst_update_step_backward": [vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp],
+        "mst_adamw_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.c_float, vp],
+        "mst_sumsq2": [vp, vp, i64, vp, vp],
         "mst_test_gemm_bf16": [vp, vp, vp, vp, i32, i32, i32, vp],
         "mst_test_gemm_epi_bf16": [i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "mst_test_set_gemm_debug": [vp],

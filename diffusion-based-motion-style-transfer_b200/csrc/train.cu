@@ -1,0 +1,879 @@
+// Training path of the denoiser: forward with an activation tape, backward
+// through OutputProcess -> 8 x TransformerEncoderLayer -> InputProcess, the masked-L2 style loss, the gradient of
+// the per-step update, and the fused multi-tensor AdamW / norm kernels.  fp32 SIMT (the parity precision).
+//
+// What it restates (reference file:line):
+//   few_shot_style_finetune_losses      diffusion/gaussian_diffusion.py:1317-1399
+//   masked_l2                           diffusion/gaussian_diffusion.py:223-235
+//   p_sample_with_grad / ddim_..._grad  diffusion/inpainting_gaussian_diffusion.py:66-123, :176-239
+//   StyleDiffusion.forward              model/mdm_forstyledataset.py:602-625   (torch autograd does the backward there)
+//   MotionEncoder.forward               model/mdm_forstyledataset.py:89-124
+//   MixedPrecisionTrainer._compute_norms / AdamW step   diffusion/fp16_util.py:208-223, train/training_loop.py:97-99
+//
+// Layer algebra (nn.TransformerEncoderLayer, post-norm, exact GELU; dropout is identity: see DESIGN.md):
+//   qkv = x Wqkv^T + b ; P = softmax(Q K^T / sqrt(dh)) ; ao = P V ; z1 = x + ao Wo^T + bo ; y = LN1(z1)
+//   u = y W1^T + b1 ; h = gelu(u) ; z2 = y + h W2^T + b2 ; x' = LN2(z2)
+#include "common.cuh"
+#include "simt.cuh"
+
+#include <math.h>
+
+namespace mst {
+
+// ---------------------------------------------------------------------------------------------------------
+// General batched fp32 GEMM   C = alpha * op(A) op(B) (+ bias) (+ add) (+ C)
+// ---------------------------------------------------------------------------------------------------------
+enum AModeEx { AX_NORMAL = 0, AX_TRANS = 1, AX_MOTION_TOK = 2, AX_TOKROWS = 3 };
+enum CModeEx { CX_NORMAL = 0, CX_MOTION = 1 };
+
+struct GemmEx {
+  const float* a = nullptr;
+  const float* b = nullptr;
+  float* c = nullptr;
+  const float* bias = nullptr;  // [N]
+  const float* add = nullptr;   // same layout / leading dimension as c
+  int M = 0, N = 0, K = 0, lda = 0, ldb = 0, ldc = 0;
+  int a_mode = AX_NORMAL;  // NORMAL a[m*lda+k] | TRANS a[k*lda+m] | MOTION_TOK m=(seq,s): s<tok_off ? 0 : a[(seq*K+k)*T+s-tok_off]
+                           // | TOKROWS m=(seq,t): a[(seq*S+t+tok_off)*lda+k]
+  int trans_b = 0;         // 0: B(k,n) = b[k*ldb+n]   1: B(k,n) = b[n*ldb+k]
+  int c_mode = CX_NORMAL;  // MOTION: m=(seq,t) -> c[(seq*N+n)*T+t]
+  int T = 0, tok_off = 1;  // token geometry of the MOTION / TOKROWS modes (S = T + tok_off)
+  float alpha = 1.0f;
+  int accumulate = 0;
+  int batch = 1, heads = 1;  // blockIdx.z -> (z / heads, z % heads)
+  long long a_bs = 0, a_hs = 0, b_bs = 0, b_hs = 0, c_bs = 0, c_hs = 0;
+  int split_k = 1;  // > 1: partial products are atomically added into c (which the caller zeroed or accumulates into)
+};
+
+template <int TM>
+__global__ void __launch_bounds__(256) gemm_ex_kernel(GemmEx p) {
+  constexpr int BT = 16 * TM;  // square tile
+  constexpr int BK = 16;
+  __shared__ float As[BK][BT + 4];
+  __shared__ float Bs[BK][BT + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int z = blockIdx.z / p.split_k, split = blockIdx.z - z * p.split_k;
+  const int zb = z / p.heads, zh = z - zb * p.heads;
+  const float* __restrict__ a = p.a + zb * p.a_bs + zh * p.a_hs;
+  const float* __restrict__ b = p.b + zb * p.b_bs + zh * p.b_hs;
+  float* __restrict__ c = p.c + zb * p.c_bs + zh * p.c_hs;
+  const float* __restrict__ addp = p.add ? p.add + zb * p.c_bs + zh * p.c_hs : nullptr;
+  const int m0 = blockIdx.y * BT, n0 = blockIdx.x * BT;
+  const int k_per = ((p.K + p.split_k - 1) / p.split_k + BK - 1) / BK * BK;
+  const int k_begin = split * k_per, k_end = min(p.K, k_begin + k_per);
+  const int S = p.T + p.tok_off;
+
+  float acc[TM][TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TM; ++j) acc[i][j] = 0.0f;
+
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+    for (int l = 0; l < (BT * BK) / 256; ++l) {
+      const int idx = tid + l * 256;
+      int mm, kk;
+      if (p.a_mode == AX_NORMAL || p.a_mode == AX_TOKROWS) { kk = idx & 15; mm = idx >> 4; }
+      else { mm = idx % BT; kk = idx / BT; }
+      const int m = m0 + mm, k = k0 + kk;
+      float v = 0.0f;
+      if (m < p.M && k < k_end) {
+        switch (p.a_mode) {
+          case AX_NORMAL: v = a[(long long)m * p.lda + k]; break;
+          case AX_TRANS: v = a[(long long)k * p.lda + m]; break;
+          case AX_MOTION_TOK: {
+            const int seq = m / S, s = m - seq * S;
+            v = s < p.tok_off ? 0.0f : a[((long long)seq * p.K + k) * p.T + (s - p.tok_off)];
+            break;
+          }
+          default: {
+            const int seq = m / p.T, t = m - seq * p.T;
+            v = a[((long long)seq * S + t + p.tok_off) * p.lda + k];
+          }
+        }
+      }
+      As[kk][mm] = v;
+      int nn, kb;
+      if (p.trans_b) { kb = idx & 15; nn = idx >> 4; }
+      else { nn = idx % BT; kb = idx / BT; }
+      const int n = n0 + nn, k2 = k0 + kb;
+      float w = 0.0f;
+      if (n < p.N && k2 < k_end) w = p.trans_b ? b[(long long)n * p.ldb + k2] : b[(long long)k2 * p.ldb + n];
+      Bs[kb][nn] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[TM], bv[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TM; ++j) bv[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (k_begin >= k_end && split != 0) return;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TM; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= p.N) continue;
+      long long o;
+      if (p.c_mode == CX_MOTION) {
+        const int seq = m / p.T, t = m - seq * p.T;
+        o = ((long long)seq * p.N + n) * p.T + t;
+      } else {
+        o = (long long)m * p.ldc + n;
+      }
+      float v = p.alpha * acc[i][j];
+      if (split == 0) {
+        if (p.bias) v += p.bias[n];
+        if (addp) v += addp[o];
+      }
+      if (p.split_k > 1) atomicAdd(c + o, v);
+      else if (p.accumulate) c[o] += v;
+      else c[o] = v;
+    }
+  }
+}
+
+static int gemm_ex(GemmEx p, cudaStream_t s, const char* name) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return fail(MST_ERR_INVALID, "gemm_ex: empty problem");
+  const long long z = (long long)p.batch * p.heads;
+  const long long tiles128 = (long long)ceil_div(p.M, 128) * ceil_div(p.N, 128) * z * p.split_k;
+  if (p.split_k > 1 && !p.accumulate) {
+    if (p.c_mode != CX_NORMAL || z != 1 || p.ldc != p.N)
+      return fail(MST_ERR_INVALID, "gemm_ex: split-k overwrite needs a dense single output");
+    MST_CUDA_OK(cudaMemsetAsync(p.c, 0, (size_t)p.M * p.N * sizeof(float), s));
+  }
+  if (tiles128 >= 120) {
+    dim3 grid(ceil_div(p.N, 128), ceil_div(p.M, 128), (unsigned)(z * p.split_k));
+    gemm_ex_kernel<8><<<grid, 256, 0, s>>>(p);
+  } else {
+    dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64), (unsigned)(z * p.split_k));
+    gemm_ex_kernel<4><<<grid, 256, 0, s>>>(p);
+  }
+  MST_LAUNCHED(name, s);
+  return MST_OK;
+}
+
+// split factor for a weight-gradient GEMM (small output, long reduction over the token rows)
+static int pick_split(int M, int N, int K) {
+  const int tiles = ceil_div(M, 128) * ceil_div(N, 128);
+  int split = 1;
+  while (tiles * split < 2 * sm_count() && K / (split * 2) >= 64 && split < 32) split *= 2;
+  return split;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// row kernels: softmax, softmax backward, LayerNorm backward, GELU forward / backward, column sums
+// ---------------------------------------------------------------------------------------------------------
+// rows of scores [rows, S] -> softmax in place; key_valid [n_seqs, S] (1 = attend) or NULL; row -> seq = row / (heads*S)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ p, const uint8_t* __restrict__ key_valid,
+                                                           long long rows, int S, int rows_per_seq) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* r = p + row * S;
+  const uint8_t* kv = key_valid ? key_valid + (row / rows_per_seq) * S : nullptr;
+  float mx = -INFINITY;
+  for (int j = lane; j < S; j += 32)
+    if (!kv || kv[j]) mx = fmaxf(mx, r[j]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.0f;
+  for (int j = lane; j < S; j += 32) {
+    const float e = (!kv || kv[j]) ? expf(r[j] - mx) : 0.0f;
+    r[j] = e;
+    sum += e;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  for (int j = lane; j < S; j += 32) r[j] *= inv;
+}
+
+// dS = P * (dP - sum_j P dP), in place in dP
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* __restrict__ p, float* __restrict__ dp,
+                                                               long long rows, int S) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* pr = p + row * S;
+  float* dr = dp + row * S;
+  float dot = 0.0f;
+  for (int j = lane; j < S; j += 32) dot = fmaf(pr[j], dr[j], dot);
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  for (int j = lane; j < S; j += 32) dr[j] = pr[j] * (dr[j] - dot);
+}
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ u, float* __restrict__ h, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    h[i] = gelu_f(u[i]);
+}
+// du = dh * gelu'(u), in place in dh
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ u, float* __restrict__ dh, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dh[i] *= gelu_grad_f(u[i]);
+}
+
+// LayerNorm backward over rows of width d (d % 32 == 0, d <= 1024): dz = rstd * (g - mean(g) - xhat * mean(g xhat)),
+// g = dy * gamma; dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (block partials, then atomics).
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                            const float* __restrict__ gamma, float* __restrict__ dz,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int d) {
+  __shared__ float red[8][64];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int per = d / 32;
+  float dg[32], db[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) dg[i] = db[i] = 0.0f;
+  const float inv_d = 1.0f / (float)d;
+  for (int row = blockIdx.x * 8 + wib; row < M; row += gridDim.x * 8) {
+    const float* zr = z + (long long)row * d;
+    const float* gr = dy + (long long)row * d;
+    float v[32], g[32];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < per) { v[i] = zr[lane + 32 * i]; s += v[i]; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_d;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < per) { const float cdev = v[i] - mean; q += cdev * cdev; }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_d + 1e-5f);
+    float sg = 0.0f, sgx = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < per) {
+        const int n = lane + 32 * i;
+        const float xh = (v[i] - mean) * rstd, go = gr[n];
+        v[i] = xh;
+        g[i] = go * gamma[n];
+        sg += g[i];
+        sgx += g[i] * xh;
+        dg[i] += go * xh;
+        db[i] += go;
+      }
+    for (int o = 16; o > 0; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    const float mg = sg * inv_d, mgx = sgx * inv_d;
+    float* dr = dz + (long long)row * d;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < per) dr[lane + 32 * i] = rstd * (g[i] - mg - v[i] * mgx);
+  }
+  // block reduction of the per-warp column partials, one 32-column slab at a time
+  for (int i = 0; i < per; ++i) {
+    red[wib][lane] = dg[i];
+    red[wib][32 + lane] = db[i];
+    __syncthreads();
+    if (wib == 0) {
+      float a = 0.0f, b2 = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { a += red[w][lane]; b2 += red[w][32 + lane]; }
+      if (dgamma) atomicAdd(dgamma + lane + 32 * i, a);
+      if (dbeta) atomicAdd(dbeta + lane + 32 * i, b2);
+    }
+    __syncthreads();
+  }
+}
+
+// out[n] += sum_m x[m*ld + n]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int ld,
+                                                     int rows_per_block) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.0f;
+  if (n < N)
+    for (int m = r0 + ty; m < r1; m += 8) s += x[(long long)m * ld + n];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][tx];
+    atomicAdd(out + n, t);
+  }
+}
+
+static int colsum(const float* x, float* out, int M, int N, int ld, cudaStream_t s) {
+  int rows_per_block = 256;
+  dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_block));
+  colsum_kernel<<<grid, 256, 0, s>>>(x, out, M, N, ld, rows_per_block);
+  MST_LAUNCHED("colsum", s);
+  return MST_OK;
+}
+
+static int ew_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// MotionEncoder tokens: rows 0 / 1 of every sequence = muQuery / sigmaQuery + pe[row]; rows >= 2 (already holding
+// InputProcess(x)) += pe[row]
+__global__ void __launch_bounds__(128) menc_tokens_kernel(const float* __restrict__ q0, const float* __restrict__ q1,
+                                                          const float* __restrict__ pe, float* __restrict__ x, int S, int d) {
+  const int seq = blockIdx.x / S, r = blockIdx.x - seq * S;
+  float* xr = x + ((long long)seq * S + r) * d;
+  const float* per = pe + (long long)r * d;
+  for (int n = threadIdx.x; n < d; n += blockDim.x) {
+    if (r == 0) xr[n] = q0[n] + per[n];
+    else if (r == 1) xr[n] = q1[n] + per[n];
+    else xr[n] += per[n];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tape: everything the backward needs, per layer
+// ---------------------------------------------------------------------------------------------------------
+struct LayerTape {
+  float *x, *qkv, *p, *ao, *z1, *y, *u, *h, *z2;
+};
+struct Tape {
+  LayerTape l[MST_MAX_LAYERS];
+  float* x_out;  // output of the last layer [M, d]
+};
+
+static size_t carve_tape(const mst_model_desc& d, int n_seqs, int S, void* base, Tape* t) {
+  const size_t M = (size_t)n_seqs * S, dm = d.d_model, ff = d.d_ff;
+  const size_t pp = (size_t)n_seqs * d.n_heads * S * S;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    off = align_up(off, 256);
+    float* r = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+    off += n * sizeof(float);
+    return r;
+  };
+  Tape tp;
+  float* x = take(M * dm);
+  for (int l = 0; l < d.n_layers; ++l) {
+    LayerTape& L = tp.l[l];
+    L.x = x;
+    L.qkv = take(M * 3 * dm);
+    L.p = take(pp);
+    L.ao = take(M * dm);
+    L.z1 = take(M * dm);
+    L.y = take(M * dm);
+    L.u = take(M * ff);
+    L.h = take(M * ff);
+    L.z2 = take(M * dm);
+    x = take(M * dm);
+  }
+  tp.x_out = x;
+  if (t) *t = tp;
+  return align_up(off, 256);
+}
+
+static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const uint8_t* key_valid, cudaStream_t s) {
+  const mst_model_desc& d = e->desc;
+  const int M = NS * S, dm = d.d_model, H = d.n_heads, dh = dm / H, ff = d.d_ff;
+  const float scale = 1.0f / sqrtf((float)dh);
+  int rc;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const LayerF32& L = e->lf[l];
+    const LayerTape& t = tp.l[l];
+    float* x_next = l + 1 < d.n_layers ? tp.l[l + 1].x : tp.x_out;
+    GemmEx g;
+    g.a = t.x; g.lda = dm; g.b = L.qkv_w; g.ldb = dm; g.trans_b = 1; g.bias = L.qkv_b; g.c = t.qkv; g.ldc = 3 * dm;
+    g.M = M; g.N = 3 * dm; g.K = dm;
+    if ((rc = gemm_ex(g, s, "train_qkv"))) return rc;
+    GemmEx sc;  // scores = scale * Q K^T per (seq, head)
+    sc.a = t.qkv; sc.lda = 3 * dm; sc.b = t.qkv + dm; sc.ldb = 3 * dm; sc.trans_b = 1; sc.c = t.p; sc.ldc = S;
+    sc.M = S; sc.N = S; sc.K = dh; sc.alpha = scale; sc.batch = NS; sc.heads = H;
+    sc.a_bs = (long long)S * 3 * dm; sc.a_hs = dh; sc.b_bs = sc.a_bs; sc.b_hs = dh;
+    sc.c_bs = (long long)H * S * S; sc.c_hs = (long long)S * S;
+    if ((rc = gemm_ex(sc, s, "train_scores"))) return rc;
+    const long long rows = (long long)NS * H * S;
+    softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, key_valid, rows, S, H * S);
+    MST_LAUNCHED("train_softmax", s);
+    GemmEx pv;  // ao = P V
+    pv.a = t.p; pv.lda = S; pv.b = t.qkv + 2 * dm; pv.ldb = 3 * dm; pv.c = t.ao; pv.ldc = dm;
+    pv.M = S; pv.N = dh; pv.K = S; pv.batch = NS; pv.heads = H;
+    pv.a_bs = sc.c_bs; pv.a_hs = sc.c_hs; pv.b_bs = sc.a_bs; pv.b_hs = dh; pv.c_bs = (long long)S * dm; pv.c_hs = dh;
+    if ((rc = gemm_ex(pv, s, "train_pv"))) return rc;
+    GemmEx o;
+    o.a = t.ao; o.lda = dm; o.b = L.o_w; o.ldb = dm; o.trans_b = 1; o.bias = L.o_b; o.add = t.x; o.c = t.z1; o.ldc = dm;
+    o.M = M; o.N = dm; o.K = dm;
+    if ((rc = gemm_ex(o, s, "train_outproj"))) return rc;
+    if ((rc = layernorm_f32(t.z1, L.ln1_g, L.ln1_b, t.y, M, dm, s))) return rc;
+    GemmEx f1;
+    f1.a = t.y; f1.lda = dm; f1.b = L.w1; f1.ldb = dm; f1.trans_b = 1; f1.bias = L.b1; f1.c = t.u; f1.ldc = ff;
+    f1.M = M; f1.N = ff; f1.K = dm;
+    if ((rc = gemm_ex(f1, s, "train_ffn1"))) return rc;
+    gelu_fwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, t.h, (long long)M * ff);
+    MST_LAUNCHED("train_gelu", s);
+    GemmEx f2;
+    f2.a = t.h; f2.lda = ff; f2.b = L.w2; f2.ldb = ff; f2.trans_b = 1; f2.bias = L.b2; f2.add = t.y; f2.c = t.z2; f2.ldc = dm;
+    f2.M = M; f2.N = dm; f2.K = ff;
+    if ((rc = gemm_ex(f2, s, "train_ffn2"))) return rc;
+    if ((rc = layernorm_f32(t.z2, L.ln2_g, L.ln2_b, x_next, M, dm, s))) return rc;
+  }
+  return MST_OK;
+}
+
+// Backward of the encoder stack.  g_out [M, d]: gradient w.r.t. the stack's output, overwritten with scratch;
+// on return `g_x` [M, d] holds the gradient w.r.t. the stack's input.  Parameter gradients are ACCUMULATED.
+struct BwdScratch {
+  float *ga, *gb, *dqkv, *dp, *dh;  // [M,d] x2, [M,3d], [NS*H*S*S], [M,ff]
+};
+
+static size_t carve_bwd(const mst_model_desc& d, int n_seqs, int S, void* base, BwdScratch* o) {
+  const size_t M = (size_t)n_seqs * S, dm = d.d_model;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    off = align_up(off, 256);
+    float* r = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+    off += n * sizeof(float);
+    return r;
+  };
+  BwdScratch b;
+  b.ga = take(M * dm);
+  b.gb = take(M * dm);
+  b.dqkv = take(M * 3 * dm);
+  b.dp = take((size_t)n_seqs * d.n_heads * S * S);
+  b.dh = take(M * d.d_ff);
+  if (o) *o = b;
+  return align_up(off, 256);
+}
+
+static int weight_grad(const float* dy, int ldy, const float* x, int ldx, float* dw, int n_out, int n_in, int M,
+                       cudaStream_t s, const char* name) {
+  if (!dw) return MST_OK;
+  GemmEx g;  // dW[n_out, n_in] += dy^T x
+  g.a = dy; g.lda = ldy; g.a_mode = AX_TRANS; g.b = x; g.ldb = ldx; g.c = dw; g.ldc = n_in;
+  g.M = n_out; g.N = n_in; g.K = M; g.accumulate = 1; g.split_k = pick_split(n_out, n_in, M);
+  return gemm_ex(g, s, name);
+}
+
+static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* grads, int NS, int S, float* g_in_out,
+                            const BwdScratch& w, float** g_x, cudaStream_t s) {
+  const mst_model_desc& d = e->desc;
+  const int M = NS * S, dm = d.d_model, H = d.n_heads, dh = dm / H, ff = d.d_ff;
+  const float scale = 1.0f / sqrtf((float)dh);
+  int rc;
+  float* gx = g_in_out;  // gradient w.r.t. the current layer's output
+  float* spare = w.ga;
+  float* spare2 = w.gb;
+  for (int l = d.n_layers - 1; l >= 0; --l) {
+    const LayerF32& L = e->lf[l];
+    const LayerTape& t = tp.l[l];
+    const mst_layer_grads& G = grads[l];
+    const int ln_blocks = ceil_div(M, 8) < 4 * sm_count() ? ceil_div(M, 8) : 4 * sm_count();
+    // LN2
+    float* dz2 = spare;
+    layernorm_bwd_kernel<<<ln_blocks, 256, 0, s>>>(gx, t.z2, L.ln2_g, dz2, G.ln2_g, G.ln2_b, M, dm);
+    MST_LAUNCHED("bwd_ln2", s);
+    if (G.b2 && (rc = colsum(dz2, G.b2, M, dm, dm, s))) return rc;
+    if ((rc = weight_grad(dz2, dm, t.h, ff, G.w2, dm, ff, M, s, "bwd_dw2"))) return rc;
+    GemmEx g3;  // dh = dz2 W2
+    g3.a = dz2; g3.lda = dm; g3.b = L.w2; g3.ldb = ff; g3.c = w.dh; g3.ldc = ff; g3.M = M; g3.N = ff; g3.K = dm;
+    if ((rc = gemm_ex(g3, s, "bwd_dh"))) return rc;
+    gelu_bwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, w.dh, (long long)M * ff);
+    MST_LAUNCHED("bwd_gelu", s);
+    if (G.b1 && (rc = colsum(w.dh, G.b1, M, ff, ff, s))) return rc;
+    if ((rc = weight_grad(w.dh, ff, t.y, dm, G.w1, ff, dm, M, s, "bwd_dw1"))) return rc;
+    GemmEx g6;  // dy = dz2 + du W1   (into gx: the incoming gradient is no longer needed)
+    g6.a = w.dh; g6.lda = ff; g6.b = L.w1; g6.ldb = dm; g6.add = dz2; g6.c = gx; g6.ldc = dm; g6.M = M; g6.N = dm; g6.K = ff;
+    if ((rc = gemm_ex(g6, s, "bwd_dy"))) return rc;
+    // LN1
+    float* dz1 = spare;  // dz2 is dead
+    layernorm_bwd_kernel<<<ln_blocks, 256, 0, s>>>(gx, t.z1, L.ln1_g, dz1, G.ln1_g, G.ln1_b, M, dm);
+    MST_LAUNCHED("bwd_ln1", s);
+    if (G.o_b && (rc = colsum(dz1, G.o_b, M, dm, dm, s))) return rc;
+    if ((rc = weight_grad(dz1, dm, t.ao, dm, G.o_w, dm, dm, M, s, "bwd_dwo"))) return rc;
+    float* dao = spare2;
+    GemmEx g9;  // dao = dz1 Wo
+    g9.a = dz1; g9.lda = dm; g9.b = L.o_w; g9.ldb = dm; g9.c = dao; g9.ldc = dm; g9.M = M; g9.N = dm; g9.K = dm;
+    if ((rc = gemm_ex(g9, s, "bwd_dao"))) return rc;
+    // attention
+    const long long qkv_bs = (long long)S * 3 * dm, pp_bs = (long long)H * S * S, pp_hs = (long long)S * S;
+    GemmEx dp;  // dP = dao V^T
+    dp.a = dao; dp.lda = dm; dp.b = t.qkv + 2 * dm; dp.ldb = 3 * dm; dp.trans_b = 1; dp.c = w.dp; dp.ldc = S;
+    dp.M = S; dp.N = S; dp.K = dh; dp.batch = NS; dp.heads = H;
+    dp.a_bs = (long long)S * dm; dp.a_hs = dh; dp.b_bs = qkv_bs; dp.b_hs = dh; dp.c_bs = pp_bs; dp.c_hs = pp_hs;
+    if ((rc = gemm_ex(dp, s, "bwd_dp"))) return rc;
+    GemmEx dv;  // dV = P^T dao
+    dv.a = t.p; dv.lda = S; dv.a_mode = AX_TRANS; dv.b = dao; dv.ldb = dm; dv.c = w.dqkv + 2 * dm; dv.ldc = 3 * dm;
+    dv.M = S; dv.N = dh; dv.K = S; dv.batch = NS; dv.heads = H;
+    dv.a_bs = pp_bs; dv.a_hs = pp_hs; dv.b_bs = (long long)S * dm; dv.b_hs = dh; dv.c_bs = qkv_bs; dv.c_hs = dh;
+    if ((rc = gemm_ex(dv, s, "bwd_dv"))) return rc;
+    const long long rows = (long long)NS * H * S;
+    softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, w.dp, rows, S);
+    MST_LAUNCHED("bwd_softmax", s);
+    GemmEx dq;  // dQ = scale dS K
+    dq.a = w.dp; dq.lda = S; dq.b = t.qkv + dm; dq.ldb = 3 * dm; dq.c = w.dqkv; dq.ldc = 3 * dm; dq.alpha = scale;
+    dq.M = S; dq.N = dh; dq.K = S; dq.batch = NS; dq.heads = H;
+    dq.a_bs = pp_bs; dq.a_hs = pp_hs; dq.b_bs = qkv_bs; dq.b_hs = dh; dq.c_bs = qkv_bs; dq.c_hs = dh;
+    if ((rc = gemm_ex(dq, s, "bwd_dq"))) return rc;
+    GemmEx dk = dq;  // dK = scale dS^T Q
+    dk.a_mode = AX_TRANS; dk.b = t.qkv; dk.c = w.dqkv + dm;
+    if ((rc = gemm_ex(dk, s, "bwd_dk"))) return rc;
+    if (G.qkv_b && (rc = colsum(w.dqkv, G.qkv_b, M, 3 * dm, 3 * dm, s))) return rc;
+    if ((rc = weight_grad(w.dqkv, 3 * dm, t.x, dm, G.qkv_w, 3 * dm, dm, M, s, "bwd_dwqkv"))) return rc;
+    GemmEx g12;  // gradient w.r.t. the layer input = dz1 + dqkv Wqkv
+    g12.a = w.dqkv; g12.lda = 3 * dm; g12.b = L.qkv_w; g12.ldb = dm; g12.add = dz1; g12.c = gx; g12.ldc = dm;
+    g12.M = M; g12.N = dm; g12.K = 3 * dm;
+    if ((rc = gemm_ex(g12, s, "bwd_dx"))) return rc;
+  }
+  *g_x = gx;
+  return MST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// masked L2 (gaussian_diffusion.py:223-235) and the gradient of the per-step update
+// ---------------------------------------------------------------------------------------------------------
+// loss[r] = sum_{f,t} (a - b)^2 mask[t] / (sum_t mask[t] * F);  rows r of a,b: [R, F, T]; a / mask rows are taken
+// modulo a_rows / mask_rows (the reference expands a [1,...] target and mask over the stacked steps)
+__global__ void __launch_bounds__(256) masked_l2_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            const float* __restrict__ mask, float* __restrict__ loss,
+                                                            int F, int T, int a_rows, int mask_rows) {
+  __shared__ float red[2][8];
+  const int r = blockIdx.x;
+  const float* ar = a + (long long)(r % a_rows) * F * T;
+  const float* br = b + (long long)r * F * T;
+  const float* mr = mask + (long long)(r % mask_rows) * T;
+  float s = 0.0f, ms = 0.0f;
+  for (int i = threadIdx.x; i < F * T; i += blockDim.x) {
+    const float dlt = ar[i] - br[i];
+    s += dlt * dlt * mr[i % T];
+  }
+  for (int t = threadIdx.x; t < T; t += blockDim.x) ms += mr[t];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ms += __shfl_xor_sync(0xffffffffu, ms, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = ms; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.0f, tm = 0.0f;
+    for (int w = 0; w < 8; ++w) { ts += red[0][w]; tm += red[1][w]; }
+    loss[r] = ts / (tm * (float)F);
+  }
+}
+
+// db[r,f,t] = gl[r] * 2 (b - a) mask[t] / (sum_t mask * F)
+__global__ void __launch_bounds__(256) masked_l2_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            const float* __restrict__ mask, const float* __restrict__ gl,
+                                                            float* __restrict__ db, int F, int T, int a_rows, int mask_rows) {
+  __shared__ float red[8];
+  __shared__ float coef;
+  const int r = blockIdx.x;
+  const float* ar = a + (long long)(r % a_rows) * F * T;
+  const float* br = b + (long long)r * F * T;
+  const float* mr = mask + (long long)(r % mask_rows) * T;
+  float ms = 0.0f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) ms += mr[t];
+  for (int o = 16; o > 0; o >>= 1) ms += __shfl_xor_sync(0xffffffffu, ms, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ms;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tm = 0.0f;
+    for (int w = 0; w < 8; ++w) tm += red[w];
+    coef = 2.0f * gl[r] / (tm * (float)F);
+  }
+  __syncthreads();
+  float* dr = db + (long long)r * F * T;
+  for (int i = threadIdx.x; i < F * T; i += blockDim.x) dr[i] = coef * (br[i] - ar[i]) * mr[i % T];
+}
+
+// d out = (d x0 + k[t_b] d sample) (1 - mask) [|x0| < 1 when clipped]
+__global__ void __launch_bounds__(256) update_bwd_kernel(const float* __restrict__ d_x0, const float* __restrict__ d_sample,
+                                                         const float* __restrict__ k_table, const int64_t* __restrict__ t_vec,
+                                                         const float* __restrict__ mask, int mask_kind,
+                                                         const float* __restrict__ x0, int clip, float* __restrict__ d_out,
+                                                         int B, int F, int T) {
+  const long long per = (long long)F * T, n = (long long)B * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    const long long r = i - (long long)b * per;
+    float g = d_x0 ? d_x0[i] : 0.0f;
+    if (d_sample) g = fmaf(k_table[t_vec[b]], d_sample[i], g);
+    float m = 0.0f;
+    if (mask_kind == MST_MASK_FULL) m = mask[i];
+    else if (mask_kind == MST_MASK_FT) m = mask[r];
+    else if (mask_kind == MST_MASK_F) m = mask[r / T];
+    g *= 1.0f - m;
+    if (clip && x0 && fabsf(x0[i]) >= 1.0f && m == 0.0f) g = 0.0f;
+    d_out[i] = g;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// optimizer: flat fp32 arenas (parameters, gradients, two moments)
+// ---------------------------------------------------------------------------------------------------------
+// torch.optim.AdamW semantics (decoupled decay, bias correction, eps added after the sqrt):
+//   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n, float lr, float beta1, float beta2,
+                                                    float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i];
+    pi -= lr * wd * pi;
+    const float mi = fmaf(beta1, m[i], (1.0f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.0f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+// out[0] += sum x^2, out[1] += sum y^2 (y may be NULL): the grad / param norms of _compute_norms in one pass
+__global__ void __launch_bounds__(256) sumsq2_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n,
+                                                     double* __restrict__ out) {
+  __shared__ double red[2][8];
+  double sx = 0.0, sy = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float a = x[i];
+    sx += (double)a * a;
+    if (y) { const float b = y[i]; sy += (double)b * b; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sx; red[1][threadIdx.x >> 5] = sy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+    atomicAdd(out, a);
+    if (y) atomicAdd(out + 1, b);
+  }
+}
+
+}  // namespace mst
+
+using namespace mst;
+
+// ---------------------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------------------
+static int check_train_engine(Engine* e) {
+  if (!e->weights_loaded) return fail(MST_ERR_INVALID, "weights not loaded");
+  if (e->desc.precision != MST_PREC_FP32)
+    return fail(MST_ERR_UNSUPPORTED, "the training path runs on an MST_PREC_FP32 engine");
+  if (e->desc.d_model % 32 != 0 || e->desc.d_model > 1024) return fail(MST_ERR_UNSUPPORTED, "d_model must be a multiple of 32, <= 1024");
+  return MST_OK;
+}
+
+extern "C" int mst_abi_sizes_train(size_t* layer_grads, size_t* backward_args) {
+  if (layer_grads) *layer_grads = sizeof(mst_layer_grads);
+  if (backward_args) *backward_args = sizeof(mst_backward_args);
+  return MST_OK;
+}
+
+extern "C" int mst_train_sizes(mst_engine_t h, int32_t n_seqs, int32_t seq_len, size_t* tape_bytes, size_t* scratch_bytes) {
+  MST_CHECK_ARG(h != nullptr, "null engine");
+  MST_CHECK_ARG(n_seqs > 0 && seq_len > 0, "non-positive size");
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (tape_bytes) *tape_bytes = carve_tape(e->desc, n_seqs, seq_len, nullptr, nullptr);
+  if (scratch_bytes) *scratch_bytes = carve_bwd(e->desc, n_seqs, seq_len, nullptr, nullptr);
+  return MST_OK;
+}
+
+extern "C" int mst_denoiser_forward_train(mst_engine_t h, const mst_forward_args* ap, void* tape, size_t tape_bytes,
+                                          void* stream) {
+  MST_CHECK_ARG(h && ap && tape, "null argument");
+  Engine* e = reinterpret_cast<Engine*>(h);
+  int rc;
+  if ((rc = check_train_engine(e))) return rc;
+  const mst_forward_args& a = *ap;
+  MST_CHECK_ARG(a.batch > 0 && a.n_frames > 0, "empty batch");
+  MST_CHECK_ARG(!a.cfg, "the training forward runs one pass (the reference trains the unwrapped model)");
+  MST_CHECK_ARG(a.x && a.temb && a.out_cond, "null tensor pointer");
+  MST_CHECK_ARG(a.n_frames + 1 <= e->desc.pe_len, "sequence longer than the positional table");
+  const mst_model_desc& d = e->desc;
+  const int B = a.batch, T = a.n_frames, S = T + 1, dm = d.d_model;
+  Tape tp;
+  MST_CHECK_ARG(tape_bytes >= carve_tape(d, B, S, tape, &tp), "tape too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  Token0Params t0;
+  t0.temb = a.temb; t0.temb_row_dev = a.temb_row_dev; t0.temb_row_offset = a.temb_row_offset;
+  t0.text_emb = a.text_emb; t0.txt_b = e->txt_b; t0.pe = e->pe; t0.x_f32 = tp.l[0].x;
+  t0.B = B; t0.T = T; t0.d = dm; t0.cfg = 0; t0.uncond = a.uncond;
+  if ((rc = token0(t0, B, s))) return rc;
+  {
+    GemmF32Params p;
+    p.a = a.x; p.a_mode = A_MOTION; p.w = e->in_w; p.ldw = d.n_feats; p.bias = e->in_b;
+    p.c = tp.l[0].x; p.ldc = dm; p.M = B * T; p.N = dm; p.K = d.n_feats; p.epi = EPI_INPROJ;
+    p.pe = e->pe; p.B = B; p.T = T; p.n_pass = 1;
+    if ((rc = gemm_f32(p, s))) return rc;
+  }
+  if ((rc = encoder_forward_tape(e, tp, B, S, nullptr, s))) return rc;
+  {
+    GemmF32Params p;
+    p.a = tp.x_out; p.lda = dm; p.w = e->out_w; p.ldw = dm; p.bias = e->out_b;
+    p.c = a.out_cond; p.M = B * S; p.N = d.n_feats; p.K = dm; p.epi = EPI_OUTPROJ; p.T = T; p.B = B;
+    if ((rc = gemm_f32(p, s))) return rc;
+  }
+  return MST_OK;
+}
+
+extern "C" int mst_denoiser_backward(mst_engine_t h, const mst_backward_args* ap, void* stream) {
+  MST_CHECK_ARG(h && ap, "null argument");
+  Engine* e = reinterpret_cast<Engine*>(h);
+  int rc;
+  if ((rc = check_train_engine(e))) return rc;
+  const mst_backward_args& a = *ap;
+  MST_CHECK_ARG(a.batch > 0 && a.n_frames > 0, "empty batch");
+  MST_CHECK_ARG(a.d_out && a.tape && a.scratch && a.layer_grads, "null tensor pointer");
+  const mst_model_desc& d = e->desc;
+  const int B = a.batch, T = a.n_frames, S = T + 1, M = B * S, dm = d.d_model;
+  Tape tp;
+  BwdScratch w;
+  MST_CHECK_ARG(a.tape_bytes >= carve_tape(d, B, S, const_cast<void*>(a.tape), &tp), "tape too small");
+  MST_CHECK_ARG(a.scratch_bytes >= carve_bwd(d, B, S, a.scratch, &w), "scratch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  // OutputProcess backward: g[(b,s)][k] = s == 0 ? 0 : sum_f d_out[b][f][s-1] out_w[f][k]   (into the dqkv scratch's
+  // first [M, d] floats would alias later use - the tape's x_out slot is dead after the forward, reuse it)
+  float* g = tp.x_out;
+  GemmEx go;
+  go.a = a.d_out; go.a_mode = AX_MOTION_TOK; go.T = T; go.tok_off = 1; go.b = e->out_w; go.ldb = dm; go.c = g; go.ldc = dm;
+  go.M = M; go.N = dm; go.K = d.n_feats;
+  if ((rc = gemm_ex(go, s, "bwd_outproj"))) return rc;
+  float* gx = nullptr;
+  if ((rc = encoder_backward(e, tp, a.layer_grads, B, S, g, w, &gx, s))) return rc;
+  if (a.d_x) {  // InputProcess backward: d_x[b][f][t] = sum_n gx[(b,t+1)][n] in_w[n][f]
+    GemmEx gi;
+    gi.a = gx; gi.lda = dm; gi.a_mode = AX_TOKROWS; gi.T = T; gi.tok_off = 1; gi.b = e->in_w; gi.ldb = d.n_feats;
+    gi.c = a.d_x; gi.c_mode = CX_MOTION; gi.M = B * T; gi.N = d.n_feats; gi.K = dm;
+    if ((rc = gemm_ex(gi, s, "bwd_inproj"))) return rc;
+  }
+  return MST_OK;
+}
+
+// MotionEncoder (mdm_forstyledataset.py:89-124): tokens = [muQuery, sigmaQuery, InputProcess(x)] + pe, key-padding
+// mask over the keys, the encoder stack of THIS engine; mu = output row 0 of every sequence.  The engine's in_w /
+// in_b / pe are the frozen mdm_model's (the Python layer loads them so).
+extern "C" int mst_motion_encoder_forward(mst_engine_t h, const float* x, const uint8_t* key_valid, const float* mu_query,
+                                          const float* sigma_query, int32_t batch, int32_t n_frames, float* mu_out,
+                                          void* tape, size_t tape_bytes, void* stream) {
+  MST_CHECK_ARG(h && x && mu_query && sigma_query && mu_out && tape, "null argument");
+  Engine* e = reinterpret_cast<Engine*>(h);
+  int rc;
+  if ((rc = check_train_engine(e))) return rc;
+  const mst_model_desc& d = e->desc;
+  const int B = batch, T = n_frames, S = T + 2, dm = d.d_model;
+  MST_CHECK_ARG(B > 0 && T > 0 && S <= d.pe_len, "bad geometry");
+  Tape tp;
+  MST_CHECK_ARG(tape_bytes >= carve_tape(d, B, S, tape, &tp), "tape too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  GemmEx g;  // tokens[(b, t+2)] = x[b,:,t] in_w^T + in_b
+  g.a = x; g.a_mode = AX_MOTION_TOK; g.T = T; g.tok_off = 2; g.b = e->in_w; g.ldb = d.n_feats; g.trans_b = 1;
+  g.bias = e->in_b; g.c = tp.l[0].x; g.ldc = dm; g.M = B * S; g.N = dm; g.K = d.n_feats;
+  if ((rc = gemm_ex(g, s, "menc_inproj"))) return rc;
+  menc_tokens_kernel<<<B * S, 128, 0, s>>>(mu_query, sigma_query, e->pe, tp.l[0].x, S, dm);
+  MST_LAUNCHED("menc_tokens", s);
+  if ((rc = encoder_forward_tape(e, tp, B, S, key_valid, s))) return rc;
+  MST_CUDA_OK(cudaMemcpy2DAsync(mu_out, (size_t)dm * 4, tp.x_out, (size_t)S * dm * 4, (size_t)dm * 4, B,
+                                cudaMemcpyDeviceToDevice, s));
+  return MST_OK;
+}
+
+// d_x [B,F,T] = d mu / d x (all MotionEncoder parameters are frozen: the reference only needs the input gradient)
+extern "C" int mst_motion_encoder_backward(mst_engine_t h, const float* d_mu, int32_t batch, int32_t n_frames, float* d_x,
+                                           void* tape, size_t tape_bytes, void* scratch, size_t scratch_bytes,
+                                           void* stream) {
+  MST_CHECK_ARG(h && d_mu && d_x && tape && scratch, "null argument");
+  Engine* e = reinterpret_cast<Engine*>(h);
+  int rc;
+  if ((rc = check_train_engine(e))) return rc;
+  const mst_model_desc& d = e->desc;
+  const int B = batch, T = n_frames, S = T + 2, dm = d.d_model;
+  Tape tp;
+  BwdScratch w;
+  MST_CHECK_ARG(tape_bytes >= carve_tape(d, B, S, tape, &tp), "tape too small");
+  MST_CHECK_ARG(scratch_bytes >= carve_bwd(d, B, S, scratch, &w), "scratch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* g = tp.x_out;
+  MST_CUDA_OK(cudaMemsetAsync(g, 0, (size_t)B * S * dm * 4, s));
+  MST_CUDA_OK(cudaMemcpy2DAsync(g, (size_t)S * dm * 4, d_mu, (size_t)dm * 4, (size_t)dm * 4, B, cudaMemcpyDeviceToDevice, s));
+  static const mst_layer_grads kNoGrads[MST_MAX_LAYERS] = {};
+  float* gx = nullptr;
+  if ((rc = encoder_backward(e, tp, kNoGrads, B, S, g, w, &gx, s))) return rc;
+  GemmEx gi;
+  gi.a = gx; gi.lda = dm; gi.a_mode = AX_TOKROWS; gi.T = T; gi.tok_off = 2; gi.b = e->in_w; gi.ldb = d.n_feats;
+  gi.c = d_x; gi.c_mode = CX_MOTION; gi.M = B * T; gi.N = d.n_feats; gi.K = dm;
+  return gemm_ex(gi, s, "menc_bwd_inproj");
+}
+
+extern "C" int mst_masked_l2(const float* a, const float* b, const float* mask, float* loss, const float* grad_loss,
+                             float* grad_b, int32_t rows, int32_t a_rows, int32_t mask_rows, int32_t n_feats,
+                             int32_t n_frames, void* stream) {
+  MST_CHECK_ARG(a && b && mask, "null tensor pointer");
+  MST_CHECK_ARG(rows > 0 && a_rows > 0 && mask_rows > 0 && n_feats > 0 && n_frames > 0, "non-positive size");
+  MST_CHECK_ARG((loss != nullptr) != (grad_b != nullptr), "give either loss (forward) or grad_loss + grad_b (backward)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (loss) {
+    masked_l2_fwd_kernel<<<rows, 256, 0, s>>>(a, b, mask, loss, n_feats, n_frames, a_rows, mask_rows);
+    MST_LAUNCHED("masked_l2_fwd", s);
+  } else {
+    MST_CHECK_ARG(grad_loss != nullptr, "backward needs grad_loss");
+    masked_l2_bwd_kernel<<<rows, 256, 0, s>>>(a, b, mask, grad_loss, grad_b, n_feats, n_frames, a_rows, mask_rows);
+    MST_LAUNCHED("masked_l2_bwd", s);
+  }
+  return MST_OK;
+}
+
+extern "C" int mst_update_step_backward(const float* d_pred_xstart, const float* d_sample, const float* k_table,
+                                        const int64_t* t_vec, int32_t mask_kind, const float* mask, const float* pred_xstart,
+                                        int32_t clip_denoised, float* d_out, int32_t batch, int32_t n_feats,
+                                        int32_t n_frames, void* stream) {
+  MST_CHECK_ARG(d_out && (d_pred_xstart || d_sample), "null tensor pointer");
+  MST_CHECK_ARG(!d_sample || (k_table && t_vec), "d_sample needs the coefficient table and t");
+  MST_CHECK_ARG(mask_kind == MST_MASK_NONE || mask, "mask_kind without a mask");
+  MST_CHECK_ARG(!clip_denoised || pred_xstart, "clip_denoised needs pred_xstart");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = (long long)batch * n_feats * n_frames;
+  update_bwd_kernel<<<ew_blocks(n), 256, 0, s>>>(d_pred_xstart, d_sample, k_table, t_vec, mask, mask_kind, pred_xstart,
+                                                clip_denoised, d_out, batch, n_feats, n_frames);
+  MST_LAUNCHED("update_bwd", s);
+  return MST_OK;
+}
+
+extern "C" int mst_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                              void* stream) {
+  MST_CHECK_ARG(params && grads && exp_avg && exp_avg_sq, "null tensor pointer");
+  MST_CHECK_ARG(n > 0 && step > 0, "n and step must be positive");
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = 1.0f - powf(beta2, (float)step);
+  cudaStream_t s = (cudaStream_t)stream;
+  adamw_kernel<<<ew_blocks(n), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1,
+                                           sqrtf(bc2), grad_scale);
+  MST_LAUNCHED("adamw", s);
+  return MST_OK;
+}
+
+extern "C" int mst_sumsq2(const float* x, const float* y, int64_t n, double* out2, void* stream) {
+  MST_CHECK_ARG(x && out2 && n > 0, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  MST_CUDA_OK(cudaMemsetAsync(out2, 0, 2 * sizeof(double), s));
+  sumsq2_kernel<<<ew_blocks(n), 256, 0, s>>>(x, y, n, out2);
+  MST_LAUNCHED("sumsq2", s);
+  return MST_OK;
+}

@@ -1,0 +1,101 @@
+"""``MixedPrecisionTrainer`` of the reference (``diffusion/fp16_util.py:148-235``), fp32 only (the reference
+hard-codes ``use_fp16 = False``, ``train/training_loop.py:51``), re-laid for one GPU kernel per operation:
+
+* every parameter of the model is moved into ONE flat fp32 arena (trainable tensors first); ``p.data`` become views;
+* ``p.grad`` of the trainable tensors are views of a second flat arena, so ``zero_grad`` is one memset, the
+  data-parallel gradient exchange is one all-reduce, and the optimizer (``train.training_loop.FusedAdamW``) is
+  one ``mst_adamw_step`` launch over the arena;
+* ``_compute_norms`` is one ``mst_sumsq2`` launch and ONE device-to-host read instead of 192 ``.item()`` syncs.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch as th
+
+from .. import engine as K
+
+
+class FlatParams:
+    """Flat arenas behind a model's parameters."""
+
+    def __init__(self, model):
+        params = [p for n, p in model.named_parameters() if not n.startswith("clip_model.") and ".clip_model." not in n]
+        seen, uniq = set(), []
+        for p in params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.trainable = [p for p in uniq if p.requires_grad]
+        self.frozen = [p for p in uniq if not p.requires_grad]
+        if not self.trainable:
+            raise ValueError("the model has no trainable parameters")
+        dev = self.trainable[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("the mst trainer needs the model on a CUDA device (there is no CPU path)")
+        if any(p.dtype != th.float32 or p.device != dev for p in uniq):
+            raise RuntimeError("all parameters must be fp32 on one CUDA device")
+        self.n_train = sum(p.numel() for p in self.trainable)
+        n_all = self.n_train + sum(p.numel() for p in self.frozen)
+        self.params = th.empty(n_all, dtype=th.float32, device=dev)
+        self.grads = th.zeros(self.n_train, dtype=th.float32, device=dev)
+        off = 0
+        with th.no_grad():
+            for p in self.trainable + self.frozen:
+                n = p.numel()
+                view = self.params[off:off + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                if p.requires_grad:
+                    p.grad = self.grads[off:off + n].view(p.shape)
+                off += n
+
+    @property
+    def train_params(self):
+        return self.params[:self.n_train]
+
+    def ensure_grad_views(self):
+        """Re-attach the arena views if someone replaced / dropped ``p.grad`` (e.g. zero_grad(set_to_none=True))."""
+        off = 0
+        for p in self.trainable:
+            n = p.numel()
+            view = self.grads[off:off + n].view(p.shape)
+            if p.grad is None:
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+            off += n
+
+
+class MixedPrecisionTrainer:
+    def __init__(self, *, model, use_fp16=False, fp16_scale_growth=1e-3, initial_lg_loss_scale=20.0):
+        if use_fp16:
+            raise NotImplementedError("fp16 master-weight training is deprecated in the reference "
+                                      "(train/training_loop.py:51) and not built")
+        self.model = model
+        self.use_fp16 = False
+        self.flat = FlatParams(model)
+        self.model_params = self.flat.trainable + self.flat.frozen
+        self.master_params = self.model_params
+        self.lg_loss_scale = initial_lg_loss_scale
+        self.last_norms = (0.0, 0.0)
+
+    def zero_grad(self):
+        self.flat.ensure_grad_views()
+        self.flat.grads.zero_()
+
+    def backward(self, loss: th.Tensor):
+        loss.backward()
+        self.flat.ensure_grad_views()
+
+    def optimize(self, opt):
+        grad_norm, param_norm = self._compute_norms()
+        self.last_norms = (grad_norm, param_norm)
+        opt.step()
+        return True
+
+    def _compute_norms(self, grad_scale=1.0):
+        """(||grad||_2 / grad_scale, ||param||_2) over all master params (reference :215-223)."""
+        sq = K.sumsq2(self.flat.grads, None).cpu()
+        sp = K.sumsq2(self.flat.params, None).cpu()
+        return float(np.sqrt(sq[0].item())) / grad_scale, float(np.sqrt(sp[0].item()))

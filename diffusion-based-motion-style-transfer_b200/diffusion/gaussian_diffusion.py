@@ -101,6 +101,39 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+class _MaskedL2Fn(th.autograd.Function):
+    """masked_l2 rows with an explicit CUDA backward w.r.t. ``b`` (the stacked x0 predictions)."""
+
+    @staticmethod
+    def forward(ctx, a, b, mask):
+        ctx.save_for_backward(a, b, mask)
+        return K.masked_l2_forward(a, b, mask)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, mask = ctx.saved_tensors
+        return None, K.masked_l2_backward(a, b, mask, _f32c(g)), None
+
+
+class _UpdateStepFn(th.autograd.Function):
+    """Fused per-step update with a gradient path x0-prediction -> model output (what
+    p_sample_with_grad / ddim_sample_with_grad keep in the graph, inpainting_gaussian_diffusion.py:66-123, :176-239).
+    ``sample`` is produced outside the graph there (under the loop's no_grad), so only pred_xstart is differentiable."""
+
+    @staticmethod
+    def forward(ctx, out, run, mask, clip_denoised, shape):
+        sample, x0 = run(out)
+        ctx.mask, ctx.clip, ctx.shape = mask, bool(clip_denoised), tuple(shape)
+        ctx.x0 = x0 if clip_denoised else None
+        ctx.mark_non_differentiable(sample)
+        return sample, x0
+
+    @staticmethod
+    def backward(ctx, d_sample, d_x0):
+        d_out = K.update_step_backward(_f32c(d_x0), None, None, None, ctx.mask, ctx.x0, ctx.clip, ctx.shape)
+        return d_out, None, None, None, None
+
+
 class GaussianDiffusion:
     """Sampling utilities of the diffusion process (reference class of the same name, :111)."""
 
@@ -194,11 +227,16 @@ class GaussianDiffusion:
     # ------------------------------------------------------------------ small API
     def masked_l2(self, a, b, mask):
         """sum((a-b)^2 * mask) / (sum(mask) * J*Jdim) per sample (reference :223-235)."""
-        loss = self.l2_loss(a, b)
-        loss = (loss * mask.float()).flatten(1).sum(dim=1)
-        n_entries = a.shape[1] * a.shape[2]
-        non_zero_elements = mask.flatten(1).sum(dim=1) * n_entries
-        return loss / non_zero_elements
+        _require_cuda(b, "masked_l2 input")
+        assert a.shape[1:] == b.shape[1:] and mask.shape[-1] == b.shape[-1]
+        if a.requires_grad and th.is_grad_enabled():
+            raise NotImplementedError("masked_l2 is differentiable w.r.t. its second argument only (the reference "
+                                      "passes the target first, gaussian_diffusion.py:1381)")
+        # expand() views of the reference (target / mask repeated over the stacked steps) are read modulo their rows
+        a_rows = a[:1] if (a.shape[0] > 1 and a.stride(0) == 0) else a
+        m_rows = mask[:1] if (mask.shape[0] > 1 and mask.stride(0) == 0) else mask
+        assert b.shape[0] % a_rows.shape[0] == 0 and b.shape[0] % m_rows.shape[0] == 0
+        return _MaskedL2Fn.apply(_f32c(a_rows), _f32c(b), _f32c(m_rows.reshape(m_rows.shape[0], 1, 1, -1)))
 
     def q_mean_variance(self, x_start, t):
         mean = _extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
@@ -426,17 +464,115 @@ class GaussianDiffusion:
         """One DDIM step (reference :796-847)."""
         return self._sample_step(L.SAMPLER_DDIM, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, eta=eta)
 
-    def p_sample_with_grad(self, *args, **kwargs):
-        raise NotImplementedError(
-            "p_sample_with_grad (differentiable sampling for few_shot_style_finetune_losses) needs the backward "
-            "kernels, which are the next row of the scope table (DESIGN.md section 'Out of scope / next')")
+    def _sample_step_with_grad(self, sampler, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs,
+                               const_noise=False, eta=0.0, step_no=0, pred_xstart_in_graph=False):
+        """p_sample_with_grad / ddim_sample_with_grad (inpainting_gaussian_diffusion.py:66-123, :176-239): the
+        denoiser runs with an activation tape and pred_xstart stays attached to it; x is detached at entry."""
+        if model_kwargs is None:
+            model_kwargs = {}
+        if cond_fn is not None or denoised_fn is not None:
+            raise NotImplementedError("cond_fn / denoised_fn hooks are not supported on the differentiable sampling "
+                                      "path (no reference caller passes them)")
+        _require_cuda(x, "x")
+        native, cfgw = self._unwrap(model)
+        if native is None or cfgw is not None:
+            raise NotImplementedError("differentiable sampling needs a native denoiser without the CFG wrapper "
+                                      "(the reference finetunes the unwrapped StyleDiffusion)")
+        x = _f32c(x.detach())
+        assert t.shape == (x.shape[0],)
+        mask, inp = self._check_inpainting(model_kwargs, x.shape)
+        nmask = self._inpainting_mask_for_noise(model_kwargs)
+        tabs = self.device_tables(x.device, eta)
+        if self.rng == "philox" and self.noise_fn is None:
+            noise_kind, eps = L.NOISE_PHILOX, None
+        else:
+            noise_kind, eps = L.NOISE_TENSOR, self._draw_noise(x, step_no, const_noise)
+            const_noise = False
+        kmask = mask if mask is not None else (_f32c(nmask) if nmask is not None else None)
+        tl = t.to(th.int64).contiguous()
 
-    ddim_sample_with_grad = p_sample_with_grad
+        def run(out):
+            sample, x0 = th.empty_like(x), th.empty_like(x)
+            common = dict(out_cond=_f32c(out), x_t=x, x_prev=sample, pred_xstart=x0, mask=kmask, x_inpaint=inp,
+                          mask_noise=nmask is not None, clip_denoised=clip_denoised, t_vec=tl, noise_kind=noise_kind,
+                          noise=eps, const_noise=const_noise, philox_seed=self.philox_seed,
+                          philox_sample_offset=self.philox_sample_offset)
+            if sampler == L.SAMPLER_DDPM:
+                K.update_step(sampler=sampler, coef1=tabs["c1"], coef2=tabs["c2"], sigma=tabs["sigma"], **common)
+            else:
+                K.update_step(sampler=sampler, coef1=tabs["ddim_c1"], coef2=tabs["ddim_c2"], sigma=tabs["ddim_sigma"],
+                              recip=tabs["recip"], recipm1=tabs["recipm1"], **common)
+            return sample, x0
 
-    def few_shot_style_finetune_losses(self, *args, **kwargs):
-        raise NotImplementedError(
-            "few_shot_style_finetune_losses needs the fused backward kernels (SURVEY section 8 rows A19/A20); "
-            "not built in this round - see DESIGN.md")
+        with th.enable_grad():
+            out = native(x, self._map_model_t(t), **model_kwargs)
+            # the blend only zeroes the gradient where the inpainting mask is set (mask is None without inpainting)
+            sample, x0 = _UpdateStepFn.apply(out, run, mask, clip_denoised, tuple(x.shape))
+        if not pred_xstart_in_graph:
+            x0 = x0.detach()
+        return {"sample": sample.detach(), "pred_xstart": x0}
+
+    def p_sample_with_grad(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                           pred_xstart_in_graph=False, const_noise=False):
+        return self._sample_step_with_grad(L.SAMPLER_DDPM, model, x, t, clip_denoised, denoised_fn, cond_fn,
+                                           model_kwargs, const_noise=const_noise,
+                                           pred_xstart_in_graph=pred_xstart_in_graph)
+
+    def ddim_sample_with_grad(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                              eta=0.0, pred_xstart_in_graph=False):
+        return self._sample_step_with_grad(L.SAMPLER_DDIM, model, x, t, clip_denoised, denoised_fn, cond_fn,
+                                           model_kwargs, eta=eta, pred_xstart_in_graph=pred_xstart_in_graph)
+
+    def few_shot_style_finetune_losses(self, model, x_start, t, x_content_start, x_style_start, skip_steps=700,
+                                       model_kwargs=None, noise=None, model_t2m_kwargs=None, semantic_guidance=0,
+                                       use_ddim=0, Ls=10):
+        """Few-shot style finetune loss (reference :1317-1399): masked L2 between the style example and every x0
+        prediction of a short differentiable sampling run started from the content motion, plus - with
+        ``semantic_guidance`` - ``Ls`` x (1 - cos) between the MotionEncoder's mu of the denoised t2m batch and
+        the CLIP feature of its (style-word-modified) captions.  Returns {'rot_mse', ['text_cosine'], 'loss'}."""
+        native, _ = self._unwrap(model)
+        if native is None:
+            raise NotImplementedError("few_shot_style_finetune_losses needs a native denoiser (StyleDiffusion)")
+        motion_enc = native.controlmdm.motion_enc if hasattr(native, "controlmdm") else native.motion_enc
+        mask = model_kwargs['y']['mask']
+        if noise is None:
+            noise = th.randn_like(x_content_start)
+        terms = {}
+        mu = text_features = None
+        noise_t2m = th.rand_like(x_start)  # sic: uniform noise in the reference (:1334); drawn in the same RNG order
+        if semantic_guidance:
+            # (the reference also runs this forward with semantic_guidance == 0 and discards the result, :1335-1337)
+            x_t = self.q_sample(x_start, t, noise=noise_t2m, model_kwargs=model_t2m_kwargs)
+            model_output = native(x_t, self._map_model_t(t), **model_t2m_kwargs)
+            mu, text_features = motion_enc(model_output, **model_t2m_kwargs)
+        if not use_ddim:
+            sample_fn = self.p_sample_loop
+        else:
+            sample_fn = self.ddim_sample_loop
+            skip_steps = int(skip_steps / 1000 * 20)
+        sample = sample_fn(model, x_content_start.shape, clip_denoised=False, model_kwargs=model_kwargs,
+                           skip_timesteps=skip_steps, init_image=x_content_start, progress=False, dump_steps=None,
+                           noise=None, const_noise=False, cond_fn_with_grad=True, pred_xstart_in_graph=True,
+                           dump_all_xstart=True)
+        num_step = len(sample)
+        sample = th.cat(sample, dim=0)  # noised_step * b_size * J * 1 * seq
+        if self.loss_type not in (LossType.MSE, LossType.RESCALED_MSE):
+            raise NotImplementedError(self.loss_type)
+        assert self.model_mean_type == ModelMeanType.START_X  # only support predict x_0
+        target = x_style_start
+        assert target.shape == x_content_start.shape
+        target = target.expand(num_step, -1, -1, -1)
+        mask = mask.expand(num_step, -1, -1, -1)
+        terms["rot_mse"] = self.masked_l2(target, sample, mask)
+        if semantic_guidance:
+            features_norm = text_features / text_features.norm(dim=-1, keepdim=True)
+            mu_norm = mu / mu.norm(dim=-1, keepdim=True)
+            cos = th.nn.functional.cosine_similarity(features_norm, mu_norm, dim=1, eps=1e-6)
+            terms["text_cosine"] = (1 - cos).mean()
+            terms["loss"] = terms["rot_mse"].mean() + terms["text_cosine"] * Ls
+        else:
+            terms["loss"] = terms["rot_mse"].mean()
+        return terms
 
     # ------------------------------------------------------------------ loops
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
@@ -471,7 +607,7 @@ class GaussianDiffusion:
         yield from self._loop(L.SAMPLER_DDPM, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs,
                               device, progress, skip_timesteps, init_image, randomize_class,
                               cond_fn_with_grad or pred_xstart_in_graph, const_noise, stop_timesteps, 0.0,
-                              _want_xstart, _own_buffers)
+                              _want_xstart, _own_buffers, pred_xstart_in_graph)
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                          model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0, init_image=None,
@@ -504,15 +640,12 @@ class GaussianDiffusion:
         yield from self._loop(L.SAMPLER_DDIM, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs,
                               device, progress, skip_timesteps, init_image, randomize_class,
                               cond_fn_with_grad or pred_xstart_in_graph, False, stop_timesteps, eta, _want_xstart,
-                              _own_buffers)
+                              _own_buffers, pred_xstart_in_graph)
 
     # the shared driver -----------------------------------------------------------
     def _loop(self, sampler, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress,
               skip_timesteps, init_image, randomize_class, with_grad, const_noise, stop_timesteps, eta, want_xstart,
-              own_buffers):
-        if with_grad:
-            raise NotImplementedError(
-                "cond_fn_with_grad / pred_xstart_in_graph sampling needs the backward kernels (not built this round)")
+              own_buffers, pred_xstart_in_graph=False):
         if device is None:
             try:
                 device = next(model.parameters()).device
@@ -539,7 +672,7 @@ class GaussianDiffusion:
 
         native, cfgw = self._unwrap(model)
         fused = (native is not None and cond_fn is None and denoised_fn is None and not randomize_class
-                 and model_kwargs is not None and 'y' in model_kwargs and native.mst_ready(img))
+                 and not with_grad and model_kwargs is not None and 'y' in model_kwargs and native.mst_ready(img))
         if fused:
             yield from self._fused_trajectory(sampler, native, cfgw, img, indices, clip_denoised, model_kwargs,
                                               const_noise, eta, progress, want_xstart, own_buffers)
@@ -554,8 +687,13 @@ class GaussianDiffusion:
                 model_kwargs['y'] = th.randint(low=0, high=model.num_classes, size=model_kwargs['y'].shape,
                                                device=model_kwargs['y'].device)
             with th.no_grad():
-                out = self._sample_step(sampler, model, img, t, clip_denoised, denoised_fn, cond_fn, model_kwargs,
-                                        const_noise=const_noise, eta=eta, step_no=step_no)
+                if with_grad:  # reference :781 / :1069: the *_with_grad step re-enables autograd around the model
+                    out = self._sample_step_with_grad(sampler, model, img, t, clip_denoised, denoised_fn, cond_fn,
+                                                      model_kwargs, const_noise=const_noise, eta=eta, step_no=step_no,
+                                                      pred_xstart_in_graph=pred_xstart_in_graph)
+                else:
+                    out = self._sample_step(sampler, model, img, t, clip_denoised, denoised_fn, cond_fn, model_kwargs,
+                                            const_noise=const_noise, eta=eta, step_no=step_no)
                 yield out
                 img = out["sample"]
 

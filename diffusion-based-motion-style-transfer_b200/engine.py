@@ -166,6 +166,137 @@ class Engine:
         return (out_cond, out_uncond) if cfg else out_cond
 
 
+    # -- training path (fp32 engines) ------------------------------------------------
+    def train_sizes(self, n_seqs: int, seq_len: int):
+        """(tape bytes, backward scratch bytes) for n_seqs sequences of seq_len tokens."""
+        tb, sb = C.c_size_t(), C.c_size_t()
+        L.check(self.lib.mst_train_sizes(self._h, n_seqs, seq_len, C.byref(tb), C.byref(sb)), "mst_train_sizes")
+        return int(tb.value), int(sb.value)
+
+    def _scratch(self, nbytes: int) -> torch.Tensor:
+        if getattr(self, "_bwd_scratch", None) is None or self._bwd_scratch.numel() < nbytes:
+            self._bwd_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._bwd_scratch
+
+    def forward_train(self, x: torch.Tensor, temb: torch.Tensor, text_emb: Optional[torch.Tensor], *,
+                      uncond: bool = False):
+        """Denoiser forward that records the activation tape.  Returns (out [B,F,1,T], tape)."""
+        B, T = x.shape[0], x.shape[-1]
+        if x.numel() != B * self.n_feats * T:
+            raise ValueError(f"x has shape {tuple(x.shape)}, expected [B,{self.n_feats},1,T]")
+        tape_bytes, _ = self.train_sizes(B, T + 1)
+        tape = torch.empty(tape_bytes, dtype=torch.uint8, device=self.device)
+        out = torch.empty_like(x)
+        a = L.ForwardArgs()
+        a.batch, a.n_frames, a.cfg, a.uncond = B, T, 0, int(uncond)
+        a.x = _ptr(x, name="x")
+        a.temb = _ptr(temb, name="temb")
+        a.temb_row_dev, a.temb_row_offset = None, 0
+        a.text_emb = _ptr(text_emb, name="text_emb")
+        a.out_cond, a.out_uncond = _ptr(out, name="out"), None
+        a.workspace, a.workspace_bytes = None, 0
+        L.check(self.lib.mst_denoiser_forward_train(self._h, C.byref(a), tape.data_ptr(), tape.numel(), _stream_ptr()),
+                "mst_denoiser_forward_train")
+        return out, tape
+
+    def backward(self, d_out: torch.Tensor, tape: torch.Tensor, layer_grads: list, want_dx: bool = False):
+        """Back-propagate d_out [B,F,1,T] through the taped forward.  layer_grads: per layer a dict keyed by LAYER_KEYS
+        of fp32 CUDA tensors (or None) that the gradients are ACCUMULATED into.  Returns d_x or None."""
+        B, T = d_out.shape[0], d_out.shape[-1]
+        _, scratch_bytes = self.train_sizes(B, T + 1)
+        scratch = self._scratch(scratch_bytes)
+        n_layers = self.desc.n_layers
+        if len(layer_grads) != n_layers:
+            raise ValueError(f"expected {n_layers} layer gradient dicts, got {len(layer_grads)}")
+        arr = (L.LayerGrads * n_layers)()
+        for i, lg in enumerate(layer_grads):
+            for k in self.LAYER_KEYS:
+                setattr(arr[i], k, _ptr(lg.get(k), name=f"grad.layer{i}.{k}"))
+        d_x = torch.empty_like(d_out) if want_dx else None
+        a = L.BackwardArgs()
+        a.batch, a.n_frames = B, T
+        a.d_out, a.d_x = _ptr(d_out, name="d_out"), _ptr(d_x, name="d_x")
+        a.layer_grads = arr
+        a.tape, a.tape_bytes = tape.data_ptr(), tape.numel()
+        a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+        L.check(self.lib.mst_denoiser_backward(self._h, C.byref(a), _stream_ptr()), "mst_denoiser_backward")
+        return d_x
+
+    def motion_encoder_forward(self, x: torch.Tensor, key_valid: Optional[torch.Tensor], mu_query: torch.Tensor,
+                               sigma_query: torch.Tensor):
+        """MotionEncoder.forward on this engine's stack.  Returns (mu [B,d], tape)."""
+        B, T = x.shape[0], x.shape[-1]
+        tape_bytes, _ = self.train_sizes(B, T + 2)
+        tape = torch.empty(tape_bytes, dtype=torch.uint8, device=self.device)
+        mu = torch.empty(B, self.d_model, dtype=torch.float32, device=self.device)
+        L.check(self.lib.mst_motion_encoder_forward(
+            self._h, _ptr(x, name="x"), _ptr(key_valid, torch.uint8, "key_valid"), _ptr(mu_query, name="muQuery"),
+            _ptr(sigma_query, name="sigmaQuery"), B, T, mu.data_ptr(), tape.data_ptr(), tape.numel(), _stream_ptr()),
+            "mst_motion_encoder_forward")
+        return mu, tape
+
+    def motion_encoder_backward(self, d_mu: torch.Tensor, tape: torch.Tensor, shape):
+        B, T = shape[0], shape[-1]
+        _, scratch_bytes = self.train_sizes(B, T + 2)
+        scratch = self._scratch(scratch_bytes)
+        d_x = torch.empty(shape, dtype=torch.float32, device=self.device)
+        L.check(self.lib.mst_motion_encoder_backward(
+            self._h, _ptr(d_mu, name="d_mu"), B, T, d_x.data_ptr(), tape.data_ptr(), tape.numel(), scratch.data_ptr(),
+            scratch.numel(), _stream_ptr()), "mst_motion_encoder_backward")
+        return d_x
+
+
+# ---------------------------------------------------------------------------------
+# training kernels that need no engine
+# ---------------------------------------------------------------------------------
+def masked_l2_forward(a, b, mask):
+    """masked_l2 rows (reference gaussian_diffusion.py:223-235): a [Ra,F,1,T] (rows repeat), b [R,F,1,T], mask [Rm,1,1,T]."""
+    R, F, T = b.shape[0], b.shape[1] * b.shape[2], b.shape[3]
+    loss = torch.empty(R, dtype=torch.float32, device=b.device)
+    L.check(L.load().mst_masked_l2(_ptr(a, name="a"), _ptr(b, name="b"), _ptr(mask, name="mask"), loss.data_ptr(), None, None,
+                                   R, a.shape[0], mask.shape[0], F, T, _stream_ptr()), "mst_masked_l2")
+    return loss
+
+
+def masked_l2_backward(a, b, mask, grad_loss):
+    R, F, T = b.shape[0], b.shape[1] * b.shape[2], b.shape[3]
+    gb = torch.empty_like(b)
+    L.check(L.load().mst_masked_l2(_ptr(a, name="a"), _ptr(b, name="b"), _ptr(mask, name="mask"), None,
+                                   _ptr(grad_loss, name="grad_loss"), gb.data_ptr(), R, a.shape[0], mask.shape[0], F, T,
+                                   _stream_ptr()), "mst_masked_l2")
+    return gb
+
+
+def update_step_backward(d_x0, d_sample, k_table, t_vec, mask, pred_xstart, clip_denoised, shape):
+    B, F, T = shape[0], shape[1] * shape[2], shape[3]
+    ref = d_x0 if d_x0 is not None else d_sample
+    d_out = torch.empty(shape, dtype=torch.float32, device=ref.device)
+    L.check(L.load().mst_update_step_backward(
+        _ptr(d_x0, name="d_pred_xstart"), _ptr(d_sample, name="d_sample"), _ptr(k_table, name="k_table"),
+        _ptr(t_vec, torch.int64, "t"), mask_kind_of(mask, shape), _ptr(mask, name="inpainting_mask"),
+        _ptr(pred_xstart, name="pred_xstart") if clip_denoised else None, int(bool(clip_denoised)), d_out.data_ptr(),
+        B, F, T, _stream_ptr()), "mst_update_step_backward")
+    return d_out
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,
+               grad_scale=1.0):
+    """torch.optim.AdamW step over flat fp32 arenas, one launch."""
+    n = params.numel()
+    if not (grads.numel() == exp_avg.numel() == exp_avg_sq.numel() == n):
+        raise ValueError("adamw_step: arenas differ in size")
+    L.check(L.load().mst_adamw_step(_ptr(params, name="params"), _ptr(grads, name="grads"), _ptr(exp_avg, name="exp_avg"),
+                                    _ptr(exp_avg_sq, name="exp_avg_sq"), n, lr, beta1, beta2, eps, weight_decay, int(step),
+                                    grad_scale, _stream_ptr()), "mst_adamw_step")
+
+
+def sumsq2(x, y=None):
+    """device float64 [2] = (sum x^2, sum y^2)."""
+    out = torch.empty(2, dtype=torch.float64, device=x.device)
+    L.check(L.load().mst_sumsq2(_ptr(x, name="x"), _ptr(y, name="y"), x.numel(), out.data_ptr(), _stream_ptr()), "mst_sumsq2")
+    return out
+
+
 # ---------------------------------------------------------------------------------
 # fused diffusion kernels (no engine needed)
 # ---------------------------------------------------------------------------------

@@ -129,6 +129,73 @@ def _load_clip(clip_version):
 
 
 # ----------------------------------------------------------------------------------
+# autograd bridges: the forward records an activation tape in the C-ABI engine, the backward is the explicit
+# CUDA backward (csrc/train.cu).  torch only routes the gradient tensors (plumbing).
+# ----------------------------------------------------------------------------------
+def _flat_layer_grads(params_by_layer, needs):
+    """One zero arena for the gradients of every trainable encoder parameter + per-layer dicts of views."""
+    total = sum(p.numel() for lp in params_by_layer for k, p in lp.items() if needs[id(p)])
+    ref = next(p for lp in params_by_layer for p in lp.values())
+    arena = torch.zeros(total, dtype=torch.float32, device=ref.device)
+    off, out = 0, []
+    for lp in params_by_layer:
+        d = {}
+        for k, p in lp.items():
+            if needs[id(p)]:
+                d[k] = arena[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            else:
+                d[k] = None
+        out.append(d)
+    return out
+
+
+class _DenoiserGradFn(torch.autograd.Function):
+    """x0 prediction with a gradient path to the encoder-layer parameters (and to x when it requires grad)."""
+
+    @staticmethod
+    def forward(ctx, native, x, temb, text_emb, uncond, *params):
+        eng = native.mst_engine(x.device, precision="fp32")
+        out, tape = eng.forward_train(x, temb, text_emb, uncond=uncond)
+        ctx.native, ctx.eng, ctx.tape = native, eng, tape
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        if ctx.tape is None:
+            raise RuntimeError("the mst activation tape of this forward was already consumed by a backward pass "
+                               "(retain_graph is not supported: run the forward again)")
+        layers = [l.mst_tensors() for l in ctx.native._mst_encoder().layers]
+        flat = [p for lp in layers for p in lp.values()]
+        needs = {id(p): bool(ctx.needs_input_grad[5 + i]) for i, p in enumerate(flat)}
+        grads = _flat_layer_grads(layers, needs)
+        d_x = ctx.eng.backward(d_out.float().contiguous(), ctx.tape, grads, want_dx=bool(ctx.needs_input_grad[1]))
+        ctx.tape = None
+        return (None, d_x, None, None, None) + tuple(g for lg in grads for g in lg.values())
+
+
+class _MotionEncoderGradFn(torch.autograd.Function):
+    """mu of MotionEncoder.forward with a gradient path to its input motion only (its parameters are frozen)."""
+
+    @staticmethod
+    def forward(ctx, enc, x, key_valid):
+        eng = enc.mst_engine(x.device, precision="fp32")
+        mu, tape = eng.motion_encoder_forward(x, key_valid, enc.muQuery.detach().reshape(-1).contiguous(),
+                                              enc.sigmaQuery.detach().reshape(-1).contiguous())
+        ctx.eng, ctx.tape, ctx.shape = eng, tape, tuple(x.shape)
+        return mu
+
+    @staticmethod
+    def backward(ctx, d_mu):
+        if ctx.tape is None:
+            raise RuntimeError("the mst activation tape of this forward was already consumed by a backward pass")
+        d_x = ctx.eng.motion_encoder_backward(d_mu.float().contiguous(), ctx.tape, ctx.shape) \
+            if ctx.needs_input_grad[1] else None
+        ctx.tape = None
+        return None, d_x, None
+
+
+# ----------------------------------------------------------------------------------
 class NativeDenoiser(nn.Module):
     """Common engine plumbing of MDM and StyleDiffusion."""
 
@@ -176,9 +243,15 @@ class NativeDenoiser(nn.Module):
                                "to the CUDA device first (there is no CPU fallback)")
         return True
 
-    def mst_engine(self, device) -> Engine:
+    def mst_weights_changed(self):
+        """Call after parameters were updated behind torch's back (the fused optimizer writes through raw
+        pointers, which does not bump the tensors' version counters): forces a re-pack on next use."""
+        for ent in self.__dict__.get("_mst_engines", {}).values():
+            ent[1] = None
+
+    def mst_engine(self, device, precision=None) -> Engine:
         """Engine for this module on ``device``; weights are (re)packed whenever a parameter changed."""
-        prec = self.mst_precision or default_precision()
+        prec = precision or self.mst_precision or default_precision()
         key = (str(device), prec)
         cache = self.__dict__.setdefault("_mst_engines", {})
         top, layers = self._mst_all_tensors()
@@ -239,12 +312,12 @@ class NativeDenoiser(nn.Module):
             feat = self.encode_text(y['text'])
         return self.mask_cond(feat.to(device).float()).contiguous()
 
-    def text_embedding(self, y, device):
+    def text_embedding(self, y, device, precision=None):
         """embed_text(mask_cond(clip(text))) [B, d]; computed once per trajectory by the sampler."""
         feat = self.text_features(y, device)
         if feat is None:
             return None
-        return self.mst_engine(device).text_embed(feat)
+        return self.mst_engine(device, precision).text_embed(feat)
 
     @staticmethod
     def compact_mask(mask):
@@ -267,14 +340,42 @@ class NativeDenoiser(nn.Module):
         if not self.mst_ready(x):
             raise RuntimeError("the mst denoiser runs on CUDA tensors only (no CPU fallback)")
         y = y if y is not None else {}
-        eng = self.mst_engine(x.device)
         force_mask = bool(y.get('uncond', False))
         xc = x.float().contiguous()
+        if self._mst_wants_grad(xc):
+            # training / differentiable-sampling path (fp32 engine with an activation tape)
+            enc_params = [p for l in self._mst_encoder().layers for p in l.mst_tensors().values()]
+            with torch.no_grad():
+                eng = self.mst_engine(x.device, precision="fp32")
+                temb = eng.time_embed(timesteps)
+                text_emb = None if force_mask else self.text_embedding(y, x.device, precision="fp32")
+            if 'text' in self.cond_mode and text_emb is None and not force_mask:
+                raise RuntimeError("text-conditioned model called without text")
+            return _DenoiserGradFn.apply(self, xc, temb, text_emb, force_mask or text_emb is None, *enc_params)
+        eng = self.mst_engine(x.device)
         temb = eng.time_embed(timesteps)
         text_emb = None if force_mask else self.text_embedding(y, x.device)
         if 'text' in self.cond_mode and text_emb is None and not force_mask:
             raise RuntimeError("text-conditioned model called without text")
         return eng.forward(xc, temb, text_emb, cfg=False, uncond=force_mask or text_emb is None)
+
+    def _mst_wants_grad(self, x) -> bool:
+        """True when autograd is recording and something upstream of the output needs a gradient.  Only the encoder
+        stack is differentiable w.r.t. its parameters (the reference finetunes StyleDiffusion.seqTransEncoder with
+        every other module frozen, mdm_forstyledataset.py:562-567); trainable projections / embedders raise."""
+        if not torch.is_grad_enabled():
+            return False
+        enc = any(p.requires_grad for l in self._mst_encoder().layers for p in l.parameters())
+        if not (enc or x.requires_grad):
+            return False
+        f = self._mst_front()
+        front = [f.input_process, f.output_process, f.embed_timestep] + ([f.embed_text] if hasattr(f, "embed_text") else [])
+        if any(p.requires_grad for m in front for p in m.parameters()):
+            raise NotImplementedError(
+                "gradients w.r.t. the in/out projections and the time/text embedders are not built: the reference's "
+                "finetune path trains only StyleDiffusion.seqTransEncoder (freeze the other modules or run under "
+                "torch.no_grad())")
+        return True
 
     def forward_cfg(self, x, timesteps, y):
         """Both passes of ClassifierFreeSampleModel.forward batched: returns (out_cond, out_uncond)."""
@@ -362,11 +463,10 @@ class MDM(NativeDenoiser):
         return [p for name, p in self.named_parameters() if not name.startswith('clip_model.')]
 
 
-class MotionEncoder(nn.Module):
-    """Parameter holder of the reference's frozen semantic discriminator (mdm_forstyledataset.py:11-124).
-    Its own forward (mu/sigma query tokens + key-padding mask) is only used by the finetune loss and is
-    listed under "next" in the scope table; here it carries ``mdm_model``, whose projections and
-    embedders ``StyleDiffusion`` borrows."""
+class MotionEncoder(NativeDenoiser):
+    """The reference's frozen semantic discriminator (mdm_forstyledataset.py:11-124): two learned query tokens
+    (mu, sigma) in front of InputProcess(x), its own encoder stack with a key-padding mask, mu = output token 0.
+    It also carries ``mdm_model``, whose projections and embedders ``StyleDiffusion`` borrows."""
 
     def __init__(self, modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot,
                  latent_dim=256, ff_size=1024, num_layers=8, num_heads=4, dropout=0.1,
@@ -376,6 +476,9 @@ class MotionEncoder(nn.Module):
         self.latent_dim, self.ff_size, self.num_layers, self.num_heads = latent_dim, ff_size, num_layers, num_heads
         self.njoints, self.nfeats = njoints, nfeats
         self.input_feats = njoints * nfeats
+        self.clip_dim = clip_dim
+        self.cond_mode = kargs.get('cond_mode', 'no_cond')
+        self.dataset = dataset
         self.cond_mask_prob = kargs.get('cond_mask_prob', 0.)
         self.muQuery = nn.Parameter(torch.randn(1, latent_dim))
         self.sigmaQuery = nn.Parameter(torch.randn(1, latent_dim))
@@ -400,9 +503,36 @@ class MotionEncoder(nn.Module):
         assert len(unexpected_keys) == 0
         assert all([k.startswith('clip_model.') for k in missing_keys])
 
+    def _mst_front(self):
+        return self.mdm_model
+
+    def _mst_encoder(self):
+        return self.seqTransEncoder
+
+    def mask_cond(self, cond, force_mask=False):
+        return cond  # reference :126-127
+
+    def encode_text(self, raw_text):
+        return self.mdm_model.encode_text(raw_text)
+
     def forward(self, x, y=None):
-        raise NotImplementedError("MotionEncoder.forward (semantic guidance of the finetune loss) is the N3 "
-                                  "'next' row of the scope table and is not built in this round")
+        """x [B, njoints, nfeats, T] -> (mu [B, d], CLIP text features [B, clip_dim] or None)  (reference :89-124).
+        Differentiable w.r.t. x (the finetune loss back-propagates the cosine term into the denoiser's output)."""
+        if not self.mst_ready(x):
+            raise RuntimeError("the mst MotionEncoder runs on CUDA tensors only (no CPU fallback)")
+        bs, nframes = x.shape[0], x.shape[-1]
+        enc_text = None
+        if y is not None:
+            mask = y.get("mask").to(x.device).squeeze(1).squeeze(1).bool()
+            if y.get('text_feat', None) is not None:
+                enc_text = y['text_feat'].to(x.device).float()
+            elif y.get('text', None) is not None:
+                enc_text = self.mdm_model.encode_text(y['text'])
+        else:
+            mask = torch.ones((bs, nframes), dtype=torch.bool, device=x.device)
+        key_valid = torch.cat((torch.ones((bs, 2), dtype=torch.bool, device=x.device), mask), dim=1).to(torch.uint8)
+        mu = _MotionEncoderGradFn.apply(self, x.float().contiguous(), key_valid.contiguous())
+        return mu, enc_text
 
 
 class StyleDiffusion(NativeDenoiser):

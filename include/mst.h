@@ -260,6 +260,91 @@ int mst_philox_normal(float* out, int32_t batch, int64_t per_sample, uint64_t se
                       uint64_t sample_offset, int32_t t, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * Training path - fp32, MST_PREC_FP32 engines.
+ * The reference lets torch autograd differentiate StyleDiffusion.forward
+ * (model/mdm_forstyledataset.py:602-625) inside
+ * few_shot_style_finetune_losses (diffusion/gaussian_diffusion.py:1317-1399);
+ * here the forward records an activation tape and the backward is explicit.
+ * Dropout is the identity.
+ * ------------------------------------------------------------------------ */
+/* Gradient buffers of one encoder layer, same order and shapes as
+ * mst_layer_weights.  Gradients are ACCUMULATED (+=) into non-NULL buffers
+ * (torch .grad semantics); a NULL pointer skips that gradient.             */
+typedef struct {
+  float* qkv_w; float* qkv_b; float* o_w; float* o_b; float* w1; float* b1; float* w2; float* b2;
+  float* ln1_g; float* ln1_b; float* ln2_g; float* ln2_b;
+} mst_layer_grads;
+
+/* Bytes of the activation tape / of the backward scratch for n_seqs sequences
+ * of seq_len TOKENS (T+1 for the denoiser, T+2 for the MotionEncoder).      */
+int mst_train_sizes(mst_engine_t e, int32_t n_seqs, int32_t seq_len, size_t* tape_bytes, size_t* scratch_bytes);
+
+/* mst_denoiser_forward (cfg must be 0) that also fills `tape`.              */
+int mst_denoiser_forward_train(mst_engine_t e, const mst_forward_args* a, void* tape, size_t tape_bytes, void* stream);
+
+typedef struct {
+  int32_t batch, n_frames;
+  const float* d_out;       /* [B,F,T] gradient w.r.t. the model output      */
+  float* d_x;               /* [B,F,T] gradient w.r.t. x, or NULL            */
+  const mst_layer_grads* layer_grads; /* host array of n_layers entries      */
+  void* tape;               /* filled by mst_denoiser_forward_train; the
+                               backward reuses dead slots as scratch, so a
+                               tape can be back-propagated ONCE              */
+  size_t tape_bytes;
+  void* scratch;
+  size_t scratch_bytes;
+} mst_backward_args;
+
+int mst_denoiser_backward(mst_engine_t e, const mst_backward_args* a, void* stream);
+
+/* sizeof() of the training structs as compiled (binding self-check, no GPU). */
+int mst_abi_sizes_train(size_t* layer_grads, size_t* backward_args);
+
+/* MotionEncoder.forward (model/mdm_forstyledataset.py:89-124): tokens
+ * [muQuery, sigmaQuery, InputProcess(x)] + pe, encoder stack of THIS engine
+ * with a key-padding mask (key_valid [B, T+2] bytes, 1 = attend; NULL = all),
+ * mu_out [B, d] = output token 0.  The engine's in_w/in_b/pe must be the
+ * frozen mdm_model's.  The backward yields only d_x: every MotionEncoder
+ * parameter is frozen in the finetune loss.                                 */
+int mst_motion_encoder_forward(mst_engine_t e, const float* x, const uint8_t* key_valid, const float* mu_query,
+                               const float* sigma_query, int32_t batch, int32_t n_frames, float* mu_out, void* tape,
+                               size_t tape_bytes, void* stream);
+int mst_motion_encoder_backward(mst_engine_t e, const float* d_mu, int32_t batch, int32_t n_frames, float* d_x,
+                                void* tape, size_t tape_bytes, void* scratch, size_t scratch_bytes, void* stream);
+
+/* masked_l2 (diffusion/gaussian_diffusion.py:223-235) over `rows` rows of
+ * b [rows,F,T]; a ([a_rows,F,T]) and mask ([mask_rows,T]) rows are taken
+ * modulo their row counts (the reference expands them over the stacked
+ * steps).  Forward: loss [rows] (grad_* NULL).  Backward: grad_b [rows,F,T]
+ * = grad_loss[row] * d loss / d b (loss NULL).                              */
+int mst_masked_l2(const float* a, const float* b, const float* mask, float* loss, const float* grad_loss,
+                  float* grad_b, int32_t rows, int32_t a_rows, int32_t mask_rows, int32_t n_feats, int32_t n_frames,
+                  void* stream);
+
+/* Gradient of mst_update_step w.r.t. the (non-CFG) model output:
+ * d_out = (d_pred_xstart + k_table[t] * d_sample) * (1 - mask), zeroed where
+ * the x0 clamp was active.  k_table: d sample / d x0 per timestep (DDPM:
+ * posterior_mean_coef1; DDIM: sqrt(abar_prev) - sqrt(1-abar_prev-sig^2) /
+ * sqrt_recipm1).  Either gradient may be NULL.
+ * (inpainting_gaussian_diffusion.py:66-123, :176-239)                       */
+int mst_update_step_backward(const float* d_pred_xstart, const float* d_sample, const float* k_table,
+                             const int64_t* t_vec, int32_t mask_kind, const float* mask, const float* pred_xstart,
+                             int32_t clip_denoised, float* d_out, int32_t batch, int32_t n_feats, int32_t n_frames,
+                             void* stream);
+
+/* torch.optim.AdamW step over flat fp32 arenas (train/training_loop.py:97-99);
+ * grads are multiplied by grad_scale first (1/world_size after a SUM
+ * all-reduce).  `step` is the 1-based step count.                           */
+int mst_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                   void* stream);
+
+/* out2[0] = sum x^2, out2[1] = sum y^2 (y may be NULL) as float64 on the
+ * device: MixedPrecisionTrainer._compute_norms (diffusion/fp16_util.py:
+ * 215-223) without its 192 host syncs.                                      */
+int mst_sumsq2(const float* x, const float* y, int64_t n, double* out2, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Kernel-level test hooks (used by tests/ and bench.py roofline legs only).
  * ------------------------------------------------------------------------ */
 /* C[M,N] (fp32) = A[M,K](bf16) * W[N,K](bf16)^T + bias[N], tcgen05 path.    */

@@ -1,0 +1,292 @@
+"""GPU: the finetune path - taped forward, explicit backward, MotionEncoder,
+masked-L2 loss, differentiable sampling, AdamW / norms - against (a) the oracle's torch-CPU autograd on the same
+seeded inputs and (b) tests/golden/finetune.npz, produced by the REAL reference
+(tests/golden/make_golden_finetune.py: StyleDiffusion + few_shot_style_finetune_losses + backward + AdamW).
+
+Tolerance: fp32 everywhere, gradients / losses within 2e-4 relative (max |a-b| / max |b| per tensor); the oracle
+itself sits within 1e-6 of the reference.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import Args, relerr
+from oracle import denoiser as OD
+from oracle import finetune as OF
+from oracle.weights import NoiseTape, mdm_state_dict, text_features
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 2e-4
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def FI_digest(t):
+    t = t.detach().double().flatten().cpu()
+    return np.array([t.norm().item(), t.sum().item()] + t[:14].tolist(), dtype=np.float64)
+
+
+def _golden_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_finetune_inputs",
+                                                  os.path.join(REPO, "tests", "golden", "finetune_inputs.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return dict(np.load(os.path.join(REPO, "tests", "golden", "finetune.npz")))
+
+
+@pytest.fixture(scope="module")
+def FI():
+    return _golden_module()
+
+
+def _style_model(mu, FI, tmp_path_factory):
+    """mst StyleDiffusion with the golden script's deterministic weights (frozen MDM front, own encoder, MotionEncoder)."""
+    from mst_b200.model.mdm_forstyledataset import StyleDiffusion
+    tmp = tmp_path_factory.mktemp("ckpt")
+    front, enc, menc = mdm_state_dict(181, seed=0), FI.style_encoder_state(), FI.motion_encoder_state()
+    torch.save(front, tmp / "mdm.pt")
+    torch.save(menc, tmp / "menc.pt")
+    args = Args()
+    args.mdm_path, args.semantic_discriminator_path = str(tmp / "mdm.pt"), str(tmp / "menc.pt")
+    model = StyleDiffusion(**mu.get_transfer_args(args))
+    missing, unexpected = model.load_state_dict(enc, strict=False)
+    assert not unexpected and all(k.startswith("motion_enc.") for k in missing)
+    return model.to(DEV).eval(), front, enc, menc
+
+
+@pytest.fixture(scope="module")
+def mu():
+    from mst_b200.utils import model_util
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return model_util
+
+
+@pytest.fixture(scope="module")
+def style(mu, FI, tmp_path_factory):
+    return _style_model(mu, FI, tmp_path_factory)
+
+
+def test_taped_forward_equals_inference_forward(style):
+    model, *_ = style
+    model.mst_precision = "fp32"
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 181, 1, 20, generator=g).to(DEV)
+    t = torch.tensor([999, 10], device=DEV)
+    y = {"text_feat": text_features(["a", "b"]).to(DEV), "text": ["a", "b"]}
+    with torch.no_grad():
+        ref = model(x, t, y)
+    out = model(x, t, y)  # grad mode: taped fp32 path
+    assert out.requires_grad and out.grad_fn is not None
+    assert relerr(out.detach(), ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,T", [(2, 20), (1, 76), (3, 33)])
+def test_denoiser_backward_matches_oracle_autograd(style, B, T):
+    model, front, enc, _ = style
+    g = torch.Generator().manual_seed(100 + T)
+    x = torch.randn(B, 181, 1, T, generator=g)
+    d_out = torch.randn(B, 181, 1, T, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    feat = text_features(["walk", "run", "jump"][:B])
+    # oracle: torch-CPU autograd over the plain tensor algebra
+    w_enc = {k: v.clone().requires_grad_(True) for k, v in enc.items()}
+    xo = x.clone().requires_grad_(True)
+    out_o = OD.mdm_forward(front, xo, t, feat, enc_w=w_enc)
+    (out_o * d_out).sum().backward()
+    # product
+    model.zero_grad(set_to_none=True)
+    xg = x.to(DEV).requires_grad_(True)
+    out = model(xg, t.to(DEV), {"text_feat": feat.to(DEV), "text": ["x"] * B})
+    assert relerr(out.detach(), out_o.detach()) < 1e-4
+    (out * d_out.to(DEV)).sum().backward()
+    assert relerr(xg.grad, xo.grad) < TOL
+    worst = 0.0
+    for name, p in model.seqTransEncoder.named_parameters():
+        e = relerr(p.grad, w_enc["seqTransEncoder." + name].grad)
+        worst = max(worst, e)
+        assert e < TOL, (name, e)
+    print(f"B={B} T={T}: worst parameter-gradient rel err {worst:.2e}")
+    # gradients accumulate (torch .grad semantics): a second backward doubles them
+    before = model.seqTransEncoder.layers[3].linear1.weight.grad.clone()
+    out2 = model(x.to(DEV), t.to(DEV), {"text_feat": feat.to(DEV), "text": ["x"] * B})
+    (out2 * d_out.to(DEV)).sum().backward()
+    assert relerr(model.seqTransEncoder.layers[3].linear1.weight.grad, 2 * before) < 1e-5
+
+
+def test_motion_encoder_matches_reference_golden(style, gold, FI):
+    model, *_ = style
+    inp = FI.make_inputs()
+    x = inp["x_start"].to(DEV).requires_grad_(True)
+    y = {"mask": inp["frame_mask_t2m"][:, None, None, :].to(DEV), "text_feat": text_features(inp["texts_t2m"]).to(DEV)}
+    mu_, feat = model.motion_enc(x, y)
+    assert relerr(mu_.detach(), gold["menc/mu"]) < 1e-4
+    assert torch.equal(feat.cpu(), text_features(inp["texts_t2m"]))
+    (mu_ * torch.from_numpy(gold["menc/w"]).to(DEV)).sum().backward()
+    assert relerr(x.grad, gold["menc/dx"]) < TOL
+
+
+def test_masked_l2_kernel_forward_backward():
+    from mst_b200.diffusion.gaussian_diffusion import GaussianDiffusion  # noqa: F401
+    from mst_b200 import engine as K
+    g = torch.Generator().manual_seed(5)
+    R, F, T = 6, 181, 20
+    a = torch.randn(1, F, 1, T, generator=g)
+    b = torch.randn(R, F, 1, T, generator=g).requires_grad_(True)
+    mask = (torch.arange(T) < 13).float().view(1, 1, 1, T)
+    want = OF.masked_l2(a.expand(R, -1, -1, -1), b, mask.expand(R, -1, -1, -1))
+    gl = torch.randn(R, generator=g)
+    (want * gl).sum().backward()
+    got = K.masked_l2_forward(a.to(DEV), b.detach().to(DEV), mask.to(DEV))
+    assert relerr(got, want.detach()) < 1e-6
+    gb = K.masked_l2_backward(a.to(DEV), b.detach().to(DEV), mask.to(DEV), gl.to(DEV))
+    assert relerr(gb, b.grad) < 1e-6
+
+
+def _patched_noise(tape, noise_t2m):
+    import torch as th
+    orig = th.randn, th.randn_like, th.rand_like
+
+    class _Ctx:
+        def __enter__(self):
+            th.randn = lambda *s, **k: tape.draw(
+                s[0] if len(s) == 1 and isinstance(s[0], (tuple, list, torch.Size)) else s).to(k.get("device", "cpu"))
+            th.randn_like = lambda a, **k: tape.draw(a.shape).to(a.device)
+            th.rand_like = lambda a, **k: noise_t2m.clone().to(a.device)
+
+        def __exit__(self, *exc):
+            th.randn, th.randn_like, th.rand_like = orig
+    return _Ctx()
+
+
+def _finetune_terms(mu, model, FI, cfg):
+    from mst_b200.data_loaders.stylexia_posrot_utils import get_inpainting_mask
+    inp = FI.make_inputs()
+    F, T = 181, inp["content"].shape[-1]
+    diffusion = mu.create_gaussian_diffusion(Args(), mu.InpaintingGaussianDiffusion, timestep_respacing=cfg["respacing"])
+    mask_style = torch.from_numpy(get_inpainting_mask("root_horizontal", (1, F, 1, T))).float().to(DEV)
+    mask_t2m = torch.from_numpy(get_inpainting_mask("root_horizontal", tuple(inp["x_start"].shape))).float().to(DEV)
+    style_kwargs = {"y": {"text": inp["texts_style"], "text_feat": text_features(inp["texts_style"]).to(DEV),
+                          "mask": torch.ones(1, 1, 1, T, dtype=torch.bool, device=DEV), "lengths": torch.tensor([T]),
+                          "inpainted_motion": inp["style"].to(DEV), "inpainting_mask": mask_style}}
+    t2m_kwargs = {"y": {"text": inp["texts_t2m"], "text_feat": text_features(inp["texts_t2m"]).to(DEV),
+                        "mask": inp["frame_mask_t2m"][:, None, None, :].to(DEV), "lengths": torch.tensor(inp["lengths"]),
+                        "inpainting_mask": mask_t2m}}
+    with _patched_noise(NoiseTape(17), inp["noise_t2m"]):
+        terms = diffusion.few_shot_style_finetune_losses(
+            model, inp["x_start"].to(DEV), inp["t"].to(DEV), inp["content"].to(DEV), inp["style"].to(DEV),
+            skip_steps=cfg["skip_steps"], model_kwargs=style_kwargs, model_t2m_kwargs=t2m_kwargs,
+            semantic_guidance=cfg["semantic_guidance"], use_ddim=cfg["use_ddim"], Ls=10)
+    return terms
+
+
+@pytest.mark.parametrize("case", ["ddim_sg0", "ddim_sg1", "ddpm_sg0"])
+def test_finetune_losses_and_gradients_match_reference(mu, FI, gold, tmp_path_factory, case):
+    model, *_ = _style_model(mu, FI, tmp_path_factory)
+    cfg = dict(FI.cases())[case]
+    terms = _finetune_terms(mu, model, FI, cfg)
+    assert abs(terms["loss"].item() - float(gold[f"{case}/loss"])) < 1e-4 * abs(float(gold[f"{case}/loss"]))
+    assert relerr(terms["rot_mse"].detach(), gold[f"{case}/rot_mse"]) < 1e-4
+    if cfg["semantic_guidance"]:
+        assert abs(terms["text_cosine"].item() - float(gold[f"{case}/text_cosine"])) < 1e-4
+    model.zero_grad(set_to_none=True)
+    terms["loss"].backward()
+    names = [str(n) for n in gold["param_names"]]
+    params = dict(model.named_parameters())
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert trainable == names  # the same 96 tensors as the reference, in the same order
+    dig = gold[f"{case}/grad_digest"]
+    worst = 0.0
+    for i, n in enumerate(names):
+        got = FI_digest(params[n].grad)
+        scale = max(abs(dig[i][0]) / np.sqrt(params[n].numel()), 1e-12)  # rms of the reference gradient
+        assert abs(got[0] - dig[i][0]) < TOL * abs(dig[i][0]), (n, got[0], dig[i][0])
+        assert np.abs(got[2:] - dig[i][2:]).max() < 5 * TOL * max(scale, np.abs(dig[i][2:]).max()), n
+        worst = max(worst, abs(got[0] - dig[i][0]) / abs(dig[i][0]))
+    print(f"{case}: worst gradient-norm rel err over 96 tensors {worst:.2e}")
+    for key in gold:
+        if key.startswith(f"{case}/grad/"):
+            assert relerr(params[key.split("/grad/")[1]].grad, gold[key]) < TOL, key
+    assert relerr(params["seqTransEncoder.layers.0.linear1.weight"].grad[:8, :64],
+                  gold[f"{case}/grad_slice/layers.0.linear1.weight"]) < TOL
+    assert relerr(params["seqTransEncoder.layers.7.self_attn.in_proj_weight"].grad[510:518, :64],
+                  gold[f"{case}/grad_slice/layers.7.self_attn.in_proj_weight"]) < TOL
+
+
+def test_trainer_norms_adamw_step_match_reference(mu, FI, gold, tmp_path_factory):
+    """zero_grad -> loss -> backward -> norms -> fused AdamW (training_loop.py:196-200) == torch.optim.AdamW of the
+    reference run, tensor by tensor."""
+    from mst_b200.diffusion.fp16_util import MixedPrecisionTrainer
+    from mst_b200.train.training_loop import FusedAdamW
+    case = "ddim_sg1"
+    model, *_ = _style_model(mu, FI, tmp_path_factory)
+    trainer = MixedPrecisionTrainer(model=model)
+    opt = FusedAdamW(trainer.flat, lr=1e-4, weight_decay=0.0, model=model)
+    trainer.zero_grad()
+    terms = _finetune_terms(mu, model, FI, dict(FI.cases())[case])
+    trainer.backward(terms["loss"])
+    grad_norm, param_norm = trainer._compute_norms()
+    dig = gold[f"{case}/grad_digest"]
+    assert abs(grad_norm - np.sqrt((dig[:, 0] ** 2).sum())) < TOL * grad_norm
+    want_pn = np.sqrt(sum(float(p.detach().double().pow(2).sum()) for p in model.parameters()))
+    assert abs(param_norm - want_pn) < 1e-5 * want_pn
+    trainer.optimize(opt)
+    after = gold[f"{case}/param_after_digest"]
+    params = dict(model.named_parameters())
+    for i, n in enumerate(str(s) for s in gold["param_names"]):
+        got = FI_digest(params[n])
+        # Adam's first step moves every element by lr * g / (|g| + eps) ~ +-1e-4: an element whose gradient is ~1e-8
+        # may legitimately land anywhere in +-lr; everything else must agree to fp32 rounding
+        assert abs(got[0] - after[i][0]) < 1e-5 * abs(after[i][0]), n
+        diff = np.abs(got[2:] - after[i][2:])
+        assert diff.max() < 2.1e-4 and (diff < 2e-6).sum() >= 12, (n, diff)
+    # the optimiser wrote through raw pointers: the engines must notice (weights re-packed on next use)
+    with torch.no_grad():
+        y = {"text_feat": text_features(["a"]).to(DEV), "text": ["a"]}
+        x = torch.zeros(1, 181, 1, 20, device=DEV)
+        model.mst_precision = "fp32"
+        out_new = model(x, torch.tensor([5], device=DEV), y)
+    w_enc = {k: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith("seqTransEncoder.")}
+    want = OD.mdm_forward(mdm_state_dict(181, seed=0), x.cpu(), torch.tensor([5]), text_features(["a"]), enc_w=w_enc)
+    assert relerr(out_new, want) < 1e-4
+
+
+def test_training_loop_runs_and_reduces_the_loss(mu, FI, tmp_path_factory):
+    from mst_b200.data_loaders.stylexia_posrot_utils import get_inpainting_mask
+    from mst_b200.train.training_loop import TrainInpaintingLoop
+    model, *_ = _style_model(mu, FI, tmp_path_factory)
+    inp = FI.make_inputs()
+    F, T = 181, inp["content"].shape[-1]
+
+    class A(Args):
+        batch_size, lr, weight_decay, lr_anneal_steps, style_finetune, semantic_guidance = 3, 1e-4, 0.0, 0, 1, 1
+        skip_steps, use_ddim, Ls, num_steps = 700, 1, 10, 4
+
+    diffusion = mu.create_gaussian_diffusion(A(), mu.InpaintingGaussianDiffusion, timestep_respacing="ddim20")
+    mask_style = torch.from_numpy(get_inpainting_mask("root_horizontal", (1, F, 1, T))).float().to(DEV)
+    mask_t2m = torch.from_numpy(get_inpainting_mask("root_horizontal", tuple(inp["x_start"].shape))).float().to(DEV)
+    style_cond = {"y": {"text": inp["texts_style"], "text_feat": text_features(inp["texts_style"]).to(DEV),
+                        "mask": torch.ones(1, 1, 1, T, dtype=torch.bool, device=DEV), "lengths": torch.tensor([T]),
+                        "inpainted_motion": inp["style"].to(DEV), "inpainting_mask": mask_style}}
+    cond = {"y": {"text": inp["texts_t2m"], "text_feat": text_features(inp["texts_t2m"]).to(DEV),
+                  "mask": inp["frame_mask_t2m"][:, None, None, :].to(DEV), "lengths": torch.tensor(inp["lengths"]),
+                  "inpainting_mask": mask_t2m}}
+    loop = TrainInpaintingLoop(A(), None, model, [(inp["x_start"], cond)], diffusion=diffusion,
+                               style_data=((inp["content"].to(DEV), style_cond),))
+    np.random.seed(0)
+    torch.manual_seed(0)
+    losses = []
+    for _ in range(4):
+        loop.run_step(inp["x_start"].to(DEV), cond, inp["content"].to(DEV), style_cond)
+        losses.append(float(loop.last_losses["loss"]))
+    assert all(np.isfinite(losses))
+    assert losses[-1] < losses[0], losses
+    assert loop.step == 4 and loop.opt.step_count == 4
