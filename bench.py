@@ -206,6 +206,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     if a.gpus != world and rank == 0:
         print(f"bench.py: --gpus {a.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run for N>1", file=sys.stderr)

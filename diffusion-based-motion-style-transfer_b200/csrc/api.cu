@@ -31,7 +31,10 @@ struct Profile {
   std::vector<cudaEvent_t> ev;  // ev[0] = begin, ev[i+1] = after launch i
   std::vector<const char*> names;
 };
-static thread_local Profile g_prof;
+// One profile per process (not per thread): torch runs backward passes on its autograd thread, and their launches
+// belong in the table too.  Profiling is a single-threaded diagnostic; the mutex only keeps the vectors consistent.
+static Profile g_prof;
+static std::mutex g_prof_mu;
 
 // During stream capture an ordinary record is swallowed into the graph's internal dependencies; an EXTERNAL
 // record becomes an event-record node that updates the real event on every replay.
@@ -45,6 +48,7 @@ static cudaError_t record_event(cudaEvent_t e, cudaStream_t s) {
 void note_launch(const char* name, cudaStream_t s) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (g_prof.open && s == g_prof.stream) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     cudaEvent_t e;
     if (cudaEventCreate(&e) == cudaSuccess) {
       record_event(e, s);
@@ -134,6 +138,12 @@ static size_t packed_bytes(const mst_model_desc& d, int f_pad) {
   c.take<__nv_bfloat16>((size_t)f_pad * d.d_model);   // out_w
   c.take<float>(f_pad);                               // out_b padded
   for (int l = 0; l < d.n_layers; ++l) {
+    c.take<__nv_bfloat16>((size_t)3 * d.d_model * d.d_model);
+    c.take<__nv_bfloat16>((size_t)d.d_model * d.d_model);
+    c.take<__nv_bfloat16>((size_t)d.d_ff * d.d_model);
+    c.take<__nv_bfloat16>((size_t)d.d_model * d.d_ff);
+  }
+  for (int l = 0; l < d.n_layers; ++l) {  // transposed copies for the training backward (dX = dY W)
     c.take<__nv_bfloat16>((size_t)3 * d.d_model * d.d_model);
     c.take<__nv_bfloat16>((size_t)d.d_model * d.d_model);
     c.take<__nv_bfloat16>((size_t)d.d_ff * d.d_model);
@@ -307,6 +317,18 @@ extern "C" int mst_engine_load_weights(mst_engine_t h, const mst_weights* w, voi
       if ((rc = pack_bf16(L.w1, w1, d.d_ff, d.d_model, d.d_ff, d.d_model, s))) return rc;
       if ((rc = pack_bf16(L.w2, w2, d.d_model, d.d_ff, d.d_model, d.d_ff, s))) return rc;
       e->lb[l] = LayerBF16{qkv, o, w1, w2};
+    }
+    for (int l = 0; l < d.n_layers; ++l) {
+      const mst_layer_weights& L = w->layers[l];
+      auto* qkv = c.take<__nv_bfloat16>((size_t)3 * d.d_model * d.d_model);  // [d, 3d]
+      auto* o = c.take<__nv_bfloat16>((size_t)d.d_model * d.d_model);         // [d, d]
+      auto* w1 = c.take<__nv_bfloat16>((size_t)d.d_ff * d.d_model);           // [d, ff]
+      auto* w2 = c.take<__nv_bfloat16>((size_t)d.d_model * d.d_ff);           // [ff, d]
+      if ((rc = cvt_bf16(L.qkv_w, 3 * d.d_model, d.d_model, d.d_model, nullptr, qkv, 3 * d.d_model, s))) return rc;
+      if ((rc = cvt_bf16(L.o_w, d.d_model, d.d_model, d.d_model, nullptr, o, d.d_model, s))) return rc;
+      if ((rc = cvt_bf16(L.w1, d.d_ff, d.d_model, d.d_model, nullptr, w1, d.d_ff, s))) return rc;
+      if ((rc = cvt_bf16(L.w2, d.d_model, d.d_ff, d.d_ff, nullptr, w2, d.d_model, s))) return rc;
+      e->lbt[l] = LayerBF16T{qkv, o, w1, w2};
     }
   }
   e->weights_loaded = true;

@@ -81,6 +81,9 @@ struct LayerF32 {
 struct LayerBF16 {
   const __nv_bfloat16 *qkv_w, *o_w, *w1, *w2;  // [N, K] row-major bf16
 };
+struct LayerBF16T {
+  const __nv_bfloat16 *qkv_w, *o_w, *w1, *w2;  // the same weights transposed, [K, N] row-major (dX = dY W)
+};
 
 struct Engine {
   mst_model_desc desc;
@@ -93,6 +96,7 @@ struct Engine {
   const __nv_bfloat16* out_w_bf = nullptr;  // [Fpad, d]
   const float* out_b_pad = nullptr;         // [Fpad]
   LayerBF16 lb[MST_MAX_LAYERS];
+  LayerBF16T lbt[MST_MAX_LAYERS];
   int f_pad = 0;  // F rounded up to 64
 };
 

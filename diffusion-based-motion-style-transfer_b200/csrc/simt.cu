@@ -112,7 +112,30 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32Params p) {
   }
 }
 
+// Few output rows (time / text embedding of a handful of samples, the B=1 style example of the finetune step): the
+// 128 x 128 tiling would run on a handful of CTAs with a long serial k-loop; one warp per output element instead.
+__global__ void __launch_bounds__(256) gemm_f32_skinny_kernel(GemmF32Params p) {
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)p.M * p.N;
+  for (long long o = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; o < total;
+       o += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int m = (int)(o / p.N), n = (int)(o - (long long)m * p.N);
+    const float* w = p.w + (int64_t)n * p.ldw;
+    float acc = 0.0f;
+    for (int k = lane; k < p.K; k += 32) acc = fmaf(load_a(p, m, k), w[k], acc);
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) store_c(p, m, n, acc);
+  }
+}
+
 int gemm_f32(const GemmF32Params& p, cudaStream_t s) {
+  if ((long long)p.M * p.N <= 65536 && p.M <= 128 && (long long)p.M * p.N * p.K <= (24ll << 20)) {
+    const long long warps = (long long)p.M * p.N;
+    const int blocks = (int)((warps + 7) / 8 < 4096 ? (warps + 7) / 8 : 4096);
+    gemm_f32_skinny_kernel<<<blocks, 256, 0, s>>>(p);
+    MST_LAUNCHED("gemm_f32_skinny", s);
+    return MST_OK;
+  }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
   gemm_f32_kernel<<<grid, 256, 0, s>>>(p);
   MST_LAUNCHED("gemm_f32", s);

@@ -12,6 +12,7 @@ enum TcEpi {
   TC_EPI_INPROJ,          // token rows (b, t+1) of every pass = acc + bias + pe[t+1]
   TC_EPI_OUTPROJ_F32,     // out fp32 [seq][n][s-1] = acc + bias (token 0 dropped, n < n_valid)
   TC_EPI_BIAS_F32,        // out fp32 [M, ldo]  = acc + bias                     (test hook)
+  TC_EPI_TRAIN_F32,       // out fp32 [M, ldo]  (+)= acc (+ bias) (+ add)        (training GEMMs: forward, dX, dW)
 };
 
 struct TcGemmParams {
@@ -32,6 +33,8 @@ struct TcGemmParams {
   int td_mode = 0;           // experiment knob (MST_TEARDOWN)
   long long* dbg = nullptr;  // test hook: clock64 timeline of cluster 0 (see mst_test_set_gemm_debug)
   float* out2 = nullptr;  // OUTPROJ: rows of sequences >= B go here (uncond pass)
+  const float* add = nullptr;  // TRAIN_F32: fp32 tensor with out's layout added to the result (residual paths)
+  int accumulate = 0;          // TRAIN_F32: out += result (gradient accumulation)
 };
 
 int tc_gemm(const TcGemmParams& p, cudaStream_t s);
@@ -42,6 +45,11 @@ int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T,
 
 // fp32 [rows, cols] -> bf16 [rows_pad, cols_pad] zero padded (weight packing)
 int pack_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, int rows_pad, int cols_pad, cudaStream_t s);
+
+// fp32 [rows, cols] (leading dimension ld) -> bf16 copy dst [rows, cols] and / or transposed copy dst_t [cols, rows_pad]
+// (columns [rows, rows_pad) zero): operands of the training GEMMs (dX needs W^T, dW needs dY^T and X^T)
+int cvt_bf16(const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, __nv_bfloat16* dst_t, int rows_pad,
+             cudaStream_t s);
 
 struct TcAttnParams {
   const __nv_bfloat16* qkv = nullptr;  // [n_seqs*S, 3d]  (Q | K | V column blocks)

@@ -143,6 +143,28 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, int n, const uint32_t (&v)[32]) {
   if (row >= p.M) return;
   float x[32];
+  if constexpr (EPI == TC_EPI_TRAIN_F32) {
+    float* dst = static_cast<float*>(p.out) + (size_t)row * p.ldo + n;
+    const float* addp = p.add ? p.add + (size_t)row * p.ldo + n : nullptr;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      if (p.bias) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
+      }
+      if (addp) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(addp + j));
+        r.x += a4.x; r.y += a4.y; r.z += a4.z; r.w += a4.w;
+      }
+      if (p.accumulate) {
+        const float4 o4 = *reinterpret_cast<const float4*>(dst + j);
+        r.x += o4.x; r.y += o4.y; r.z += o4.z; r.w += o4.w;
+      }
+      *reinterpret_cast<float4*>(dst + j) = r;
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
@@ -948,6 +970,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
   if (r != CUDA_SUCCESS) return fail(MST_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   {
     std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 8192) cache.clear();  // training tapes come and go: bound the cache
     cache[key] = m;
   }
   *out = m;
@@ -1016,7 +1039,7 @@ static int launch_gemm(const TcGemmParams& p, cudaStream_t s) {
   const int grid = tiles < sm_count() ? tiles : sm_count();
   MST_CUDA_OK(launch_pdl(tc_gemm_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tw, p));
   static const char* const kNames[] = {"tc_gemm_qkv", "tc_gemm_ffn1_gelu", "tc_gemm_res_ln", "tc_gemm_inproj",
-                                       "tc_gemm_outproj", "tc_gemm_f32"};
+                                       "tc_gemm_outproj", "tc_gemm_f32", "tc_gemm_train"};
   MST_LAUNCHED(kNames[EPI], s);
   return MST_OK;
 }
@@ -1100,7 +1123,7 @@ int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
     const char* e = getenv("MST_TEARDOWN");
     p.td_mode = e ? atoi(e) : 0;
   }
-  MST_CHECK_ARG(p.a && p.w && p.bias && p.out, "null pointer");
+  MST_CHECK_ARG(p.a && p.w && p.out && (p.bias || p.epi == TC_EPI_TRAIN_F32), "null pointer");
   MST_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0, "empty problem");
   MST_CHECK_ARG(p.K % BLOCK_K == 0, "K must be a multiple of 64");
   switch (p.epi) {
@@ -1123,6 +1146,10 @@ int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
       MST_CHECK_ARG(p.N % 64 == 0 && p.ldo % 4 == 0, "N must be a multiple of 64");
       if (p.N % 256 == 0) return launch_gemm<256, TC_EPI_BIAS_F32>(p, s);
       return launch_gemm<64, TC_EPI_BIAS_F32>(p, s);
+    case TC_EPI_TRAIN_F32:
+      MST_CHECK_ARG(p.N % 64 == 0 && p.ldo % 4 == 0, "N must be a multiple of 64");
+      if (p.N % 256 == 0) return launch_gemm<256, TC_EPI_TRAIN_F32>(p, s);
+      return launch_gemm<64, TC_EPI_TRAIN_F32>(p, s);
     default:
       return fail(MST_ERR_INVALID, "tc_gemm: unknown epilogue");
   }
@@ -1164,6 +1191,35 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict_
     int r = (int)(i / cols_pad), c = (int)(i - (size_t)r * cols_pad);
     dst[i] = __float2bfloat16_rn((r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.0f);
   }
+}
+
+// src fp32 [rows, cols] -> dst bf16 [rows, cols] and / or dst_t bf16 [cols, rows_pad] (zero padded), 32 x 32 smem transpose
+__global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__ src, int rows, int cols, int ld,
+                                                       __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_t,
+                                                       int rows_pad) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    const float v = (r < rows && c < cols) ? src[(size_t)r * ld + c] : 0.0f;
+    tile[i][tx] = v;
+    if (dst && r < rows && c < cols) dst[(size_t)r * cols + c] = __float2bfloat16_rn(v);
+  }
+  if (!dst_t) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows_pad) dst_t[(size_t)c * rows_pad + r] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+int cvt_bf16(const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, __nv_bfloat16* dst_t, int rows_pad,
+             cudaStream_t s) {
+  const int rgrid = dst_t ? ceil_div(rows_pad, 32) : ceil_div(rows, 32);
+  cvt_bf16_kernel<<<dim3(ceil_div(cols, 32), rgrid), 256, 0, s>>>(src, rows, cols, ld, dst, dst_t, rows_pad);
+  MST_LAUNCHED("cvt_bf16", s);
+  return MST_OK;
 }
 
 int pack_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, int rows_pad, int cols_pad, cudaStream_t s) {

@@ -15,6 +15,7 @@
 //   u = y W1^T + b1 ; h = gelu(u) ; z2 = y + h W2^T + b2 ; x' = LN2(z2)
 #include "common.cuh"
 #include "simt.cuh"
+#include "tc.cuh"
 
 #include <math.h>
 
@@ -145,9 +146,76 @@ __global__ void __launch_bounds__(256) gemm_ex_kernel(GemmEx p) {
   }
 }
 
+__device__ __forceinline__ float gemm_ex_a(const GemmEx& p, const float* a, int m, int k, int S) {
+  switch (p.a_mode) {
+    case AX_NORMAL: return a[(long long)m * p.lda + k];
+    case AX_TRANS: return a[(long long)k * p.lda + m];
+    case AX_MOTION_TOK: {
+      const int seq = m / S, s = m - seq * S;
+      return s < p.tok_off ? 0.0f : a[((long long)seq * p.K + k) * p.T + (s - p.tok_off)];
+    }
+    default: {
+      const int seq = m / p.T, t = m - seq * p.T;
+      return a[((long long)seq * S + t + p.tok_off) * p.lda + k];
+    }
+  }
+}
+
+// Small problems (the B=1 style example: 77-token sequences, per-head 77 x 77 products): one warp per output element,
+// lanes stride the reduction - hundreds of warps in flight instead of a dozen CTAs with a serial k-loop.
+__global__ void __launch_bounds__(256) gemm_ex_skinny_kernel(GemmEx p) {
+  const int lane = threadIdx.x & 31;
+  const int S = p.T + p.tok_off;
+  const long long per = (long long)p.M * p.N, total = per * p.batch * p.heads;
+  for (long long o = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; o < total;
+       o += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int z = (int)(o / per);
+    const long long r = o - (long long)z * per;
+    const int m = (int)(r / p.N), n = (int)(r - (long long)m * p.N);
+    const int zb = z / p.heads, zh = z - zb * p.heads;
+    const float* a = p.a + zb * p.a_bs + zh * p.a_hs;
+    const float* b = p.b + zb * p.b_bs + zh * p.b_hs;
+    float acc = 0.0f;
+    if (p.trans_b) {
+      const float* br = b + (long long)n * p.ldb;
+      for (int k = lane; k < p.K; k += 32) acc = fmaf(gemm_ex_a(p, a, m, k, S), br[k], acc);
+    } else {
+      for (int k = lane; k < p.K; k += 32) acc = fmaf(gemm_ex_a(p, a, m, k, S), b[(long long)k * p.ldb + n], acc);
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      long long oo;
+      if (p.c_mode == CX_MOTION) {
+        const int seq = m / p.T, t = m - seq * p.T;
+        oo = ((long long)seq * p.N + n) * p.T + t;
+      } else {
+        oo = (long long)m * p.ldc + n;
+      }
+      oo += zb * p.c_bs + zh * p.c_hs;
+      float v = p.alpha * acc;
+      if (p.bias) v += p.bias[n];
+      if (p.add) v += p.add[oo];
+      if (p.accumulate) p.c[oo] += v;
+      else p.c[oo] = v;
+    }
+  }
+}
+
 static int gemm_ex(GemmEx p, cudaStream_t s, const char* name) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return fail(MST_ERR_INVALID, "gemm_ex: empty problem");
   const long long z = (long long)p.batch * p.heads;
+  if ((long long)p.M * p.N * z <= 131072 && (long long)p.M * p.N * z * p.K <= (24ll << 20)) {
+    const long long warps = (long long)p.M * p.N * z;
+    const int blocks = (int)((warps + 7) / 8 < 8192 ? (warps + 7) / 8 : 8192);
+    gemm_ex_skinny_kernel<<<blocks, 256, 0, s>>>(p);
+    MST_LAUNCHED(name, s);
+    return MST_OK;
+  }
+  if (p.split_k == 1 && z == 1 && p.c_mode == CX_NORMAL && (p.accumulate || p.ldc == p.N) && p.K >= 512 &&
+      ceil_div(p.M, 64) * ceil_div(p.N, 64) < 64) {
+    // a handful of tiles with a long reduction (fp32 linears of the B=1 style example): spread the k-loop over CTAs
+    p.split_k = p.K / 128 < 8 ? p.K / 128 : 8;
+  }
   const long long tiles128 = (long long)ceil_div(p.M, 128) * ceil_div(p.N, 128) * z * p.split_k;
   if (p.split_k > 1 && !p.accumulate) {
     if (p.c_mode != CX_NORMAL || z != 1 || p.ldc != p.N)
@@ -346,6 +414,108 @@ __global__ void __launch_bounds__(128) menc_tokens_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Linear layers of the encoder stack: y = x W^T (+ bias) (+ add);  dx = dy W (+ add);  dW += dy^T x.
+// MST_PREC_FP32 engines run them on the fp32 SIMT GEMM above (parity mode); MST_PREC_BF16 engines convert the
+// operands to bf16 (K-major copies; dW needs both operands transposed, dX the transposed weight packed at load time)
+// and run them on the tcgen05 kernel with fp32 accumulation and an fp32 epilogue (csrc/tc_gemm.cu, TC_EPI_TRAIN_F32).
+// ---------------------------------------------------------------------------------------------------------
+struct Stage {          // bf16 staging for the tensor-core path (null in fp32 mode)
+  __nv_bfloat16* a;     // [M, max(3d, ff)]
+  __nv_bfloat16* at;    // [max(3d, ff), Mpad]
+  __nv_bfloat16* bt;    // [max(d, ff), Mpad]
+  int m_pad;
+};
+
+struct Lin {
+  const float* w;              // [n_out, n_in] fp32
+  const __nv_bfloat16* w_bf;   // [n_out, n_in]
+  const __nv_bfloat16* wt_bf;  // [n_in, n_out]
+  int n_out, n_in;
+};
+
+static size_t stage_elems(const mst_model_desc& d, int M, int* m_pad) {
+  const int mp = (M + 63) / 64 * 64;
+  if (m_pad) *m_pad = mp;
+  const size_t wide = (size_t)(3 * d.d_model > d.d_ff ? 3 * d.d_model : d.d_ff);
+  const size_t mid = (size_t)(d.d_model > d.d_ff ? d.d_model : d.d_ff);
+  return (size_t)M * wide + 64 + wide * mp + mid * mp;
+}
+
+static void carve_stage(const mst_model_desc& d, int M, void* base, Stage* st) {
+  int mp;
+  stage_elems(d, M, &mp);
+  const size_t wide = (size_t)(3 * d.d_model > d.d_ff ? 3 * d.d_model : d.d_ff);
+  __nv_bfloat16* p = static_cast<__nv_bfloat16*>(base);
+  st->a = p;
+  st->at = p + (((size_t)M * wide + 63) / 64) * 64;
+  st->bt = st->at + wide * mp;
+  st->m_pad = mp;
+}
+
+static int linear_fwd(bool tc, const Stage& st, const float* x, const Lin& L, const float* bias, const float* add, float* out,
+                      int M, cudaStream_t s, const char* name) {
+  if (!tc) {
+    GemmEx g;
+    g.a = x; g.lda = L.n_in; g.b = L.w; g.ldb = L.n_in; g.trans_b = 1; g.bias = bias; g.add = add; g.c = out; g.ldc = L.n_out;
+    g.M = M; g.N = L.n_out; g.K = L.n_in;
+    return gemm_ex(g, s, name);
+  }
+  int rc;
+  if ((rc = cvt_bf16(x, M, L.n_in, L.n_in, st.a, nullptr, 0, s))) return rc;
+  TcGemmParams p;
+  p.a = st.a; p.w = L.w_bf; p.bias = bias; p.add = add; p.out = out; p.ldo = L.n_out; p.M = M; p.N = L.n_out; p.K = L.n_in;
+  p.epi = TC_EPI_TRAIN_F32;
+  return tc_gemm(p, s);
+}
+
+// dx [M, n_in] = dy W (+ add); dW [n_out, n_in] += dy^T x; db [n_out] += column sums of dy (null pointers skip)
+static int linear_bwd(bool tc, const Stage& st, const float* dy, const float* x, const Lin& L, const float* add, float* dx,
+                      float* dw, float* db, int M, cudaStream_t s, const char* name_dx, const char* name_dw) {
+  int rc;
+  if (db && (rc = colsum(dy, db, M, L.n_out, L.n_out, s))) return rc;
+  if (!tc) {
+    if (dw) {
+      GemmEx g;  // dW += dy^T x
+      g.a = dy; g.lda = L.n_out; g.a_mode = AX_TRANS; g.b = x; g.ldb = L.n_in; g.c = dw; g.ldc = L.n_in;
+      g.M = L.n_out; g.N = L.n_in; g.K = M; g.accumulate = 1; g.split_k = pick_split(L.n_out, L.n_in, M);
+      if ((rc = gemm_ex(g, s, name_dw))) return rc;
+    }
+    if (dx) {
+      GemmEx g;  // dx = dy W (+ add)
+      g.a = dy; g.lda = L.n_out; g.b = L.w; g.ldb = L.n_in; g.add = add; g.c = dx; g.ldc = L.n_in;
+      g.M = M; g.N = L.n_in; g.K = L.n_out;
+      if ((rc = gemm_ex(g, s, name_dx))) return rc;
+    }
+    return MST_OK;
+  }
+  if ((rc = cvt_bf16(dy, M, L.n_out, L.n_out, dx ? st.a : nullptr, dw ? st.at : nullptr, st.m_pad, s))) return rc;
+  if (dw) {
+    if ((rc = cvt_bf16(x, M, L.n_in, L.n_in, nullptr, st.bt, st.m_pad, s))) return rc;
+    TcGemmParams p;
+    p.a = st.at; p.w = st.bt; p.out = dw; p.ldo = L.n_in; p.M = L.n_out; p.N = L.n_in; p.K = st.m_pad;
+    p.accumulate = 1; p.epi = TC_EPI_TRAIN_F32;
+    if ((rc = tc_gemm(p, s))) return rc;
+  }
+  if (dx) {
+    TcGemmParams p;
+    p.a = st.a; p.w = L.wt_bf; p.add = add; p.out = dx; p.ldo = L.n_in; p.M = M; p.N = L.n_in; p.K = L.n_out;
+    p.epi = TC_EPI_TRAIN_F32;
+    if ((rc = tc_gemm(p, s))) return rc;
+  }
+  return MST_OK;
+}
+
+static void layer_lins(Engine* e, int l, Lin* qkv, Lin* o, Lin* f1, Lin* f2) {
+  const mst_model_desc& d = e->desc;
+  const LayerF32& L = e->lf[l];
+  const bool tc = d.precision == MST_PREC_BF16;
+  *qkv = Lin{L.qkv_w, tc ? e->lb[l].qkv_w : nullptr, tc ? e->lbt[l].qkv_w : nullptr, 3 * d.d_model, d.d_model};
+  *o = Lin{L.o_w, tc ? e->lb[l].o_w : nullptr, tc ? e->lbt[l].o_w : nullptr, d.d_model, d.d_model};
+  *f1 = Lin{L.w1, tc ? e->lb[l].w1 : nullptr, tc ? e->lbt[l].w1 : nullptr, d.d_ff, d.d_model};
+  *f2 = Lin{L.w2, tc ? e->lb[l].w2 : nullptr, tc ? e->lbt[l].w2 : nullptr, d.d_model, d.d_ff};
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // tape: everything the backward needs, per layer
 // ---------------------------------------------------------------------------------------------------------
 struct LayerTape {
@@ -354,6 +524,7 @@ struct LayerTape {
 struct Tape {
   LayerTape l[MST_MAX_LAYERS];
   float* x_out;  // output of the last layer [M, d]
+  Stage stage;   // bf16 staging of the forward (tensor-core mode)
 };
 
 static size_t carve_tape(const mst_model_desc& d, int n_seqs, int S, void* base, Tape* t) {
@@ -382,6 +553,12 @@ static size_t carve_tape(const mst_model_desc& d, int n_seqs, int S, void* base,
     x = take(M * dm);
   }
   tp.x_out = x;
+  tp.stage = Stage{nullptr, nullptr, nullptr, 0};
+  if (d.precision == MST_PREC_BF16) {
+    off = align_up(off, 1024);
+    if (base) carve_stage(d, (int)M, static_cast<char*>(base) + off, &tp.stage);
+    off += stage_elems(d, (int)M, nullptr) * sizeof(__nv_bfloat16);
+  }
   if (t) *t = tp;
   return align_up(off, 256);
 }
@@ -391,14 +568,14 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
   const int M = NS * S, dm = d.d_model, H = d.n_heads, dh = dm / H, ff = d.d_ff;
   const float scale = 1.0f / sqrtf((float)dh);
   int rc;
+  const bool tc = d.precision == MST_PREC_BF16;
   for (int l = 0; l < d.n_layers; ++l) {
     const LayerF32& L = e->lf[l];
     const LayerTape& t = tp.l[l];
     float* x_next = l + 1 < d.n_layers ? tp.l[l + 1].x : tp.x_out;
-    GemmEx g;
-    g.a = t.x; g.lda = dm; g.b = L.qkv_w; g.ldb = dm; g.trans_b = 1; g.bias = L.qkv_b; g.c = t.qkv; g.ldc = 3 * dm;
-    g.M = M; g.N = 3 * dm; g.K = dm;
-    if ((rc = gemm_ex(g, s, "train_qkv"))) return rc;
+    Lin lqkv, lo, lf1, lf2;
+    layer_lins(e, l, &lqkv, &lo, &lf1, &lf2);
+    if ((rc = linear_fwd(tc, tp.stage, t.x, lqkv, L.qkv_b, nullptr, t.qkv, M, s, "train_qkv"))) return rc;
     GemmEx sc;  // scores = scale * Q K^T per (seq, head)
     sc.a = t.qkv; sc.lda = 3 * dm; sc.b = t.qkv + dm; sc.ldb = 3 * dm; sc.trans_b = 1; sc.c = t.p; sc.ldc = S;
     sc.M = S; sc.N = S; sc.K = dh; sc.alpha = scale; sc.batch = NS; sc.heads = H;
@@ -413,21 +590,12 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
     pv.M = S; pv.N = dh; pv.K = S; pv.batch = NS; pv.heads = H;
     pv.a_bs = sc.c_bs; pv.a_hs = sc.c_hs; pv.b_bs = sc.a_bs; pv.b_hs = dh; pv.c_bs = (long long)S * dm; pv.c_hs = dh;
     if ((rc = gemm_ex(pv, s, "train_pv"))) return rc;
-    GemmEx o;
-    o.a = t.ao; o.lda = dm; o.b = L.o_w; o.ldb = dm; o.trans_b = 1; o.bias = L.o_b; o.add = t.x; o.c = t.z1; o.ldc = dm;
-    o.M = M; o.N = dm; o.K = dm;
-    if ((rc = gemm_ex(o, s, "train_outproj"))) return rc;
+    if ((rc = linear_fwd(tc, tp.stage, t.ao, lo, L.o_b, t.x, t.z1, M, s, "train_outproj"))) return rc;
     if ((rc = layernorm_f32(t.z1, L.ln1_g, L.ln1_b, t.y, M, dm, s))) return rc;
-    GemmEx f1;
-    f1.a = t.y; f1.lda = dm; f1.b = L.w1; f1.ldb = dm; f1.trans_b = 1; f1.bias = L.b1; f1.c = t.u; f1.ldc = ff;
-    f1.M = M; f1.N = ff; f1.K = dm;
-    if ((rc = gemm_ex(f1, s, "train_ffn1"))) return rc;
+    if ((rc = linear_fwd(tc, tp.stage, t.y, lf1, L.b1, nullptr, t.u, M, s, "train_ffn1"))) return rc;
     gelu_fwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, t.h, (long long)M * ff);
     MST_LAUNCHED("train_gelu", s);
-    GemmEx f2;
-    f2.a = t.h; f2.lda = ff; f2.b = L.w2; f2.ldb = ff; f2.trans_b = 1; f2.bias = L.b2; f2.add = t.y; f2.c = t.z2; f2.ldc = dm;
-    f2.M = M; f2.N = dm; f2.K = ff;
-    if ((rc = gemm_ex(f2, s, "train_ffn2"))) return rc;
+    if ((rc = linear_fwd(tc, tp.stage, t.h, lf2, L.b2, t.y, t.z2, M, s, "train_ffn2"))) return rc;
     if ((rc = layernorm_f32(t.z2, L.ln2_g, L.ln2_b, x_next, M, dm, s))) return rc;
   }
   return MST_OK;
@@ -437,6 +605,7 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
 // on return `g_x` [M, d] holds the gradient w.r.t. the stack's input.  Parameter gradients are ACCUMULATED.
 struct BwdScratch {
   float *ga, *gb, *dqkv, *dp, *dh;  // [M,d] x2, [M,3d], [NS*H*S*S], [M,ff]
+  Stage stage;
 };
 
 static size_t carve_bwd(const mst_model_desc& d, int n_seqs, int S, void* base, BwdScratch* o) {
@@ -454,17 +623,14 @@ static size_t carve_bwd(const mst_model_desc& d, int n_seqs, int S, void* base, 
   b.dqkv = take(M * 3 * dm);
   b.dp = take((size_t)n_seqs * d.n_heads * S * S);
   b.dh = take(M * d.d_ff);
+  b.stage = Stage{nullptr, nullptr, nullptr, 0};
+  if (d.precision == MST_PREC_BF16) {
+    off = align_up(off, 1024);
+    if (base) carve_stage(d, (int)M, static_cast<char*>(base) + off, &b.stage);
+    off += stage_elems(d, (int)M, nullptr) * sizeof(__nv_bfloat16);
+  }
   if (o) *o = b;
   return align_up(off, 256);
-}
-
-static int weight_grad(const float* dy, int ldy, const float* x, int ldx, float* dw, int n_out, int n_in, int M,
-                       cudaStream_t s, const char* name) {
-  if (!dw) return MST_OK;
-  GemmEx g;  // dW[n_out, n_in] += dy^T x
-  g.a = dy; g.lda = ldy; g.a_mode = AX_TRANS; g.b = x; g.ldb = ldx; g.c = dw; g.ldc = n_in;
-  g.M = n_out; g.N = n_in; g.K = M; g.accumulate = 1; g.split_k = pick_split(n_out, n_in, M);
-  return gemm_ex(g, s, name);
 }
 
 static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* grads, int NS, int S, float* g_in_out,
@@ -476,37 +642,30 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
   float* gx = g_in_out;  // gradient w.r.t. the current layer's output
   float* spare = w.ga;
   float* spare2 = w.gb;
+  const bool tc = d.precision == MST_PREC_BF16;
   for (int l = d.n_layers - 1; l >= 0; --l) {
     const LayerF32& L = e->lf[l];
     const LayerTape& t = tp.l[l];
     const mst_layer_grads& G = grads[l];
+    Lin lqkv, lo, lf1, lf2;
+    layer_lins(e, l, &lqkv, &lo, &lf1, &lf2);
     const int ln_blocks = ceil_div(M, 8) < 4 * sm_count() ? ceil_div(M, 8) : 4 * sm_count();
     // LN2
     float* dz2 = spare;
     layernorm_bwd_kernel<<<ln_blocks, 256, 0, s>>>(gx, t.z2, L.ln2_g, dz2, G.ln2_g, G.ln2_b, M, dm);
     MST_LAUNCHED("bwd_ln2", s);
-    if (G.b2 && (rc = colsum(dz2, G.b2, M, dm, dm, s))) return rc;
-    if ((rc = weight_grad(dz2, dm, t.h, ff, G.w2, dm, ff, M, s, "bwd_dw2"))) return rc;
-    GemmEx g3;  // dh = dz2 W2
-    g3.a = dz2; g3.lda = dm; g3.b = L.w2; g3.ldb = ff; g3.c = w.dh; g3.ldc = ff; g3.M = M; g3.N = ff; g3.K = dm;
-    if ((rc = gemm_ex(g3, s, "bwd_dh"))) return rc;
+    // FFN2: dh = dz2 W2, dW2 += dz2^T h, db2 += sum dz2
+    if ((rc = linear_bwd(tc, w.stage, dz2, t.h, lf2, nullptr, w.dh, G.w2, G.b2, M, s, "bwd_dh", "bwd_dw2"))) return rc;
     gelu_bwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, w.dh, (long long)M * ff);
     MST_LAUNCHED("bwd_gelu", s);
-    if (G.b1 && (rc = colsum(w.dh, G.b1, M, ff, ff, s))) return rc;
-    if ((rc = weight_grad(w.dh, ff, t.y, dm, G.w1, ff, dm, M, s, "bwd_dw1"))) return rc;
-    GemmEx g6;  // dy = dz2 + du W1   (into gx: the incoming gradient is no longer needed)
-    g6.a = w.dh; g6.lda = ff; g6.b = L.w1; g6.ldb = dm; g6.add = dz2; g6.c = gx; g6.ldc = dm; g6.M = M; g6.N = dm; g6.K = ff;
-    if ((rc = gemm_ex(g6, s, "bwd_dy"))) return rc;
+    // FFN1: dy = dz2 + du W1 (into gx: the incoming gradient is no longer needed), dW1 += du^T y, db1 += sum du
+    if ((rc = linear_bwd(tc, w.stage, w.dh, t.y, lf1, dz2, gx, G.w1, G.b1, M, s, "bwd_dy", "bwd_dw1"))) return rc;
     // LN1
     float* dz1 = spare;  // dz2 is dead
     layernorm_bwd_kernel<<<ln_blocks, 256, 0, s>>>(gx, t.z1, L.ln1_g, dz1, G.ln1_g, G.ln1_b, M, dm);
     MST_LAUNCHED("bwd_ln1", s);
-    if (G.o_b && (rc = colsum(dz1, G.o_b, M, dm, dm, s))) return rc;
-    if ((rc = weight_grad(dz1, dm, t.ao, dm, G.o_w, dm, dm, M, s, "bwd_dwo"))) return rc;
-    float* dao = spare2;
-    GemmEx g9;  // dao = dz1 Wo
-    g9.a = dz1; g9.lda = dm; g9.b = L.o_w; g9.ldb = dm; g9.c = dao; g9.ldc = dm; g9.M = M; g9.N = dm; g9.K = dm;
-    if ((rc = gemm_ex(g9, s, "bwd_dao"))) return rc;
+    float* dao = spare2;  // out-proj: dao = dz1 Wo, dWo += dz1^T ao, dbo += sum dz1
+    if ((rc = linear_bwd(tc, w.stage, dz1, t.ao, lo, nullptr, dao, G.o_w, G.o_b, M, s, "bwd_dao", "bwd_dwo"))) return rc;
     // attention
     const long long qkv_bs = (long long)S * 3 * dm, pp_bs = (long long)H * S * S, pp_hs = (long long)S * S;
     GemmEx dp;  // dP = dao V^T
@@ -530,12 +689,8 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     GemmEx dk = dq;  // dK = scale dS^T Q
     dk.a_mode = AX_TRANS; dk.b = t.qkv; dk.c = w.dqkv + dm;
     if ((rc = gemm_ex(dk, s, "bwd_dk"))) return rc;
-    if (G.qkv_b && (rc = colsum(w.dqkv, G.qkv_b, M, 3 * dm, 3 * dm, s))) return rc;
-    if ((rc = weight_grad(w.dqkv, 3 * dm, t.x, dm, G.qkv_w, 3 * dm, dm, M, s, "bwd_dwqkv"))) return rc;
-    GemmEx g12;  // gradient w.r.t. the layer input = dz1 + dqkv Wqkv
-    g12.a = w.dqkv; g12.lda = 3 * dm; g12.b = L.qkv_w; g12.ldb = dm; g12.add = dz1; g12.c = gx; g12.ldc = dm;
-    g12.M = M; g12.N = dm; g12.K = 3 * dm;
-    if ((rc = gemm_ex(g12, s, "bwd_dx"))) return rc;
+    // QKV: gradient w.r.t. the layer input = dz1 + dqkv Wqkv, dWqkv += dqkv^T x, dbqkv += sum dqkv
+    if ((rc = linear_bwd(tc, w.stage, w.dqkv, t.x, lqkv, dz1, gx, G.qkv_w, G.qkv_b, M, s, "bwd_dx", "bwd_dwqkv"))) return rc;
   }
   *g_x = gx;
   return MST_OK;
@@ -674,8 +829,6 @@ using namespace mst;
 // ---------------------------------------------------------------------------------------------------------
 static int check_train_engine(Engine* e) {
   if (!e->weights_loaded) return fail(MST_ERR_INVALID, "weights not loaded");
-  if (e->desc.precision != MST_PREC_FP32)
-    return fail(MST_ERR_UNSUPPORTED, "the training path runs on an MST_PREC_FP32 engine");
   if (e->desc.d_model % 32 != 0 || e->desc.d_model > 1024) return fail(MST_ERR_UNSUPPORTED, "d_model must be a multiple of 32, <= 1024");
   return MST_OK;
 }

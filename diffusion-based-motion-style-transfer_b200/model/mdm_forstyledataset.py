@@ -155,7 +155,7 @@ class _DenoiserGradFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, native, x, temb, text_emb, uncond, *params):
-        eng = native.mst_engine(x.device, precision="fp32")
+        eng = native.mst_engine(x.device, precision=native.mst_train_prec())
         out, tape = eng.forward_train(x, temb, text_emb, uncond=uncond)
         ctx.native, ctx.eng, ctx.tape = native, eng, tape
         return out
@@ -179,7 +179,7 @@ class _MotionEncoderGradFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, x, key_valid):
-        eng = enc.mst_engine(x.device, precision="fp32")
+        eng = enc.mst_engine(x.device, precision=enc.mst_train_prec())
         mu, tape = eng.motion_encoder_forward(x, key_valid, enc.muQuery.detach().reshape(-1).contiguous(),
                                               enc.sigmaQuery.detach().reshape(-1).contiguous())
         ctx.eng, ctx.tape, ctx.shape = eng, tape, tuple(x.shape)
@@ -200,6 +200,16 @@ class NativeDenoiser(nn.Module):
     """Common engine plumbing of MDM and StyleDiffusion."""
 
     mst_precision = None  # None -> MST_PRECISION env (bf16 default) ; or 'fp32' / 'bf16'
+    # precision of the linear layers on the training / differentiable-sampling path: 'fp32' (SIMT, parity mode, <=2e-4
+    # of the reference's gradients) or 'bf16' (tcgen05, bf16 operands + fp32 accumulation, <=3e-2).
+    # None -> MST_TRAIN_PRECISION env, else the same default as the sampler.
+    mst_train_precision = None
+
+    def mst_train_prec(self) -> str:
+        p = self.mst_train_precision or os.environ.get("MST_TRAIN_PRECISION") or self.mst_precision or default_precision()
+        if p not in ("bf16", "fp32"):
+            raise ValueError(f"training precision must be 'bf16' or 'fp32', got {p!r}")
+        return p
 
     # subclasses provide these views -------------------------------------------------
     def _mst_front(self):
@@ -346,9 +356,9 @@ class NativeDenoiser(nn.Module):
             # training / differentiable-sampling path (fp32 engine with an activation tape)
             enc_params = [p for l in self._mst_encoder().layers for p in l.mst_tensors().values()]
             with torch.no_grad():
-                eng = self.mst_engine(x.device, precision="fp32")
+                eng = self.mst_engine(x.device, precision=self.mst_train_prec())
                 temb = eng.time_embed(timesteps)
-                text_emb = None if force_mask else self.text_embedding(y, x.device, precision="fp32")
+                text_emb = None if force_mask else self.text_embedding(y, x.device, precision=self.mst_train_prec())
             if 'text' in self.cond_mode and text_emb is None and not force_mask:
                 raise RuntimeError("text-conditioned model called without text")
             return _DenoiserGradFn.apply(self, xc, temb, text_emb, force_mask or text_emb is None, *enc_params)
@@ -371,10 +381,16 @@ class NativeDenoiser(nn.Module):
         f = self._mst_front()
         front = [f.input_process, f.output_process, f.embed_timestep] + ([f.embed_text] if hasattr(f, "embed_text") else [])
         if any(p.requires_grad for m in front for p in m.parameters()):
-            raise NotImplementedError(
-                "gradients w.r.t. the in/out projections and the time/text embedders are not built: the reference's "
-                "finetune path trains only StyleDiffusion.seqTransEncoder (freeze the other modules or run under "
-                "torch.no_grad())")
+            # e.g. a freshly constructed MDM evaluated without torch.no_grad(): run the inference kernels; the result
+            # carries no grad_fn, so an attempted backward() fails loudly in torch instead of training half a model
+            if not getattr(self, "_mst_warned_front_grad", False):
+                import warnings
+                warnings.warn("mst denoiser called with autograd enabled while its in/out projections or time/text "
+                              "embedders require grad: gradients are only built for the encoder stack (the reference's "
+                              "finetune path, StyleDiffusion with a frozen front end); this call is NOT differentiable. "
+                              "Freeze those modules to train, or wrap inference in torch.no_grad().")
+                self._mst_warned_front_grad = True
+            return False
         return True
 
     def forward_cfg(self, x, timesteps, y):
@@ -578,6 +594,11 @@ class StyleDiffusion(NativeDenoiser):
 
     def _mst_encoder(self):
         return self.seqTransEncoder
+
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name == "mst_train_precision" and "motion_enc" in self._modules:
+            self.motion_enc.mst_train_precision = value  # the semantic discriminator runs in the same mode
 
     def encode_text(self, raw_text):
         return self.motion_enc.mdm_model.encode_text(raw_text)

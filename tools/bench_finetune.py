@@ -23,7 +23,7 @@ sys.path.insert(0, REPO)
 import bench  # noqa: E402
 
 
-def build(dev, B, T, sg):
+def build(dev, B, T, sg, precision="bf16"):
     from mst_b200.data_loaders.stylexia_posrot_utils import get_inpainting_mask
     from mst_b200.model.mdm_forstyledataset import MDM, MotionEncoder, StyleDiffusion
     from mst_b200.train.training_loop import TrainInpaintingLoop
@@ -44,6 +44,7 @@ def build(dev, B, T, sg):
     args.mdm_path, args.semantic_discriminator_path = os.path.join(tmp, "mdm.pt"), os.path.join(tmp, "menc.pt")
     model = StyleDiffusion(load_clip=False, **mu.get_transfer_args(args)).to(dev)
     model.train()
+    model.mst_train_precision = precision
     diffusion = mu.create_gaussian_diffusion(args, mu.InpaintingGaussianDiffusion, timestep_respacing="ddim20")
     g = torch.Generator().manual_seed(1)
     F = 181
@@ -70,16 +71,19 @@ def main():
     ap.add_argument("--frames", type=int, default=76)
     ap.add_argument("--sg", type=int, default=1)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     np.random.seed(0)
     from mst_b200 import engine as K
-    loop, batch = build(dev, a.batch, a.frames, a.sg)
+    loop, batch = build(dev, a.batch, a.frames, a.sg, a.precision)
     for _ in range(a.warmup):
         loop.run_step(*batch)
     torch.cuda.synchronize()
@@ -97,7 +101,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = (K.launch_count() - n0) // a.steps
     out = {"metric": "finetune_ms_per_step", "value": float(ms.item()), "unit": "ms", "n_gpus": world, "steps": a.steps,
-           "warmup": a.warmup, "higher_is_better": False, "dtype": "f32", "data": "synthetic",
+           "warmup": a.warmup, "higher_is_better": False, "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
            "config": {"workload": f"few-shot style finetune step: t2m batch B={a.batch} x T={a.frames} (sharded over "
                                   f"{world} GPU), style example B=1 x 6 DDIM steps with grad, semantic_guidance={a.sg}, "
                                   "AdamW lr 1e-4 (BASELINE configs[3])"},
