@@ -311,7 +311,9 @@ def test_denoiser_forward_matches_golden(K, state, golden, precision, tol):
     oc, ou = eng.forward(x.to(DEV), temb, text, cfg=True)
     assert relerr(oc, golden["fwd_out_cond"]) < tol and relerr(ou, golden["fwd_out_uncond"]) < tol
     if precision == "fp32":
-        assert torch.equal(oc, got_c) and torch.equal(ou, got_u)  # batching the two passes changes nothing
+        # batching the two passes changes nothing but the fp32 summation order (the row count selects between the
+        # tiled and the one-warp-per-output SIMT GEMM)
+        assert relerr(oc, got_c) < 2e-6 and relerr(ou, got_u) < 2e-6
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
