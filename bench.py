@@ -330,6 +330,12 @@ def main():
         dist.destroy_process_group()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four GEMM launches of one layer (QKV 54.6 MB,
+# out-proj+LN 56.5 MB, FFN1+GELU 32.8 MB, FFN2+LN 85.0 MB) from one `ncu --set full` capture of the B=64, T=196 step
+NCU_TRAFFIC_B64 = {(64, 196): 57.2e6}
+NCU_TRAFFIC_SRC = "profiles/r01e_ncu_full_step_kernels_summary.txt (bytes per launch, mean of the 4 GEMM launches of a layer)"
+
+
 def roofline_leg(K, model, dev, B, T, pk, ms_denoise_in_graph, steady=True):
     """Per-launch CUDA-event timing of one denoise step (forward with cond+uncond batched, then the fused update),
     captured as a CUDA graph with an event after every kernel and replayed in steady state -> roofline of the
@@ -408,8 +414,14 @@ def roofline_leg(K, model, dev, B, T, pk, ms_denoise_in_graph, steady=True):
         achieved = fl / (ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel<BN,EPI> (all epilogues)", "achieved": achieved,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-                "peak_kind": f"{pk['src']} sustained cuBLAS bf16 (kernel timed inside a long step)", "traffic": None,
+                "peak_kind": f"{pk['src']} sustained cuBLAS bf16 (kernel timed inside a long step)",
+                "traffic": NCU_TRAFFIC_B64.get((B, T)), "traffic_src": NCU_TRAFFIC_SRC if (B, T) in NCU_TRAFFIC_B64 else None,
                 "share_of_step": ms / total, "profiled_step_ms": total, "graph_step_ms": ms_denoise_in_graph}
+    if roof is not None:
+        # the secondary bound that explains the tensor fraction: every tile design here stages 128 A rows + 128 W rows
+        # per CTA and k-block = 128 flop per byte pulled through L2, and the L2 slices deliver ~6300 B/clk chip-wide
+        roof["l2_bound_note"] = ("GEMM tiles move 1 B through L2 per 128 flop; at the ~6300 B/clk LTS cap that is "
+                                 "0.66 of the tensor pipe's 8192 flop/clk/SM - see DESIGN.md section 4")
     upd = [s for s in stages if s["kernel"] == "update"]
     if upd and roof is not None:
         by = 20 * B * F_FEATS * T  # out_c, out_u, x_t, x_inp read + x_{t-1} write, [F] mask, in-kernel Philox

@@ -30,7 +30,7 @@ EXPORTED = [
     "mst_text_embed", "mst_denoiser_forward", "mst_update_step", "mst_q_sample", "mst_cfg_combine",
     "mst_philox_normal", "mst_train_sizes", "mst_denoiser_forward_train", "mst_denoiser_backward", "mst_abi_sizes_train",
     "mst_motion_encoder_forward", "mst_motion_encoder_backward", "mst_masked_l2", "mst_update_step_backward",
-    "mst_adamw_step", "mst_sumsq2", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
+    "mst_adamw_step", "mst_sumsq2", "mst_recover_from_ric", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
 ]
 
 
@@ -154,6 +154,7 @@ def _declare(lib):
         "mst_update_step_backward": [vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp],
         "mst_adamw_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.c_float, vp],
         "mst_sumsq2": [vp, vp, i64, vp, vp],
+        "mst_recover_from_ric": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "mst_test_gemm_bf16": [vp, vp, vp, vp, i32, i32, i32, vp],
         "mst_test_gemm_epi_bf16": [i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "mst_test_set_gemm_debug": [vp],

@@ -158,7 +158,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
-      printf("mst: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      if ((threadIdx.x & 31) == 0 || (threadIdx.x & 31) == 31)
+        printf("mst: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, bar, parity);
       __trap();
     }
   }

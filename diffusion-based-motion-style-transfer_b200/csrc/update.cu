@@ -330,3 +330,92 @@ extern "C" int mst_philox_normal(float* out, int32_t batch, int64_t per_sample, 
   MST_LAUNCHED("philox_normal", (cudaStream_t)stream);
   return MST_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Post-sampling decode: inv_transform (x * std + mean, data_loaders/humanml/data/dataset.py:478-479)
+// + recover_from_ric (data_loaders/humanml/scripts/motion_process.py:389-411, :444-461) fused, reading the sampler's
+// own [B, F, 1, T] layout (the reference permutes to [B, 1, T, F] on the CPU first, sample/demo_style_transfer.py:265).
+//   r_rot_ang[t] = sum_{s<t} rot_vel[s];  q = (cos, 0, sin, 0);  r_pos = cumsum_t qrot(q, (vx[t-1], 0, vz[t-1])), y = root_y
+//   joint j >= 1: qrot(q, ric_j) + (r_pos.x, 0, r_pos.z);  joint 0 = r_pos.           out: [B, T, J, 3]
+// One CTA per sample: the three prefix sums are a 3 x T sequential scan by one thread in the reference's summation
+// order (T <= a few hundred), the joints are elementwise.
+// ---------------------------------------------------------------------------------------------------------
+namespace mst {
+
+__device__ __forceinline__ void qrot_y(float c, float sn, float vx, float vy, float vz, float& ox, float& oy, float& oz) {
+  // qrot(q, v) with q = (c, 0, sn, 0) written as the reference's two cross products (quaternion.py:88-99), u = (0, sn, 0)
+  const float uvx = sn * vz - 0.0f * vy, uvy = 0.0f * vx - 0.0f * vz, uvz = 0.0f * vy - sn * vx;
+  const float uuvx = sn * uvz - 0.0f * uvy, uuvy = 0.0f * uvx - 0.0f * uvz, uuvz = 0.0f * uvy - sn * uvx;
+  ox = vx + 2.0f * (c * uvx + uuvx);
+  oy = vy + 2.0f * (c * uvy + uuvy);
+  oz = vz + 2.0f * (c * uvz + uuvz);
+}
+
+__global__ void __launch_bounds__(256) recover_from_ric_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                               const float* __restrict__ stdv, float* __restrict__ out, int F,
+                                                               int T, int J) {
+  extern __shared__ float sm[];
+  float* ang = sm;          // [T] r_rot_ang, then cos
+  float* sn = sm + T;       // [T] sin
+  float* px = sm + 2 * T;   // [T] root x
+  float* pz = sm + 3 * T;   // [T] root z
+  const int b = blockIdx.x;
+  const float* xb = x + (size_t)b * F * T;
+  auto feat = [&](int f, int t) { return mean ? xb[(size_t)f * T + t] * stdv[f] + mean[f] : xb[(size_t)f * T + t]; };
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    ang[t] = t == 0 ? 0.0f : feat(0, t - 1);
+    px[t] = t == 0 ? 0.0f : feat(1, t - 1);
+    pz[t] = t == 0 ? 0.0f : feat(2, t - 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // torch.cumsum order
+    float a = 0.0f;
+    for (int t = 0; t < T; ++t) { a += ang[t]; ang[t] = a; }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float a = ang[t];
+    const float c = cosf(a), s_ = sinf(a);
+    float ox, oy, oz;
+    qrot_y(c, s_, px[t], 0.0f, pz[t], ox, oy, oz);
+    ang[t] = c;
+    sn[t] = s_;
+    px[t] = ox;
+    pz[t] = oz;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ax = 0.0f, az = 0.0f;
+    for (int t = 0; t < T; ++t) { ax += px[t]; az += pz[t]; px[t] = ax; pz[t] = az; }
+  }
+  __syncthreads();
+  float* ob = out + (size_t)b * T * J * 3;
+  for (int i = threadIdx.x; i < T * J; i += blockDim.x) {
+    const int j = i / T, t = i - j * T;  // t fastest: coalesced reads of x[b][f][t]
+    float* o = ob + ((size_t)t * J + j) * 3;
+    if (j == 0) {
+      o[0] = px[t]; o[1] = feat(3, t); o[2] = pz[t];
+    } else {
+      const int f = 4 + 3 * (j - 1);
+      float ox, oy, oz;
+      qrot_y(ang[t], sn[t], feat(f, t), feat(f + 1, t), feat(f + 2, t), ox, oy, oz);
+      o[0] = ox + px[t]; o[1] = oy; o[2] = oz + pz[t];
+    }
+  }
+}
+
+}  // namespace mst
+
+extern "C" int mst_recover_from_ric(const float* x, const float* mean, const float* stdv, float* joints, int32_t batch,
+                                    int32_t n_feats, int32_t n_frames, int32_t joints_num, void* stream) {
+  MST_CHECK_ARG(x && joints, "null tensor pointer");
+  MST_CHECK_ARG((mean == nullptr) == (stdv == nullptr), "give both mean and std, or neither");
+  MST_CHECK_ARG(batch > 0 && n_frames > 0 && joints_num > 0, "non-positive size");
+  MST_CHECK_ARG(n_feats >= 4 + 3 * (joints_num - 1), "n_feats too small for joints_num (needs 4 + 3 (J - 1) features)");
+  const size_t smem = (size_t)4 * n_frames * sizeof(float);
+  MST_CHECK_ARG(smem <= 48 * 1024, "sequence too long for the decode kernel (n_frames <= 3072)");
+  cudaStream_t s = (cudaStream_t)stream;
+  mst::recover_from_ric_kernel<<<batch, 256, smem, s>>>(x, mean, stdv, joints, n_feats, n_frames, joints_num);
+  MST_LAUNCHED("recover_from_ric", s);
+  return MST_OK;
+}

@@ -279,6 +279,15 @@ def update_step_backward(d_x0, d_sample, k_table, t_vec, mask, pred_xstart, clip
     return d_out
 
 
+def recover_from_ric(x, joints_num, mean=None, std=None):
+    """x [B,F,1,T] (sampler layout) -> joints [B,1,T,J,3]: inv_transform + recover_from_ric fused (scope row N2)."""
+    B, F, T = x.shape[0], x.shape[1] * x.shape[2], x.shape[3]
+    out = torch.empty(B, 1, T, joints_num, 3, dtype=torch.float32, device=x.device)
+    L.check(L.load().mst_recover_from_ric(_ptr(x, name="x"), _ptr(mean, name="mean"), _ptr(std, name="std"), out.data_ptr(),
+                                          B, F, T, int(joints_num), _stream_ptr()), "mst_recover_from_ric")
+    return out
+
+
 def adamw_step(params, grads, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,
                grad_scale=1.0):
     """torch.optim.AdamW step over flat fp32 arenas, one launch."""

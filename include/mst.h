@@ -344,6 +344,14 @@ int mst_adamw_step(float* params, const float* grads, float* exp_avg, float* exp
  * 215-223) without its 192 host syncs.                                      */
 int mst_sumsq2(const float* x, const float* y, int64_t n, double* out2, void* stream);
 
+/* Post-sampling decode (scope row N2), fused: inv_transform x*std+mean
+ * (data_loaders/humanml/data/dataset.py:478-479; mean/std [F] device, both
+ * NULL = already de-normalised) + recover_from_ric
+ * (data_loaders/humanml/scripts/motion_process.py:389-411, :444-461).
+ * x: [B,F,T] in the sampler's layout; joints: [B,T,J,3] out.               */
+int mst_recover_from_ric(const float* x, const float* mean, const float* stdv, float* joints, int32_t batch,
+                         int32_t n_feats, int32_t n_frames, int32_t joints_num, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * Kernel-level test hooks (used by tests/ and bench.py roofline legs only).
  * ------------------------------------------------------------------------ */

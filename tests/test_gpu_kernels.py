@@ -327,3 +327,28 @@ def test_denoiser_forward_matches_oracle_shapes(K, precision, tol, B, T, F):
     want_u = OD.mdm_forward(st, x, t, feat, uncond=True)
     oc, ou = eng.forward(x.to(DEV), eng.time_embed(t.to(DEV)), eng.text_embed(feat.to(DEV)), cfg=True)
     assert relerr(oc, want_c) < tol and relerr(ou, want_u) < tol
+
+
+# ------------------------------------------------------------------ post-sampling decode (scope row N2)
+@pytest.mark.parametrize("name,F,T,J", [("stylexia", 181, 76, 20), ("humanml", 263, 196, 22), ("bandai", 190, 60, 21)])
+def test_decode_motion_matches_reference_recover_from_ric(name, F, T, J):
+    """inv_transform + recover_from_ric fused into one kernel against tests/golden/decode.npz (the REAL reference's
+    recover_from_ric, tests/golden/make_golden_decode.py).  fp32; the three prefix sums run in the reference's order, so
+    only cos/sin (device vs host libm) differ: 2e-5 of the largest coordinate."""
+    import os
+    import numpy as np
+    from mst_b200.data_loaders.humanml.scripts.motion_process import decode_motion, recover_from_ric
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decode.npz"))
+    g = torch.Generator().manual_seed(0)   # same draws as make_golden_decode.inputs
+    sample = torch.randn(3, F, 1, T, generator=g)
+    mean = torch.randn(F, generator=g) * 0.3
+    std = torch.rand(F, generator=g) * 0.5 + 0.05
+    want = torch.from_numpy(gold[f"{name}/joints"])
+    got = decode_motion(sample.to(DEV), mean, std, J)
+    assert tuple(got.shape) == (3, 1, T, J, 3)
+    assert relerr(got, want) < 2e-5
+    # the reference-shaped entry point: de-normalised [B, 1, T, F] in, [B, 1, T, J, 3] out
+    denorm = (sample.permute(0, 2, 3, 1) * std + mean).float().to(DEV)
+    assert relerr(recover_from_ric(denorm, J), want) < 2e-5
+    with pytest.raises(RuntimeError, match="CUDA"):
+        recover_from_ric(denorm.cpu(), J)

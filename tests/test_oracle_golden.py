@@ -83,3 +83,20 @@ def test_demo_ddim_path_matches_reference(state, golden):
                            ddim=True, mask=mask, x_inp=style, skip_timesteps=14, init_image=content)
     assert len(xs) == 6
     assert max(relerr(a, b) for a, b in zip(xs, golden["demo_xstart"])) < 5e-5
+
+
+def test_oracle_decode_matches_reference_golden():
+    """oracle/decode.py (inv_transform + recover_from_ric) against the real reference's outputs (tests/golden/decode.npz)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import decode as OD
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decode.npz"))
+    for name, F, T, J in [("stylexia", 181, 76, 20), ("humanml", 263, 196, 22), ("bandai", 190, 60, 21)]:
+        g = torch.Generator().manual_seed(0)
+        sample = torch.randn(3, F, 1, T, generator=g)
+        mean = torch.randn(F, generator=g) * 0.3
+        std = torch.rand(F, generator=g) * 0.5 + 0.05
+        got = OD.decode_motion(sample, mean, std, J)
+        want = torch.from_numpy(gold[f"{name}/joints"])
+        assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max())
