@@ -8,7 +8,7 @@ pre-processing functions of the reference module stay in the reference.  The wor
 """
 import torch
 
-from ... import engine as K
+from .... import engine as K
 
 
 def _require_cuda(t):
