@@ -622,7 +622,11 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t par_smem = exch_smem + Cfg::EXCH_BYTES;
   Ring ring{base, par_smem + Cfg::PARAM_BYTES, Cfg::STAGES, Cfg::STAGE_BYTES, Cfg::A_BYTES};
   const uint32_t tmem_slot = ring.extra(0);
-  const uint32_t stats_bar = ring.extra(1);                   // 256 local arrivals + 2048 transaction bytes from the partner
+  // Row-statistics barriers, one per tile parity: 256 local arrivals + 2048 transaction bytes from the partner.
+  // Two barriers (not one with two phases): the partner's st.async bytes of tile i+1 may be issued while a slow thread
+  // of this CTA has not yet arrived for tile i; on a single barrier they would be booked on tile i's transaction
+  // count and that phase could never complete (seen as a once-in-10^8-tiles cluster hang at B=2048).
+  auto stats_bar = [&](uint32_t par_) { return par_ ? ring.extra(6) : ring.extra(1); };
   // The residual tile of a block (128 rows x 256 columns = two ring slots of [128 x 64 | 128 x 64]) travels through the
   // SAME ring as the k-blocks, right behind the block's last k-block: it is in flight while the MMAs finish and costs
   // no dedicated staging memory.  Slot h of the two holds the columns of epilogue half h.
@@ -652,7 +656,8 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_init(ring.tfull(i), 1);
       mbar_init(ring.tempty(i), 2 * NUM_EPI_THREADS);
     }
-    mbar_init(stats_bar, NUM_EPI_THREADS);
+    mbar_init(stats_bar(0), NUM_EPI_THREADS);
+    mbar_init(stats_bar(1), NUM_EPI_THREADS);
     for (int h = 0; h < 2; ++h) {
       mbar_init(res_full(h), 1);
       mbar_init(res_free(h), NUM_EPI_THREADS / 2);
@@ -763,7 +768,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t my_obox = out_smem + ew * 2 * Cfg::OBOX_BYTES;  // output: two [32 x 32] boxes, ping-pong
     const uint32_t partner = rank ^ 2u;  // the CTA holding the other 256 columns of the same rows
     const uint32_t peer_exch = map_to_cta(exch_smem, partner);
-    const uint32_t peer_stats_bar = map_to_cta(stats_bar, partner);
+    const uint32_t peer_stats_bar0 = map_to_cta(stats_bar(0), partner), peer_stats_bar1 = map_to_cta(stats_bar(1), partner);
     const int my_src = (int)pair * 2 + half;
     const uint32_t my_row = (uint32_t)r * 128;  // this thread's row inside a [128 x 64] residual box
     int acc = 0, it = 0;
@@ -831,13 +836,14 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       MST_DBG_STAMP();
       // row statistics: 4 partials per row (2 pairs x 2 halves)
       const uint32_t slot = (uint32_t)(((par * 4 + my_src) * BLOCK_M + r) * 8);
-      st_async_f32x2(peer_exch + slot, sum, sq, peer_stats_bar);
+      const uint32_t sbar = stats_bar(par);
+      st_async_f32x2(peer_exch + slot, sum, sq, par ? peer_stats_bar1 : peer_stats_bar0);
       asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(exch_smem + slot), "f"(sum), "f"(sq) : "memory");
       if (ew == 0 && lane == 0)
-        mbar_expect_tx(stats_bar, NUM_EPI_THREADS * 8);  // arrive + the partner's 256 x 8 bytes of this phase
+        mbar_expect_tx(sbar, NUM_EPI_THREADS * 8);  // arrive + the partner's 256 x 8 bytes of this tile
       else
-        mbar_arrive(stats_bar);
-      mbar_wait_cluster(stats_bar, par);
+        mbar_arrive(sbar);
+      mbar_wait_cluster(sbar, (uint32_t)(it >> 1) & 1u);
       MST_DBG_STAMP();
       float tsum = 0.0f, tsq = 0.0f;
 #pragma unroll
