@@ -18,6 +18,11 @@
 #include "tc.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 namespace mst {
 
@@ -820,6 +825,79 @@ __global__ void __launch_bounds__(256) sumsq2_kernel(const float* __restrict__ x
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CUDA-graph replay of a whole taped forward / backward.  The B=1 style example of the finetune step is ~150 (forward) and
+// ~300 (backward) dependent launches of a few microseconds each: launch-bound.  When the caller promises stable
+// pointers (use_graph), the launch sequence is captured once per distinct argument set - on an internal stream, since
+// torch's current stream is usually the legacy default stream, which cannot be captured - and replayed with one
+// cudaGraphLaunch on the caller's stream.  Any capture problem falls back to the eager sequence.
+// ---------------------------------------------------------------------------------------------------------
+static uint64_t fnv1a(const void* p, size_t n, uint64_t h) {
+  const unsigned char* c = static_cast<const unsigned char*>(p);
+  for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+static bool train_graphs_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MST_TRAIN_GRAPH");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename Body>
+static int run_graphed(bool use_graph, uint64_t key, cudaStream_t user, Body&& body) {
+  if (!use_graph || !train_graphs_enabled()) return body(user);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(user, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return body(user);  // already inside somebody else's capture: just record the launches there
+  }
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, cudaGraphExec_t> cache;
+  static cudaStream_t cap_stream = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) exec = it->second;
+  }
+  if (!exec) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!cap_stream && cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      return body(user);
+    }
+    if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return body(user);
+    }
+    const int rc = body(cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e1 = cudaStreamEndCapture(cap_stream, &graph);
+    if (rc != MST_OK || e1 != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc != MST_OK ? rc : body(user);
+    }
+    const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess || !exec) {
+      cudaGetLastError();
+      return body(user);
+    }
+    if (cache.size() >= 256) {  // bound the cache
+      for (auto& kv : cache) cudaGraphExecDestroy(kv.second);
+      cache.clear();
+    }
+    cache[key] = exec;
+  }
+  MST_CUDA_OK(cudaGraphLaunch(exec, user));
+  note_launch("train_graph", user);
+  return MST_OK;
+}
+
 }  // namespace mst
 
 using namespace mst;
@@ -863,27 +941,32 @@ extern "C" int mst_denoiser_forward_train(mst_engine_t h, const mst_forward_args
   const int B = a.batch, T = a.n_frames, S = T + 1, dm = d.d_model;
   Tape tp;
   MST_CHECK_ARG(tape_bytes >= carve_tape(d, B, S, tape, &tp), "tape too small");
-  cudaStream_t s = (cudaStream_t)stream;
-  Token0Params t0;
-  t0.temb = a.temb; t0.temb_row_dev = a.temb_row_dev; t0.temb_row_offset = a.temb_row_offset;
-  t0.text_emb = a.text_emb; t0.txt_b = e->txt_b; t0.pe = e->pe; t0.x_f32 = tp.l[0].x;
-  t0.B = B; t0.T = T; t0.d = dm; t0.cfg = 0; t0.uncond = a.uncond;
-  if ((rc = token0(t0, B, s))) return rc;
-  {
-    GemmF32Params p;
-    p.a = a.x; p.a_mode = A_MOTION; p.w = e->in_w; p.ldw = d.n_feats; p.bias = e->in_b;
-    p.c = tp.l[0].x; p.ldc = dm; p.M = B * T; p.N = dm; p.K = d.n_feats; p.epi = EPI_INPROJ;
-    p.pe = e->pe; p.B = B; p.T = T; p.n_pass = 1;
-    if ((rc = gemm_f32(p, s))) return rc;
-  }
-  if ((rc = encoder_forward_tape(e, tp, B, S, nullptr, s))) return rc;
-  {
-    GemmF32Params p;
-    p.a = tp.x_out; p.lda = dm; p.w = e->out_w; p.ldw = dm; p.bias = e->out_b;
-    p.c = a.out_cond; p.M = B * S; p.N = d.n_feats; p.K = dm; p.epi = EPI_OUTPROJ; p.T = T; p.B = B;
-    if ((rc = gemm_f32(p, s))) return rc;
-  }
-  return MST_OK;
+  uint64_t key = fnv1a(&a, sizeof(a), 1469598103934665603ull);
+  key = fnv1a(e, sizeof(Engine), key);
+  key = fnv1a(&tape, sizeof(tape), key) ^ 0x66ull;
+  return run_graphed(a.use_graph != 0, key, (cudaStream_t)stream, [&](cudaStream_t s) -> int {
+    int rc;
+    Token0Params t0;
+    t0.temb = a.temb; t0.temb_row_dev = a.temb_row_dev; t0.temb_row_offset = a.temb_row_offset;
+    t0.text_emb = a.text_emb; t0.txt_b = e->txt_b; t0.pe = e->pe; t0.x_f32 = tp.l[0].x;
+    t0.B = B; t0.T = T; t0.d = dm; t0.cfg = 0; t0.uncond = a.uncond;
+    if ((rc = token0(t0, B, s))) return rc;
+    {
+      GemmF32Params p;
+      p.a = a.x; p.a_mode = A_MOTION; p.w = e->in_w; p.ldw = d.n_feats; p.bias = e->in_b;
+      p.c = tp.l[0].x; p.ldc = dm; p.M = B * T; p.N = dm; p.K = d.n_feats; p.epi = EPI_INPROJ;
+      p.pe = e->pe; p.B = B; p.T = T; p.n_pass = 1;
+      if ((rc = gemm_f32(p, s))) return rc;
+    }
+    if ((rc = encoder_forward_tape(e, tp, B, S, nullptr, s))) return rc;
+    {
+      GemmF32Params p;
+      p.a = tp.x_out; p.lda = dm; p.w = e->out_w; p.ldw = dm; p.bias = e->out_b;
+      p.c = a.out_cond; p.M = B * S; p.N = d.n_feats; p.K = dm; p.epi = EPI_OUTPROJ; p.T = T; p.B = B;
+      if ((rc = gemm_f32(p, s))) return rc;
+    }
+    return MST_OK;
+  });
 }
 
 extern "C" int mst_denoiser_backward(mst_engine_t h, const mst_backward_args* ap, void* stream) {
@@ -900,23 +983,32 @@ extern "C" int mst_denoiser_backward(mst_engine_t h, const mst_backward_args* ap
   BwdScratch w;
   MST_CHECK_ARG(a.tape_bytes >= carve_tape(d, B, S, const_cast<void*>(a.tape), &tp), "tape too small");
   MST_CHECK_ARG(a.scratch_bytes >= carve_bwd(d, B, S, a.scratch, &w), "scratch too small");
-  cudaStream_t s = (cudaStream_t)stream;
-  // OutputProcess backward: g[(b,s)][k] = s == 0 ? 0 : sum_f d_out[b][f][s-1] out_w[f][k]   (into the dqkv scratch's
-  // first [M, d] floats would alias later use - the tape's x_out slot is dead after the forward, reuse it)
-  float* g = tp.x_out;
-  GemmEx go;
-  go.a = a.d_out; go.a_mode = AX_MOTION_TOK; go.T = T; go.tok_off = 1; go.b = e->out_w; go.ldb = dm; go.c = g; go.ldc = dm;
-  go.M = M; go.N = dm; go.K = d.n_feats;
-  if ((rc = gemm_ex(go, s, "bwd_outproj"))) return rc;
-  float* gx = nullptr;
-  if ((rc = encoder_backward(e, tp, a.layer_grads, B, S, g, w, &gx, s))) return rc;
-  if (a.d_x) {  // InputProcess backward: d_x[b][f][t] = sum_n gx[(b,t+1)][n] in_w[n][f]
-    GemmEx gi;
-    gi.a = gx; gi.lda = dm; gi.a_mode = AX_TOKROWS; gi.T = T; gi.tok_off = 1; gi.b = e->in_w; gi.ldb = d.n_feats;
-    gi.c = a.d_x; gi.c_mode = CX_MOTION; gi.M = B * T; gi.N = d.n_feats; gi.K = dm;
-    if ((rc = gemm_ex(gi, s, "bwd_inproj"))) return rc;
-  }
-  return MST_OK;
+  // key: every device pointer / size of the call (not the host address of the layer_grads array, its contents)
+  const void* kp[] = {a.d_out, a.d_x, a.tape, a.scratch};
+  const size_t kn[] = {(size_t)a.batch, (size_t)a.n_frames, a.tape_bytes, a.scratch_bytes};
+  uint64_t key = fnv1a(kp, sizeof(kp), 1469598103934665603ull);
+  key = fnv1a(kn, sizeof(kn), key);
+  key = fnv1a(e, sizeof(Engine), key);
+  key = fnv1a(a.layer_grads, sizeof(mst_layer_grads) * d.n_layers, key) ^ 0xb7ull;
+  return run_graphed(a.use_graph != 0, key, (cudaStream_t)stream, [&](cudaStream_t s) -> int {
+    int rc;
+    // OutputProcess backward: g[(b,s)][k] = s == 0 ? 0 : sum_f d_out[b][f][s-1] out_w[f][k]   (the tape's x_out slot is
+    // dead after the forward: reuse it)
+    float* g = tp.x_out;
+    GemmEx go;
+    go.a = a.d_out; go.a_mode = AX_MOTION_TOK; go.T = T; go.tok_off = 1; go.b = e->out_w; go.ldb = dm; go.c = g; go.ldc = dm;
+    go.M = M; go.N = dm; go.K = d.n_feats;
+    if ((rc = gemm_ex(go, s, "bwd_outproj"))) return rc;
+    float* gx = nullptr;
+    if ((rc = encoder_backward(e, tp, a.layer_grads, B, S, g, w, &gx, s))) return rc;
+    if (a.d_x) {  // InputProcess backward: d_x[b][f][t] = sum_n gx[(b,t+1)][n] in_w[n][f]
+      GemmEx gi;
+      gi.a = gx; gi.lda = dm; gi.a_mode = AX_TOKROWS; gi.T = T; gi.tok_off = 1; gi.b = e->in_w; gi.ldb = d.n_feats;
+      gi.c = a.d_x; gi.c_mode = CX_MOTION; gi.M = B * T; gi.N = d.n_feats; gi.K = dm;
+      if ((rc = gemm_ex(gi, s, "bwd_inproj"))) return rc;
+    }
+    return MST_OK;
+  });
 }
 
 // MotionEncoder (mdm_forstyledataset.py:89-124): tokens = [muQuery, sigmaQuery, InputProcess(x)] + pe, key-padding

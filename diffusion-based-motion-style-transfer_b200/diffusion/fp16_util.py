@@ -79,10 +79,18 @@ class MixedPrecisionTrainer:
         self.master_params = self.model_params
         self.lg_loss_scale = initial_lg_loss_scale
         self.last_norms = (0.0, 0.0)
+        # gradients live in the arena from now on: the model may run its forward / backward on pooled tapes and
+        # accumulate straight into them (CUDA-graph replay, model/mdm_forstyledataset.py::_DenoiserGradFn)
+        for m in model.modules():
+            if hasattr(m, "mst_tape_pool"):
+                m.mst_tape_pool = True
 
     def zero_grad(self):
         self.flat.ensure_grad_views()
         self.flat.grads.zero_()
+        for m in self.model.modules():
+            if hasattr(m, "mst_tape_reset"):
+                m.mst_tape_reset()
 
     def backward(self, loss: th.Tensor):
         loss.backward()

@@ -179,15 +179,21 @@ class Engine:
         return self._bwd_scratch
 
     def forward_train(self, x: torch.Tensor, temb: torch.Tensor, text_emb: Optional[torch.Tensor], *,
-                      uncond: bool = False):
-        """Denoiser forward that records the activation tape.  Returns (out [B,F,1,T], tape)."""
+                      uncond: bool = False, tape: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                      use_graph: bool = False):
+        """Denoiser forward that records the activation tape.  Returns (out [B,F,1,T], tape).
+        use_graph=True promises that x / temb / text_emb / out / tape are the same buffers on every call with this
+        shape (a TapeSlot): the launch sequence is then captured once and replayed as a CUDA graph."""
         B, T = x.shape[0], x.shape[-1]
         if x.numel() != B * self.n_feats * T:
             raise ValueError(f"x has shape {tuple(x.shape)}, expected [B,{self.n_feats},1,T]")
-        tape_bytes, _ = self.train_sizes(B, T + 1)
-        tape = torch.empty(tape_bytes, dtype=torch.uint8, device=self.device)
-        out = torch.empty_like(x)
+        if tape is None:
+            tape_bytes, _ = self.train_sizes(B, T + 1)
+            tape = torch.empty(tape_bytes, dtype=torch.uint8, device=self.device)
+        if out is None:
+            out = torch.empty_like(x)
         a = L.ForwardArgs()
+        a.use_graph = int(bool(use_graph))
         a.batch, a.n_frames, a.cfg, a.uncond = B, T, 0, int(uncond)
         a.x = _ptr(x, name="x")
         a.temb = _ptr(temb, name="temb")
@@ -199,7 +205,8 @@ class Engine:
                 "mst_denoiser_forward_train")
         return out, tape
 
-    def backward(self, d_out: torch.Tensor, tape: torch.Tensor, layer_grads: list, want_dx: bool = False):
+    def backward(self, d_out: torch.Tensor, tape: torch.Tensor, layer_grads: list, want_dx: bool = False,
+                 use_graph: bool = False):
         """Back-propagate d_out [B,F,1,T] through the taped forward.  layer_grads: per layer a dict keyed by LAYER_KEYS
         of fp32 CUDA tensors (or None) that the gradients are ACCUMULATED into.  Returns d_x or None."""
         B, T = d_out.shape[0], d_out.shape[-1]
@@ -214,6 +221,7 @@ class Engine:
                 setattr(arr[i], k, _ptr(lg.get(k), name=f"grad.layer{i}.{k}"))
         d_x = torch.empty_like(d_out) if want_dx else None
         a = L.BackwardArgs()
+        a.use_graph = int(bool(use_graph))
         a.batch, a.n_frames = B, T
         a.d_out, a.d_x = _ptr(d_out, name="d_out"), _ptr(d_x, name="d_x")
         a.layer_grads = arr
@@ -244,6 +252,22 @@ class Engine:
             self._h, _ptr(d_mu, name="d_mu"), B, T, d_x.data_ptr(), tape.data_ptr(), tape.numel(), scratch.data_ptr(),
             scratch.numel(), _stream_ptr()), "mst_motion_encoder_backward")
         return d_x
+
+
+class TapeSlot:
+    """Persistent buffers of one taped forward / backward of a given shape: with every pointer stable from one training
+    step to the next, the C side replays the whole launch sequence as a CUDA graph (mst_forward_args.use_graph)."""
+
+    def __init__(self, eng: "Engine", B: int, T: int, has_text: bool):
+        dev, f32 = eng.device, torch.float32
+        tape_bytes, _ = eng.train_sizes(B, T + 1)
+        self.tape = torch.empty(tape_bytes, dtype=torch.uint8, device=dev)
+        self.x = torch.empty(B, eng.n_feats, 1, T, dtype=f32, device=dev)
+        self.temb = torch.empty(B, eng.d_model, dtype=f32, device=dev)
+        self.text = torch.empty(B, eng.d_model, dtype=f32, device=dev) if has_text else None
+        self.out = torch.empty(B, eng.n_feats, 1, T, dtype=f32, device=dev)
+        self.d_out = torch.empty(B, eng.n_feats, 1, T, dtype=f32, device=dev)
+        self.epoch = 0  # bumped every time the slot is handed out: a stale autograd node can tell its tape is gone
 
 
 # ---------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ..engine import Engine, default_precision
+from ..engine import Engine, TapeSlot, default_precision
 
 
 # ----------------------------------------------------------------------------------
@@ -151,13 +151,29 @@ def _flat_layer_grads(params_by_layer, needs):
 
 
 class _DenoiserGradFn(torch.autograd.Function):
-    """x0 prediction with a gradient path to the encoder-layer parameters (and to x when it requires grad)."""
+    """x0 prediction with a gradient path to the encoder-layer parameters (and to x when it requires grad).
+
+    Two modes.  Pooled (``native.mst_tape_pool`` active - the trainer switches it on): the forward runs on a persistent
+    TapeSlot and the backward accumulates straight into the parameters' existing ``.grad`` buffers, so every pointer is
+    the same from one training step to the next and both directions replay as CUDA graphs.  Plain: fresh tape, fresh
+    gradient tensors handed back to autograd."""
 
     @staticmethod
     def forward(ctx, native, x, temb, text_emb, uncond, *params):
         eng = native.mst_engine(x.device, precision=native.mst_train_prec())
+        slot = native._mst_tape_acquire(eng, x.shape[0], x.shape[-1], text_emb is not None)
+        ctx.native, ctx.eng, ctx.slot = native, eng, slot
+        if slot is not None:
+            slot.x.copy_(x)
+            slot.temb.copy_(temb)
+            if text_emb is not None:
+                slot.text.copy_(text_emb)
+            eng.forward_train(slot.x, slot.temb, slot.text if text_emb is not None else None, uncond=uncond,
+                              tape=slot.tape, out=slot.out, use_graph=True)
+            ctx.tape, ctx.epoch = slot.tape, slot.epoch
+            return slot.out.clone()
         out, tape = eng.forward_train(x, temb, text_emb, uncond=uncond)
-        ctx.native, ctx.eng, ctx.tape = native, eng, tape
+        ctx.tape = tape
         return out
 
     @staticmethod
@@ -168,6 +184,20 @@ class _DenoiserGradFn(torch.autograd.Function):
         layers = [l.mst_tensors() for l in ctx.native._mst_encoder().layers]
         flat = [p for lp in layers for p in lp.values()]
         needs = {id(p): bool(ctx.needs_input_grad[5 + i]) for i, p in enumerate(flat)}
+        slot = ctx.slot
+        if slot is not None:
+            if slot.epoch != ctx.epoch:
+                raise RuntimeError("this forward's pooled activation tape was recycled by a later training step "
+                                   "(call backward() before the next zero_grad(), or disable the pool)")
+            direct = all((not needs[id(p)]) or (p.grad is not None and p.grad.is_contiguous() and
+                                                 p.grad.dtype == torch.float32) for p in flat)
+            if direct and not ctx.needs_input_grad[1]:
+                # accumulate straight into .grad (what autograd's AccumulateGrad would do with a returned tensor)
+                grads = [{k: (p.grad if needs[id(p)] else None) for k, p in lp.items()} for lp in layers]
+                slot.d_out.copy_(d_out)
+                ctx.eng.backward(slot.d_out, slot.tape, grads, want_dx=False, use_graph=True)
+                ctx.tape = None
+                return (None,) * (5 + len(flat))
         grads = _flat_layer_grads(layers, needs)
         d_x = ctx.eng.backward(d_out.float().contiguous(), ctx.tape, grads, want_dx=bool(ctx.needs_input_grad[1]))
         ctx.tape = None
@@ -252,6 +282,29 @@ class NativeDenoiser(nn.Module):
             raise RuntimeError(f"model parameters are on {p.device} but the input is on {x.device}: move the model "
                                "to the CUDA device first (there is no CPU fallback)")
         return True
+
+    # -- pooled activation tapes (CUDA-graph replay of the training forward / backward) ------------------------
+    mst_tape_pool = False   # switched on by the trainer (MixedPrecisionTrainer); MST_TRAIN_GRAPH=0 disables replay
+
+    def mst_tape_reset(self):
+        """Start of a training step: every pooled slot may be handed out again, in the same order as last step."""
+        for ent in self.__dict__.get("_mst_tape_slots", {}).values():
+            ent[1] = 0
+
+    def _mst_tape_acquire(self, eng, B, T, has_text):
+        if not self.mst_tape_pool:
+            return None
+        pools = self.__dict__.setdefault("_mst_tape_slots", {})
+        ent = pools.setdefault((id(eng), B, T, has_text), [[], 0])
+        slots, nxt = ent
+        if nxt >= 16:       # more live forwards of one shape than a finetune step ever has: plain path
+            return None
+        if nxt == len(slots):
+            slots.append(TapeSlot(eng, B, T, has_text))
+        slot = slots[nxt]
+        ent[1] = nxt + 1
+        slot.epoch += 1
+        return slot
 
     def mst_weights_changed(self):
         """Call after parameters were updated behind torch's back (the fused optimizer writes through raw

@@ -186,6 +186,11 @@ typedef struct {
   float* out_uncond; /* [B, F, T] device, cfg==1                             */
   void* workspace;   /* device, >= mst_engine_workspace_bytes                */
   size_t workspace_bytes;
+  int32_t use_graph; /* mst_denoiser_forward_train only: 1 = the caller keeps
+                        every pointer of this call stable across calls, so
+                        the launch sequence may be captured into a CUDA
+                        graph once (keyed by the argument values) and
+                        replayed - ~150 launches become one              */
 } mst_forward_args;
 
 int mst_denoiser_forward(mst_engine_t e, const mst_forward_args* a, void* stream);
@@ -293,6 +298,8 @@ typedef struct {
   size_t tape_bytes;
   void* scratch;
   size_t scratch_bytes;
+  int32_t use_graph;        /* as in mst_forward_args: pointers (incl. the
+                               gradient buffers) are stable across calls    */
 } mst_backward_args;
 
 int mst_denoiser_backward(mst_engine_t e, const mst_backward_args* a, void* stream);
