@@ -30,7 +30,7 @@ EXPORTED = [
     "mst_text_embed", "mst_denoiser_forward", "mst_update_step", "mst_q_sample", "mst_cfg_combine",
     "mst_philox_normal", "mst_train_sizes", "mst_denoiser_forward_train", "mst_denoiser_backward", "mst_abi_sizes_train",
     "mst_motion_encoder_forward", "mst_motion_encoder_backward", "mst_masked_l2", "mst_update_step_backward",
-    "mst_adamw_step", "mst_sumsq2", "mst_recover_from_ric", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
+    "mst_adamw_step", "mst_sumsq2", "mst_recover_from_ric", "mst_test_dropout_scale", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
 ]
 
 
@@ -58,6 +58,7 @@ class ForwardArgs(C.Structure):
         ("x", C.c_void_p), ("temb", C.c_void_p), ("temb_row_dev", C.c_void_p), ("temb_row_offset", C.c_int32),
         ("text_emb", C.c_void_p), ("out_cond", C.c_void_p), ("out_uncond", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("use_graph", C.c_int32),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p),
     ]
 
 
@@ -86,6 +87,7 @@ class BackwardArgs(C.Structure):
         ("batch", C.c_int32), ("n_frames", C.c_int32), ("d_out", C.c_void_p), ("d_x", C.c_void_p),
         ("layer_grads", C.POINTER(LayerGrads)), ("tape", C.c_void_p), ("tape_bytes", C.c_size_t),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t), ("use_graph", C.c_int32),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p),
     ]
 
 
@@ -148,8 +150,9 @@ def _declare(lib):
         "mst_denoiser_forward_train": [vp, C.POINTER(ForwardArgs), vp, sz, vp],
         "mst_denoiser_backward": [vp, C.POINTER(BackwardArgs), vp],
         "mst_abi_sizes_train": [C.POINTER(sz), C.POINTER(sz)],
-        "mst_motion_encoder_forward": [vp, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp],
-        "mst_motion_encoder_backward": [vp, vp, i32, i32, vp, vp, sz, vp, sz, vp],
+        "mst_motion_encoder_forward": [vp, vp, vp, vp, vp, i32, i32, vp, vp, sz, C.c_float, vp, vp],
+        "mst_motion_encoder_backward": [vp, vp, i32, i32, vp, vp, sz, vp, sz, C.c_float, vp, vp],
+        "mst_test_dropout_scale": [vp, i64, C.c_float, vp, i32, vp],
         "mst_masked_l2": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "mst_update_step_backward": [vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp],
         "mst_adamw_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.c_float, vp],

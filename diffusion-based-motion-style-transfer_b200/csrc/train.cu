@@ -303,6 +303,71 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__
     dh[i] *= gelu_grad_f(u[i]);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Dropout of the training forward (nn.TransformerEncoderLayer(dropout=0.1) and PositionalEncoding(dropout=0.1) are
+// active once the reference calls model.train(), train/finetune_style_diffusion.py:256).  Counter-based: the keep /
+// drop decision of element i at site s is Philox4x32-10(key = *seed_dev, counter = (i / 4, site, 0, 0)) lane i % 4
+// < p, so the backward recomputes the mask instead of storing it, and a CUDA-graph replay picks up a new seed from
+// device memory.  Sites: 0 = token sequence after the positional encoding; 8 * (layer + 1) + {1: attention
+// probabilities, 2: out-proj output, 3: GELU output, 4: linear2 output}.
+// ---------------------------------------------------------------------------------------------------------
+struct Drop {
+  float p = 0.0f;                      // 0 = off
+  const unsigned long long* seed = nullptr;  // device
+  __host__ __device__ bool on() const { return p > 0.0f; }
+};
+
+__device__ __forceinline__ void philox4(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t (&o)[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint32_t x = c0, y = c1, z = 0u, w = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, x), lo0 = M0 * x, hi1 = __umulhi(M1, z), lo1 = M1 * z;
+    const uint32_t nx = hi1 ^ y ^ k0, nz = hi0 ^ w ^ k1;
+    x = nx; y = lo1; z = nz; w = lo0;
+    k0 += W0; k1 += W1;
+  }
+  o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+
+// scale factors (0 or 1/(1-p)) of elements [4v, 4v+3] of `site`
+__device__ __forceinline__ float4 drop_scale4(const Drop& d, uint32_t site, long long v) {
+  const unsigned long long seed = *d.seed;
+  uint32_t r[4];
+  philox4((uint32_t)v, site ^ ((uint32_t)(v >> 32) << 16), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const float keep = 1.0f / (1.0f - d.p);
+  const uint32_t thr = (uint32_t)(d.p * 4294967296.0);  // drop when r < thr
+  return make_float4(r[0] < thr ? 0.0f : keep, r[1] < thr ? 0.0f : keep, r[2] < thr ? 0.0f : keep, r[3] < thr ? 0.0f : keep);
+}
+
+// out[i] = in[i] * mask[i] (+ add[i]); n % 4 == 0, all pointers 16-byte aligned; in may alias out
+__global__ void __launch_bounds__(256) dropout_kernel(const float* in, const float* __restrict__ add, float* out, long long n4,
+                                                      Drop d, uint32_t site) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x) {
+    const float4 m = drop_scale4(d, site, v);
+    float4 x = reinterpret_cast<const float4*>(in)[v];
+    x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+    if (add) {
+      const float4 a = reinterpret_cast<const float4*>(add)[v];
+      x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+    }
+    reinterpret_cast<float4*>(out)[v] = x;
+  }
+}
+
+// du = dh * mask * gelu'(u), in place in dh
+__global__ void __launch_bounds__(256) gelu_bwd_drop_kernel(const float* __restrict__ u, float* __restrict__ dh, long long n4,
+                                                            Drop d, uint32_t site) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x) {
+    const float4 m = drop_scale4(d, site, v);
+    const float4 uu = reinterpret_cast<const float4*>(u)[v];
+    float4 g = reinterpret_cast<float4*>(dh)[v];
+    g.x *= m.x * gelu_grad_f(uu.x); g.y *= m.y * gelu_grad_f(uu.y);
+    g.z *= m.z * gelu_grad_f(uu.z); g.w *= m.w * gelu_grad_f(uu.w);
+    reinterpret_cast<float4*>(dh)[v] = g;
+  }
+}
+
 // LayerNorm backward over rows of width d (d % 32 == 0, d <= 1024): dz = rstd * (g - mean(g) - xhat * mean(g xhat)),
 // g = dy * gamma; dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (block partials, then atomics).
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
@@ -403,6 +468,14 @@ static int ew_blocks(long long n) {
   const long long cap = (long long)sm_count() * 16;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
+
+static int dropout(const float* in, const float* add, float* out, long long n, const Drop& d, uint32_t site, cudaStream_t s) {
+  if (n % 4 != 0) return fail(MST_ERR_UNSUPPORTED, "dropout: tensor sizes must be multiples of 4 (pad the sequence)");
+  dropout_kernel<<<ew_blocks(n / 4), 256, 0, s>>>(in, add, out, n / 4, d, site);
+  MST_LAUNCHED("dropout", s);
+  return MST_OK;
+}
+static inline uint32_t drop_site(int layer, int which) { return (uint32_t)(8 * (layer + 1) + which); }
 
 // MotionEncoder tokens: rows 0 / 1 of every sequence = muQuery / sigmaQuery + pe[row]; rows >= 2 (already holding
 // InputProcess(x)) += pe[row]
@@ -524,7 +597,7 @@ static void layer_lins(Engine* e, int l, Lin* qkv, Lin* o, Lin* f1, Lin* f2) {
 // tape: everything the backward needs, per layer
 // ---------------------------------------------------------------------------------------------------------
 struct LayerTape {
-  float *x, *qkv, *p, *ao, *z1, *y, *u, *h, *z2;
+  float *x, *qkv, *p, *pd, *ao, *z1, *y, *u, *h, *z2;  // pd: attention probabilities after dropout (= p when dropout is off)
 };
 struct Tape {
   LayerTape l[MST_MAX_LAYERS];
@@ -549,6 +622,7 @@ static size_t carve_tape(const mst_model_desc& d, int n_seqs, int S, void* base,
     L.x = x;
     L.qkv = take(M * 3 * dm);
     L.p = take(pp);
+    L.pd = take(pp);
     L.ao = take(M * dm);
     L.z1 = take(M * dm);
     L.y = take(M * dm);
@@ -568,7 +642,8 @@ static size_t carve_tape(const mst_model_desc& d, int n_seqs, int S, void* base,
   return align_up(off, 256);
 }
 
-static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const uint8_t* key_valid, cudaStream_t s) {
+static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const uint8_t* key_valid, const Drop& drop,
+                                cudaStream_t s) {
   const mst_model_desc& d = e->desc;
   const int M = NS * S, dm = d.d_model, H = d.n_heads, dh = dm / H, ff = d.d_ff;
   const float scale = 1.0f / sqrtf((float)dh);
@@ -590,17 +665,33 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
     const long long rows = (long long)NS * H * S;
     softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, key_valid, rows, S, H * S);
     MST_LAUNCHED("train_softmax", s);
+    const float* probs = t.p;
+    if (drop.on()) {
+      if ((rc = dropout(t.p, nullptr, t.pd, rows * S, drop, drop_site(l, 1), s))) return rc;
+      probs = t.pd;
+    }
     GemmEx pv;  // ao = P V
-    pv.a = t.p; pv.lda = S; pv.b = t.qkv + 2 * dm; pv.ldb = 3 * dm; pv.c = t.ao; pv.ldc = dm;
+    pv.a = probs; pv.lda = S; pv.b = t.qkv + 2 * dm; pv.ldb = 3 * dm; pv.c = t.ao; pv.ldc = dm;
     pv.M = S; pv.N = dh; pv.K = S; pv.batch = NS; pv.heads = H;
     pv.a_bs = sc.c_bs; pv.a_hs = sc.c_hs; pv.b_bs = sc.a_bs; pv.b_hs = dh; pv.c_bs = (long long)S * dm; pv.c_hs = dh;
     if ((rc = gemm_ex(pv, s, "train_pv"))) return rc;
-    if ((rc = linear_fwd(tc, tp.stage, t.ao, lo, L.o_b, t.x, t.z1, M, s, "train_outproj"))) return rc;
+    if (drop.on()) {  // z1 = x + dropout1(ao Wo^T + bo)
+      if ((rc = linear_fwd(tc, tp.stage, t.ao, lo, L.o_b, nullptr, t.z1, M, s, "train_outproj"))) return rc;
+      if ((rc = dropout(t.z1, t.x, t.z1, (long long)M * dm, drop, drop_site(l, 2), s))) return rc;
+    } else if ((rc = linear_fwd(tc, tp.stage, t.ao, lo, L.o_b, t.x, t.z1, M, s, "train_outproj"))) {
+      return rc;
+    }
     if ((rc = layernorm_f32(t.z1, L.ln1_g, L.ln1_b, t.y, M, dm, s))) return rc;
     if ((rc = linear_fwd(tc, tp.stage, t.y, lf1, L.b1, nullptr, t.u, M, s, "train_ffn1"))) return rc;
     gelu_fwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, t.h, (long long)M * ff);
     MST_LAUNCHED("train_gelu", s);
-    if ((rc = linear_fwd(tc, tp.stage, t.h, lf2, L.b2, t.y, t.z2, M, s, "train_ffn2"))) return rc;
+    if (drop.on()) {  // h = dropout(gelu(u)); z2 = y + dropout2(h W2^T + b2)
+      if ((rc = dropout(t.h, nullptr, t.h, (long long)M * ff, drop, drop_site(l, 3), s))) return rc;
+      if ((rc = linear_fwd(tc, tp.stage, t.h, lf2, L.b2, nullptr, t.z2, M, s, "train_ffn2"))) return rc;
+      if ((rc = dropout(t.z2, t.y, t.z2, (long long)M * dm, drop, drop_site(l, 4), s))) return rc;
+    } else if ((rc = linear_fwd(tc, tp.stage, t.h, lf2, L.b2, t.y, t.z2, M, s, "train_ffn2"))) {
+      return rc;
+    }
     if ((rc = layernorm_f32(t.z2, L.ln2_g, L.ln2_b, x_next, M, dm, s))) return rc;
   }
   return MST_OK;
@@ -609,7 +700,7 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
 // Backward of the encoder stack.  g_out [M, d]: gradient w.r.t. the stack's output, overwritten with scratch;
 // on return `g_x` [M, d] holds the gradient w.r.t. the stack's input.  Parameter gradients are ACCUMULATED.
 struct BwdScratch {
-  float *ga, *gb, *dqkv, *dp, *dh;  // [M,d] x2, [M,3d], [NS*H*S*S], [M,ff]
+  float *ga, *gb, *gm, *dqkv, *dp, *dh;  // [M,d] x3 (gm: dropout-masked gradient), [M,3d], [NS*H*S*S], [M,ff]
   Stage stage;
 };
 
@@ -625,6 +716,7 @@ static size_t carve_bwd(const mst_model_desc& d, int n_seqs, int S, void* base, 
   BwdScratch b;
   b.ga = take(M * dm);
   b.gb = take(M * dm);
+  b.gm = take(M * dm);
   b.dqkv = take(M * 3 * dm);
   b.dp = take((size_t)n_seqs * d.n_heads * S * S);
   b.dh = take(M * d.d_ff);
@@ -639,7 +731,7 @@ static size_t carve_bwd(const mst_model_desc& d, int n_seqs, int S, void* base, 
 }
 
 static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* grads, int NS, int S, float* g_in_out,
-                            const BwdScratch& w, float** g_x, cudaStream_t s) {
+                            const BwdScratch& w, float** g_x, const Drop& drop, cudaStream_t s) {
   const mst_model_desc& d = e->desc;
   const int M = NS * S, dm = d.d_model, H = d.n_heads, dh = dm / H, ff = d.d_ff;
   const float scale = 1.0f / sqrtf((float)dh);
@@ -659,9 +751,17 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     float* dz2 = spare;
     layernorm_bwd_kernel<<<ln_blocks, 256, 0, s>>>(gx, t.z2, L.ln2_g, dz2, G.ln2_g, G.ln2_b, M, dm);
     MST_LAUNCHED("bwd_ln2", s);
-    // FFN2: dh = dz2 W2, dW2 += dz2^T h, db2 += sum dz2
-    if ((rc = linear_bwd(tc, w.stage, dz2, t.h, lf2, nullptr, w.dh, G.w2, G.b2, M, s, "bwd_dh", "bwd_dw2"))) return rc;
-    gelu_bwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, w.dh, (long long)M * ff);
+    // FFN2: dh = dz2 W2, dW2 += dz2^T h, db2 += sum dz2   (dropout2: the GEMM path sees the masked gradient)
+    const float* dz2g = dz2;
+    if (drop.on()) {
+      if ((rc = dropout(dz2, nullptr, w.gm, (long long)M * dm, drop, drop_site(l, 4), s))) return rc;
+      dz2g = w.gm;
+    }
+    if ((rc = linear_bwd(tc, w.stage, dz2g, t.h, lf2, nullptr, w.dh, G.w2, G.b2, M, s, "bwd_dh", "bwd_dw2"))) return rc;
+    if (drop.on())
+      gelu_bwd_drop_kernel<<<ew_blocks((long long)M * ff / 4), 256, 0, s>>>(t.u, w.dh, (long long)M * ff / 4, drop, drop_site(l, 3));
+    else
+      gelu_bwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, w.dh, (long long)M * ff);
     MST_LAUNCHED("bwd_gelu", s);
     // FFN1: dy = dz2 + du W1 (into gx: the incoming gradient is no longer needed), dW1 += du^T y, db1 += sum du
     if ((rc = linear_bwd(tc, w.stage, w.dh, t.y, lf1, dz2, gx, G.w1, G.b1, M, s, "bwd_dy", "bwd_dw1"))) return rc;
@@ -669,8 +769,13 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     float* dz1 = spare;  // dz2 is dead
     layernorm_bwd_kernel<<<ln_blocks, 256, 0, s>>>(gx, t.z1, L.ln1_g, dz1, G.ln1_g, G.ln1_b, M, dm);
     MST_LAUNCHED("bwd_ln1", s);
-    float* dao = spare2;  // out-proj: dao = dz1 Wo, dWo += dz1^T ao, dbo += sum dz1
-    if ((rc = linear_bwd(tc, w.stage, dz1, t.ao, lo, nullptr, dao, G.o_w, G.o_b, M, s, "bwd_dao", "bwd_dwo"))) return rc;
+    float* dao = spare2;  // out-proj: dao = dz1 Wo, dWo += dz1^T ao, dbo += sum dz1   (dropout1: masked gradient)
+    const float* dz1g = dz1;
+    if (drop.on()) {
+      if ((rc = dropout(dz1, nullptr, w.gm, (long long)M * dm, drop, drop_site(l, 2), s))) return rc;
+      dz1g = w.gm;
+    }
+    if ((rc = linear_bwd(tc, w.stage, dz1g, t.ao, lo, nullptr, dao, G.o_w, G.o_b, M, s, "bwd_dao", "bwd_dwo"))) return rc;
     // attention
     const long long qkv_bs = (long long)S * 3 * dm, pp_bs = (long long)H * S * S, pp_hs = (long long)S * S;
     GemmEx dp;  // dP = dao V^T
@@ -678,12 +783,13 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     dp.M = S; dp.N = S; dp.K = dh; dp.batch = NS; dp.heads = H;
     dp.a_bs = (long long)S * dm; dp.a_hs = dh; dp.b_bs = qkv_bs; dp.b_hs = dh; dp.c_bs = pp_bs; dp.c_hs = pp_hs;
     if ((rc = gemm_ex(dp, s, "bwd_dp"))) return rc;
-    GemmEx dv;  // dV = P^T dao
-    dv.a = t.p; dv.lda = S; dv.a_mode = AX_TRANS; dv.b = dao; dv.ldb = dm; dv.c = w.dqkv + 2 * dm; dv.ldc = 3 * dm;
+    GemmEx dv;  // dV = P^T dao   (the probabilities the forward multiplied with: after dropout)
+    dv.a = drop.on() ? t.pd : t.p; dv.lda = S; dv.a_mode = AX_TRANS; dv.b = dao; dv.ldb = dm; dv.c = w.dqkv + 2 * dm; dv.ldc = 3 * dm;
     dv.M = S; dv.N = dh; dv.K = S; dv.batch = NS; dv.heads = H;
     dv.a_bs = pp_bs; dv.a_hs = pp_hs; dv.b_bs = (long long)S * dm; dv.b_hs = dh; dv.c_bs = qkv_bs; dv.c_hs = dh;
     if ((rc = gemm_ex(dv, s, "bwd_dv"))) return rc;
     const long long rows = (long long)NS * H * S;
+    if (drop.on() && (rc = dropout(w.dp, nullptr, w.dp, rows * S, drop, drop_site(l, 1), s))) return rc;
     softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, w.dp, rows, S);
     MST_LAUNCHED("bwd_softmax", s);
     GemmEx dq;  // dQ = scale dS K
@@ -941,6 +1047,10 @@ extern "C" int mst_denoiser_forward_train(mst_engine_t h, const mst_forward_args
   const int B = a.batch, T = a.n_frames, S = T + 1, dm = d.d_model;
   Tape tp;
   MST_CHECK_ARG(tape_bytes >= carve_tape(d, B, S, tape, &tp), "tape too small");
+  MST_CHECK_ARG(a.dropout_p >= 0.0f && a.dropout_p < 1.0f && (a.dropout_p == 0.0f || a.dropout_seed), "bad dropout arguments");
+  Drop drop;
+  drop.p = a.dropout_p;
+  drop.seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
   uint64_t key = fnv1a(&a, sizeof(a), 1469598103934665603ull);
   key = fnv1a(e, sizeof(Engine), key);
   key = fnv1a(&tape, sizeof(tape), key) ^ 0x66ull;
@@ -958,7 +1068,8 @@ extern "C" int mst_denoiser_forward_train(mst_engine_t h, const mst_forward_args
       p.pe = e->pe; p.B = B; p.T = T; p.n_pass = 1;
       if ((rc = gemm_f32(p, s))) return rc;
     }
-    if ((rc = encoder_forward_tape(e, tp, B, S, nullptr, s))) return rc;
+    if (drop.on() && (rc = dropout(tp.l[0].x, nullptr, tp.l[0].x, (long long)B * S * dm, drop, 0, s))) return rc;
+    if ((rc = encoder_forward_tape(e, tp, B, S, nullptr, drop, s))) return rc;
     {
       GemmF32Params p;
       p.a = tp.x_out; p.lda = dm; p.w = e->out_w; p.ldw = dm; p.bias = e->out_b;
@@ -983,9 +1094,15 @@ extern "C" int mst_denoiser_backward(mst_engine_t h, const mst_backward_args* ap
   BwdScratch w;
   MST_CHECK_ARG(a.tape_bytes >= carve_tape(d, B, S, const_cast<void*>(a.tape), &tp), "tape too small");
   MST_CHECK_ARG(a.scratch_bytes >= carve_bwd(d, B, S, a.scratch, &w), "scratch too small");
+  MST_CHECK_ARG(a.dropout_p >= 0.0f && a.dropout_p < 1.0f && (a.dropout_p == 0.0f || a.dropout_seed), "bad dropout arguments");
+  Drop drop;
+  drop.p = a.dropout_p;
+  drop.seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
   // key: every device pointer / size of the call (not the host address of the layer_grads array, its contents)
-  const void* kp[] = {a.d_out, a.d_x, a.tape, a.scratch};
-  const size_t kn[] = {(size_t)a.batch, (size_t)a.n_frames, a.tape_bytes, a.scratch_bytes};
+  const void* kp[] = {a.d_out, a.d_x, a.tape, a.scratch, a.dropout_seed};
+  uint32_t pbits;
+  memcpy(&pbits, &a.dropout_p, 4);
+  const size_t kn[] = {(size_t)a.batch, (size_t)a.n_frames, a.tape_bytes, a.scratch_bytes, (size_t)pbits};
   uint64_t key = fnv1a(kp, sizeof(kp), 1469598103934665603ull);
   key = fnv1a(kn, sizeof(kn), key);
   key = fnv1a(e, sizeof(Engine), key);
@@ -1000,8 +1117,9 @@ extern "C" int mst_denoiser_backward(mst_engine_t h, const mst_backward_args* ap
     go.M = M; go.N = dm; go.K = d.n_feats;
     if ((rc = gemm_ex(go, s, "bwd_outproj"))) return rc;
     float* gx = nullptr;
-    if ((rc = encoder_backward(e, tp, a.layer_grads, B, S, g, w, &gx, s))) return rc;
+    if ((rc = encoder_backward(e, tp, a.layer_grads, B, S, g, w, &gx, drop, s))) return rc;
     if (a.d_x) {  // InputProcess backward: d_x[b][f][t] = sum_n gx[(b,t+1)][n] in_w[n][f]
+      if (drop.on() && (rc = dropout(gx, nullptr, gx, (long long)M * dm, drop, 0, s))) return rc;
       GemmEx gi;
       gi.a = gx; gi.lda = dm; gi.a_mode = AX_TOKROWS; gi.T = T; gi.tok_off = 1; gi.b = e->in_w; gi.ldb = d.n_feats;
       gi.c = a.d_x; gi.c_mode = CX_MOTION; gi.M = B * T; gi.N = d.n_feats; gi.K = dm;
@@ -1016,7 +1134,12 @@ extern "C" int mst_denoiser_backward(mst_engine_t h, const mst_backward_args* ap
 // in_b / pe are the frozen mdm_model's (the Python layer loads them so).
 extern "C" int mst_motion_encoder_forward(mst_engine_t h, const float* x, const uint8_t* key_valid, const float* mu_query,
                                           const float* sigma_query, int32_t batch, int32_t n_frames, float* mu_out,
-                                          void* tape, size_t tape_bytes, void* stream) {
+                                          void* tape, size_t tape_bytes, float dropout_p, const uint64_t* dropout_seed,
+                                          void* stream) {
+  MST_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f && (dropout_p == 0.0f || dropout_seed), "bad dropout arguments");
+  Drop drop;
+  drop.p = dropout_p;
+  drop.seed = reinterpret_cast<const unsigned long long*>(dropout_seed);
   MST_CHECK_ARG(h && x && mu_query && sigma_query && mu_out && tape, "null argument");
   Engine* e = reinterpret_cast<Engine*>(h);
   int rc;
@@ -1033,7 +1156,8 @@ extern "C" int mst_motion_encoder_forward(mst_engine_t h, const float* x, const 
   if ((rc = gemm_ex(g, s, "menc_inproj"))) return rc;
   menc_tokens_kernel<<<B * S, 128, 0, s>>>(mu_query, sigma_query, e->pe, tp.l[0].x, S, dm);
   MST_LAUNCHED("menc_tokens", s);
-  if ((rc = encoder_forward_tape(e, tp, B, S, key_valid, s))) return rc;
+  if (drop.on() && (rc = dropout(tp.l[0].x, nullptr, tp.l[0].x, (long long)B * S * dm, drop, 0, s))) return rc;
+  if ((rc = encoder_forward_tape(e, tp, B, S, key_valid, drop, s))) return rc;
   MST_CUDA_OK(cudaMemcpy2DAsync(mu_out, (size_t)dm * 4, tp.x_out, (size_t)S * dm * 4, (size_t)dm * 4, B,
                                 cudaMemcpyDeviceToDevice, s));
   return MST_OK;
@@ -1042,7 +1166,11 @@ extern "C" int mst_motion_encoder_forward(mst_engine_t h, const float* x, const 
 // d_x [B,F,T] = d mu / d x (all MotionEncoder parameters are frozen: the reference only needs the input gradient)
 extern "C" int mst_motion_encoder_backward(mst_engine_t h, const float* d_mu, int32_t batch, int32_t n_frames, float* d_x,
                                            void* tape, size_t tape_bytes, void* scratch, size_t scratch_bytes,
-                                           void* stream) {
+                                           float dropout_p, const uint64_t* dropout_seed, void* stream) {
+  MST_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f && (dropout_p == 0.0f || dropout_seed), "bad dropout arguments");
+  Drop drop;
+  drop.p = dropout_p;
+  drop.seed = reinterpret_cast<const unsigned long long*>(dropout_seed);
   MST_CHECK_ARG(h && d_mu && d_x && tape && scratch, "null argument");
   Engine* e = reinterpret_cast<Engine*>(h);
   int rc;
@@ -1059,11 +1187,27 @@ extern "C" int mst_motion_encoder_backward(mst_engine_t h, const float* d_mu, in
   MST_CUDA_OK(cudaMemcpy2DAsync(g, (size_t)S * dm * 4, d_mu, (size_t)dm * 4, (size_t)dm * 4, B, cudaMemcpyDeviceToDevice, s));
   static const mst_layer_grads kNoGrads[MST_MAX_LAYERS] = {};
   float* gx = nullptr;
-  if ((rc = encoder_backward(e, tp, kNoGrads, B, S, g, w, &gx, s))) return rc;
+  if ((rc = encoder_backward(e, tp, kNoGrads, B, S, g, w, &gx, drop, s))) return rc;
+  if (drop.on() && (rc = dropout(gx, nullptr, gx, (long long)B * S * dm, drop, 0, s))) return rc;
   GemmEx gi;
   gi.a = gx; gi.lda = dm; gi.a_mode = AX_TOKROWS; gi.T = T; gi.tok_off = 2; gi.b = e->in_w; gi.ldb = d.n_feats;
   gi.c = d_x; gi.c_mode = CX_MOTION; gi.M = B * T; gi.N = d.n_feats; gi.K = dm;
   return gemm_ex(gi, s, "menc_bwd_inproj");
+}
+
+__global__ void __launch_bounds__(256) dropout_scale_kernel(float* out, long long n4, mst::Drop d, uint32_t site) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(out)[v] = mst::drop_scale4(d, site, v);
+}
+
+extern "C" int mst_test_dropout_scale(float* out, int64_t n, float p, const uint64_t* seed_dev, int32_t site, void* stream) {
+  MST_CHECK_ARG(out && seed_dev && n > 0 && n % 4 == 0 && p > 0.0f && p < 1.0f, "bad argument");
+  Drop d;
+  d.p = p;
+  d.seed = reinterpret_cast<const unsigned long long*>(seed_dev);
+  dropout_scale_kernel<<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(out, n / 4, d, (uint32_t)site);
+  MST_LAUNCHED("dropout_scale", (cudaStream_t)stream);
+  return MST_OK;
 }
 
 extern "C" int mst_masked_l2(const float* a, const float* b, const float* mask, float* loss, const float* grad_loss,

@@ -180,7 +180,7 @@ class Engine:
 
     def forward_train(self, x: torch.Tensor, temb: torch.Tensor, text_emb: Optional[torch.Tensor], *,
                       uncond: bool = False, tape: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                      use_graph: bool = False):
+                      use_graph: bool = False, dropout_p: float = 0.0, dropout_seed: Optional[torch.Tensor] = None):
         """Denoiser forward that records the activation tape.  Returns (out [B,F,1,T], tape).
         use_graph=True promises that x / temb / text_emb / out / tape are the same buffers on every call with this
         shape (a TapeSlot): the launch sequence is then captured once and replayed as a CUDA graph."""
@@ -194,6 +194,8 @@ class Engine:
             out = torch.empty_like(x)
         a = L.ForwardArgs()
         a.use_graph = int(bool(use_graph))
+        a.dropout_p = float(dropout_p)
+        a.dropout_seed = _ptr(dropout_seed, torch.int64, "dropout_seed") if dropout_p > 0 else None
         a.batch, a.n_frames, a.cfg, a.uncond = B, T, 0, int(uncond)
         a.x = _ptr(x, name="x")
         a.temb = _ptr(temb, name="temb")
@@ -206,7 +208,7 @@ class Engine:
         return out, tape
 
     def backward(self, d_out: torch.Tensor, tape: torch.Tensor, layer_grads: list, want_dx: bool = False,
-                 use_graph: bool = False):
+                 use_graph: bool = False, dropout_p: float = 0.0, dropout_seed: Optional[torch.Tensor] = None):
         """Back-propagate d_out [B,F,1,T] through the taped forward.  layer_grads: per layer a dict keyed by LAYER_KEYS
         of fp32 CUDA tensors (or None) that the gradients are ACCUMULATED into.  Returns d_x or None."""
         B, T = d_out.shape[0], d_out.shape[-1]
@@ -222,6 +224,8 @@ class Engine:
         d_x = torch.empty_like(d_out) if want_dx else None
         a = L.BackwardArgs()
         a.use_graph = int(bool(use_graph))
+        a.dropout_p = float(dropout_p)
+        a.dropout_seed = _ptr(dropout_seed, torch.int64, "dropout_seed") if dropout_p > 0 else None
         a.batch, a.n_frames = B, T
         a.d_out, a.d_x = _ptr(d_out, name="d_out"), _ptr(d_x, name="d_x")
         a.layer_grads = arr
@@ -231,7 +235,8 @@ class Engine:
         return d_x
 
     def motion_encoder_forward(self, x: torch.Tensor, key_valid: Optional[torch.Tensor], mu_query: torch.Tensor,
-                               sigma_query: torch.Tensor):
+                               sigma_query: torch.Tensor, dropout_p: float = 0.0,
+                               dropout_seed: Optional[torch.Tensor] = None):
         """MotionEncoder.forward on this engine's stack.  Returns (mu [B,d], tape)."""
         B, T = x.shape[0], x.shape[-1]
         tape_bytes, _ = self.train_sizes(B, T + 2)
@@ -239,18 +244,21 @@ class Engine:
         mu = torch.empty(B, self.d_model, dtype=torch.float32, device=self.device)
         L.check(self.lib.mst_motion_encoder_forward(
             self._h, _ptr(x, name="x"), _ptr(key_valid, torch.uint8, "key_valid"), _ptr(mu_query, name="muQuery"),
-            _ptr(sigma_query, name="sigmaQuery"), B, T, mu.data_ptr(), tape.data_ptr(), tape.numel(), _stream_ptr()),
+            _ptr(sigma_query, name="sigmaQuery"), B, T, mu.data_ptr(), tape.data_ptr(), tape.numel(), float(dropout_p),
+            _ptr(dropout_seed, torch.int64, "dropout_seed") if dropout_p > 0 else None, _stream_ptr()),
             "mst_motion_encoder_forward")
         return mu, tape
 
-    def motion_encoder_backward(self, d_mu: torch.Tensor, tape: torch.Tensor, shape):
+    def motion_encoder_backward(self, d_mu: torch.Tensor, tape: torch.Tensor, shape, dropout_p: float = 0.0,
+                                dropout_seed: Optional[torch.Tensor] = None):
         B, T = shape[0], shape[-1]
         _, scratch_bytes = self.train_sizes(B, T + 2)
         scratch = self._scratch(scratch_bytes)
         d_x = torch.empty(shape, dtype=torch.float32, device=self.device)
         L.check(self.lib.mst_motion_encoder_backward(
             self._h, _ptr(d_mu, name="d_mu"), B, T, d_x.data_ptr(), tape.data_ptr(), tape.numel(), scratch.data_ptr(),
-            scratch.numel(), _stream_ptr()), "mst_motion_encoder_backward")
+            scratch.numel(), float(dropout_p), _ptr(dropout_seed, torch.int64, "dropout_seed") if dropout_p > 0 else None,
+            _stream_ptr()), "mst_motion_encoder_backward")
         return d_x
 
 
@@ -267,6 +275,7 @@ class TapeSlot:
         self.text = torch.empty(B, eng.d_model, dtype=f32, device=dev) if has_text else None
         self.out = torch.empty(B, eng.n_feats, 1, T, dtype=f32, device=dev)
         self.d_out = torch.empty(B, eng.n_feats, 1, T, dtype=f32, device=dev)
+        self.seed = torch.zeros(1, dtype=torch.int64, device=dev)   # Philox key of this forward's dropout masks
         self.epoch = 0  # bumped every time the slot is handed out: a stale autograd node can tell its tape is gone
 
 
@@ -309,6 +318,14 @@ def recover_from_ric(x, joints_num, mean=None, std=None):
     out = torch.empty(B, 1, T, joints_num, 3, dtype=torch.float32, device=x.device)
     L.check(L.load().mst_recover_from_ric(_ptr(x, name="x"), _ptr(mean, name="mean"), _ptr(std, name="std"), out.data_ptr(),
                                           B, F, T, int(joints_num), _stream_ptr()), "mst_recover_from_ric")
+    return out
+
+
+def dropout_scale(n, p, seed, site):
+    """Test hook: the 0 / 1/(1-p) multipliers of dropout site ``site`` for the key in ``seed`` (int64 [1] device)."""
+    out = torch.empty(n, dtype=torch.float32, device=seed.device)
+    L.check(L.load().mst_test_dropout_scale(out.data_ptr(), n, float(p), _ptr(seed, torch.int64, "seed"), int(site),
+                                            _stream_ptr()), "mst_test_dropout_scale")
     return out
 
 

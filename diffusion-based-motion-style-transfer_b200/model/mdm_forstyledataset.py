@@ -163,16 +163,22 @@ class _DenoiserGradFn(torch.autograd.Function):
         eng = native.mst_engine(x.device, precision=native.mst_train_prec())
         slot = native._mst_tape_acquire(eng, x.shape[0], x.shape[-1], text_emb is not None)
         ctx.native, ctx.eng, ctx.slot = native, eng, slot
+        p = ctx.drop_p = native.mst_dropout_p()
+        key = native.mst_draw_dropout_key() if p > 0 else 0
         if slot is not None:
             slot.x.copy_(x)
             slot.temb.copy_(temb)
             if text_emb is not None:
                 slot.text.copy_(text_emb)
+            if p > 0:
+                slot.seed.fill_(key)
+            ctx.drop_seed = slot.seed
             eng.forward_train(slot.x, slot.temb, slot.text if text_emb is not None else None, uncond=uncond,
-                              tape=slot.tape, out=slot.out, use_graph=True)
+                              tape=slot.tape, out=slot.out, use_graph=True, dropout_p=p, dropout_seed=slot.seed)
             ctx.tape, ctx.epoch = slot.tape, slot.epoch
             return slot.out.clone()
-        out, tape = eng.forward_train(x, temb, text_emb, uncond=uncond)
+        ctx.drop_seed = torch.full((1,), key, dtype=torch.int64, device=x.device) if p > 0 else None
+        out, tape = eng.forward_train(x, temb, text_emb, uncond=uncond, dropout_p=p, dropout_seed=ctx.drop_seed)
         ctx.tape = tape
         return out
 
@@ -195,11 +201,13 @@ class _DenoiserGradFn(torch.autograd.Function):
                 # accumulate straight into .grad (what autograd's AccumulateGrad would do with a returned tensor)
                 grads = [{k: (p.grad if needs[id(p)] else None) for k, p in lp.items()} for lp in layers]
                 slot.d_out.copy_(d_out)
-                ctx.eng.backward(slot.d_out, slot.tape, grads, want_dx=False, use_graph=True)
+                ctx.eng.backward(slot.d_out, slot.tape, grads, want_dx=False, use_graph=True, dropout_p=ctx.drop_p,
+                                 dropout_seed=ctx.drop_seed)
                 ctx.tape = None
                 return (None,) * (5 + len(flat))
         grads = _flat_layer_grads(layers, needs)
-        d_x = ctx.eng.backward(d_out.float().contiguous(), ctx.tape, grads, want_dx=bool(ctx.needs_input_grad[1]))
+        d_x = ctx.eng.backward(d_out.float().contiguous(), ctx.tape, grads, want_dx=bool(ctx.needs_input_grad[1]),
+                               dropout_p=ctx.drop_p, dropout_seed=ctx.drop_seed)
         ctx.tape = None
         return (None, d_x, None, None, None) + tuple(g for lg in grads for g in lg.values())
 
@@ -210,8 +218,11 @@ class _MotionEncoderGradFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc, x, key_valid):
         eng = enc.mst_engine(x.device, precision=enc.mst_train_prec())
+        p = ctx.drop_p = enc.mst_dropout_p()
+        ctx.drop_seed = torch.full((1,), enc.mst_draw_dropout_key(), dtype=torch.int64, device=x.device) if p > 0 else None
         mu, tape = eng.motion_encoder_forward(x, key_valid, enc.muQuery.detach().reshape(-1).contiguous(),
-                                              enc.sigmaQuery.detach().reshape(-1).contiguous())
+                                              enc.sigmaQuery.detach().reshape(-1).contiguous(), dropout_p=p,
+                                              dropout_seed=ctx.drop_seed)
         ctx.eng, ctx.tape, ctx.shape = eng, tape, tuple(x.shape)
         return mu
 
@@ -219,8 +230,8 @@ class _MotionEncoderGradFn(torch.autograd.Function):
     def backward(ctx, d_mu):
         if ctx.tape is None:
             raise RuntimeError("the mst activation tape of this forward was already consumed by a backward pass")
-        d_x = ctx.eng.motion_encoder_backward(d_mu.float().contiguous(), ctx.tape, ctx.shape) \
-            if ctx.needs_input_grad[1] else None
+        d_x = ctx.eng.motion_encoder_backward(d_mu.float().contiguous(), ctx.tape, ctx.shape, dropout_p=ctx.drop_p,
+                                              dropout_seed=ctx.drop_seed) if ctx.needs_input_grad[1] else None
         ctx.tape = None
         return None, d_x, None
 
@@ -282,6 +293,22 @@ class NativeDenoiser(nn.Module):
             raise RuntimeError(f"model parameters are on {p.device} but the input is on {x.device}: move the model "
                                "to the CUDA device first (there is no CPU fallback)")
         return True
+
+    # -- dropout of the training forward ---------------------------------------------------------------------
+    # nn.TransformerEncoderLayer(dropout=p) and PositionalEncoding(dropout=p) are active in the reference as soon as
+    # model.train() was called (train/finetune_style_diffusion.py:256).  None -> follow self.training like torch does;
+    # a float forces that probability (0.0 = deterministic gradients, what the parity fixtures pin).
+    mst_train_dropout = None
+
+    def mst_dropout_p(self) -> float:
+        if self.mst_train_dropout is not None:
+            return float(self.mst_train_dropout)
+        return float(getattr(self, "dropout", 0.0)) if self.training else 0.0
+
+    @staticmethod
+    def mst_draw_dropout_key() -> int:
+        """Philox key of one forward's masks, drawn from torch's CPU generator (so torch.manual_seed controls it)."""
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
 
     # -- pooled activation tapes (CUDA-graph replay of the training forward / backward) ------------------------
     mst_tape_pool = False   # switched on by the trainer (MixedPrecisionTrainer); MST_TRAIN_GRAPH=0 disables replay
@@ -546,6 +573,7 @@ class MotionEncoder(NativeDenoiser):
         self.njoints, self.nfeats = njoints, nfeats
         self.input_feats = njoints * nfeats
         self.clip_dim = clip_dim
+        self.dropout = dropout
         self.cond_mode = kargs.get('cond_mode', 'no_cond')
         self.dataset = dataset
         self.cond_mask_prob = kargs.get('cond_mask_prob', 0.)

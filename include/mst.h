@@ -191,6 +191,13 @@ typedef struct {
                         the launch sequence may be captured into a CUDA
                         graph once (keyed by the argument values) and
                         replayed - ~150 launches become one              */
+  float dropout_p;   /* mst_denoiser_forward_train only: p of the dropouts of
+                        nn.TransformerEncoderLayer / PositionalEncoding (0.1
+                        in the reference once model.train() was called); 0 =
+                        identity (eval mode)                              */
+  const uint64_t* dropout_seed; /* device scalar: Philox key of this forward's
+                        masks (read by the kernels, so a graph replay sees
+                        a new value); the backward must get the same      */
 } mst_forward_args;
 
 int mst_denoiser_forward(mst_engine_t e, const mst_forward_args* a, void* stream);
@@ -300,6 +307,8 @@ typedef struct {
   size_t scratch_bytes;
   int32_t use_graph;        /* as in mst_forward_args: pointers (incl. the
                                gradient buffers) are stable across calls    */
+  float dropout_p;          /* the forward's values: the masks are          */
+  const uint64_t* dropout_seed; /* recomputed, not stored                   */
 } mst_backward_args;
 
 int mst_denoiser_backward(mst_engine_t e, const mst_backward_args* a, void* stream);
@@ -315,9 +324,15 @@ int mst_abi_sizes_train(size_t* layer_grads, size_t* backward_args);
  * parameter is frozen in the finetune loss.                                 */
 int mst_motion_encoder_forward(mst_engine_t e, const float* x, const uint8_t* key_valid, const float* mu_query,
                                const float* sigma_query, int32_t batch, int32_t n_frames, float* mu_out, void* tape,
-                               size_t tape_bytes, void* stream);
+                               size_t tape_bytes, float dropout_p, const uint64_t* dropout_seed, void* stream);
 int mst_motion_encoder_backward(mst_engine_t e, const float* d_mu, int32_t batch, int32_t n_frames, float* d_x,
-                                void* tape, size_t tape_bytes, void* scratch, size_t scratch_bytes, void* stream);
+                                void* tape, size_t tape_bytes, void* scratch, size_t scratch_bytes, float dropout_p,
+                                const uint64_t* dropout_seed, void* stream);
+
+/* Test hook: the multiplier (0 or 1/(1-p)) the training kernels apply to element i of dropout site `site`
+ * (0 = token sequence after the positional encoding; 8*(layer+1) + {1: attention probabilities [seq][head][q][k],
+ * 2: out-proj output, 3: GELU output, 4: linear2 output}, token-major [seq][token][column]).  n % 4 == 0.       */
+int mst_test_dropout_scale(float* out, int64_t n, float p, const uint64_t* seed_dev, int32_t site, void* stream);
 
 /* masked_l2 (diffusion/gaussian_diffusion.py:223-235) over `rows` rows of
  * b [rows,F,T]; a ([a_rows,F,T]) and mask ([mask_rows,T]) rows are taken

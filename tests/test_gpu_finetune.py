@@ -339,3 +339,101 @@ def test_bf16_finetune_loss_close_to_reference(mu, FI, gold, tmp_path_factory):
     got = np.sqrt(sum(float(params[str(n)].grad.double().pow(2).sum()) for n in gold["param_names"]))
     want = np.sqrt((dig[:, 0] ** 2).sum())
     assert abs(got - want) < 3e-2 * want
+
+
+# ------------------------------------------------------------------ dropout of the training forward
+def test_dropout_scale_statistics():
+    from mst_b200 import engine as K
+    n, p = 1 << 20, 0.1
+    seed = torch.tensor([12345], dtype=torch.int64, device=DEV)
+    m = K.dropout_scale(n, p, seed, 17)
+    vals = torch.unique(m)
+    assert vals.numel() == 2 and vals[0] == 0 and abs(float(vals[1]) - 1 / 0.9) < 1e-6
+    assert abs(float((m == 0).float().mean()) - p) < 2e-3
+    assert abs(float(m.mean()) - 1.0) < 3e-3                       # inverted dropout keeps the expectation
+    assert not torch.equal(m, K.dropout_scale(n, p, seed, 18))      # another site: another mask
+    assert not torch.equal(m, K.dropout_scale(n, p, seed + 1, 17))  # another key: another mask
+    assert torch.equal(m, K.dropout_scale(n, p, seed, 17))          # counter-based: reproducible
+
+
+def _masked_oracle_forward(front, w, x, t, feat, masks, n_heads=4):
+    """oracle.denoiser.mdm_forward with the dropout multipliers of the CUDA path applied at the same five sites
+    (token sequence after PE; per layer: attention probabilities, out-proj output, GELU output, linear2 output)."""
+    import math
+    B, F, _, T = x.shape
+    S = T + 1
+    emb = OD.time_embedding(front, t) + feat @ front["embed_text.weight"].T + front["embed_text.bias"]
+    xs = x.permute(3, 0, 1, 2).reshape(T, B, F) @ front["input_process.poseEmbedding.weight"].T + \
+        front["input_process.poseEmbedding.bias"]
+    seq = torch.cat([emb[None], xs], dim=0) + front["sequence_pos_encoder.pe"][:S]
+
+    def tok(m, width):  # token-major [B, S, width] multipliers -> [S, B, width]
+        return m.view(B, S, width).permute(1, 0, 2)
+
+    d = seq.shape[-1]
+    dh = d // n_heads
+    seq = seq * tok(masks[0], d)
+    for l in range(8):
+        pre = f"seqTransEncoder.layers.{l}."
+        qkv = seq @ w[pre + "self_attn.in_proj_weight"].T + w[pre + "self_attn.in_proj_bias"]
+        q, k, v = (z.reshape(S, B, n_heads, dh).permute(1, 2, 0, 3) for z in qkv.split(d, dim=-1))
+        att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(dh), dim=-1) * masks[8 * (l + 1) + 1].view(B, n_heads, S, S)
+        o = (att @ v).permute(2, 0, 1, 3).reshape(S, B, d)
+        sa = (o @ w[pre + "self_attn.out_proj.weight"].T + w[pre + "self_attn.out_proj.bias"]) * tok(masks[8 * (l + 1) + 2], d)
+        seq = OD.layer_norm(seq + sa, w[pre + "norm1.weight"], w[pre + "norm1.bias"])
+        h = OD.gelu(seq @ w[pre + "linear1.weight"].T + w[pre + "linear1.bias"]) * tok(masks[8 * (l + 1) + 3], 1024)
+        ff = (h @ w[pre + "linear2.weight"].T + w[pre + "linear2.bias"]) * tok(masks[8 * (l + 1) + 4], d)
+        seq = OD.layer_norm(seq + ff, w[pre + "norm2.weight"], w[pre + "norm2.bias"])
+    out = seq[1:] @ front["output_process.poseFinal.weight"].T + front["output_process.poseFinal.bias"]
+    return out.reshape(T, B, F, 1).permute(1, 2, 3, 0).contiguous()
+
+
+@pytest.mark.parametrize("pooled", [False, True])
+def test_dropout_forward_backward_matches_masked_oracle(mu, FI, tmp_path_factory, pooled):
+    """p = 0.1 dropout (the reference's train-mode setting): the masks are counter-based, so the test reads them back
+    through the test hook, applies them in the oracle's tensor algebra, and compares outputs and all 96 gradients."""
+    from mst_b200 import engine as K
+    model, front, enc, _ = _style_model(mu, FI, tmp_path_factory, precision="fp32")
+    model.mst_train_dropout = 0.1
+    B, T, p = 2, 19, 0.1
+    S, M = T + 1, B * (T + 1)
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(B, 181, 1, T, generator=g)
+    d_out = torch.randn(B, 181, 1, T, generator=g)
+    t = torch.tensor([400, 20])
+    feat = text_features(["a", "b"])
+    if pooled:  # the trainer's mode: pooled tape, CUDA-graph replay, gradients accumulated straight into .grad
+        from mst_b200.diffusion.fp16_util import MixedPrecisionTrainer
+        trainer = MixedPrecisionTrainer(model=model)
+        trainer.zero_grad()
+    else:
+        model.zero_grad(set_to_none=True)
+    y = {"text_feat": feat.to(DEV), "text": ["x"] * B}
+    for rep_ in range(2 if pooled else 1):  # second pooled pass replays the captured graphs with a NEW key
+        if pooled:
+            trainer.zero_grad()
+        torch.manual_seed(1000 + rep_)
+        xg = x.to(DEV).requires_grad_(not pooled)
+        out = model(xg, t.to(DEV), y)
+        (out * d_out.to(DEV)).sum().backward()
+        torch.manual_seed(1000 + rep_)
+        key = int(torch.randint(0, 2 ** 62, (1,)).item())
+        seed = torch.tensor([key], dtype=torch.int64, device=DEV)
+        sizes = {0: M * 512}
+        for l in range(8):
+            sizes.update({8 * (l + 1) + 1: B * 4 * S * S, 8 * (l + 1) + 2: M * 512, 8 * (l + 1) + 3: M * 1024,
+                          8 * (l + 1) + 4: M * 512})
+        masks = {site: K.dropout_scale(n, p, seed, site).cpu() for site, n in sizes.items()}
+        w_enc = {k: v.clone().requires_grad_(True) for k, v in enc.items()}
+        xo = x.clone().requires_grad_(True)
+        out_o = _masked_oracle_forward(front, w_enc, xo, t, feat, masks)
+        (out_o * d_out).sum().backward()
+        assert relerr(out.detach(), out_o.detach()) < 1e-4
+        if not pooled:
+            assert relerr(xg.grad, xo.grad) < TOL
+        for name, prm in model.seqTransEncoder.named_parameters():
+            assert relerr(prm.grad, w_enc["seqTransEncoder." + name].grad) < TOL, (name, rep_)
+    # and the masks matter: the deterministic output differs
+    model.mst_train_dropout = 0.0
+    with torch.no_grad():
+        assert relerr(model(x.to(DEV), t.to(DEV), y), out_o.detach()) > 1e-2
