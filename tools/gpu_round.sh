@@ -12,4 +12,5 @@ echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 35 -c 4 -o gpurun_out/prof_gemm python tools/profile_step.py --eager > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 fi
-cat gpurun_out/profile_step.log
+[ -f gpurun_out/profile_step.log ] && cat gpurun_out/profile_step.log
+exit 0
