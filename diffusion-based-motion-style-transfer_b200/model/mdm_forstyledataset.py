@@ -399,8 +399,26 @@ class NativeDenoiser(nn.Module):
             return None
         feat = y.get('text_feat', None)
         if feat is None:
-            feat = self.encode_text(y['text'])
+            feat = self.encode_text_cached(y['text'], device)
         return self.mask_cond(feat.to(device).float()).contiguous()
+
+    def encode_text_cached(self, raw_text, device):
+        """CLIP features of a list of captions through a per-model cache keyed by the caption string (scope row N1, the
+        "cached-feature API" half): the frozen text tower is deterministic, so a caption is encoded once per process -
+        the reference re-encodes the same strings at every denoising step and twice under CFG
+        (model/mdm_forstyledataset.py:326, model/cfg_sampler.py:36-43).  ``mst_text_cache_clear()`` drops the cache."""
+        cache = self.__dict__.setdefault("_mst_text_cache", {})
+        missing = [t for t in dict.fromkeys(raw_text) if (t, str(device)) not in cache]
+        if missing:
+            feats = self.encode_text(missing).detach().to(device).float()
+            for t, f in zip(missing, feats):
+                cache[(t, str(device))] = f.clone()
+            while len(cache) > 65536:  # bound the memory: 512 floats per caption
+                cache.pop(next(iter(cache)))
+        return torch.stack([cache[(t, str(device))] for t in raw_text])
+
+    def mst_text_cache_clear(self):
+        self.__dict__.pop("_mst_text_cache", None)
 
     def text_embedding(self, y, device, precision=None):
         """embed_text(mask_cond(clip(text))) [B, d]; computed once per trajectory by the sampler."""

@@ -195,3 +195,29 @@ def test_install_overlay_registers_reference_names():
     assert sys.modules["utils.model_util"].creat_ddpm_ddim_diffusion is mu.creat_ddpm_ddim_diffusion
     for n in names:
         sys.modules.pop(n, None)
+
+
+def test_text_feature_cache_encodes_each_caption_once():
+    """Scope row N1 (cached-feature API): CLIP is frozen, so a caption is encoded once per process."""
+    import torch
+    from mst_b200.model.mdm_forstyledataset import NativeDenoiser
+
+    class Fake(NativeDenoiser):
+        cond_mode, training, cond_mask_prob = "text", False, 0.0
+
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.calls = []
+
+        def encode_text(self, raw_text):
+            self.calls.append(list(raw_text))
+            return torch.stack([torch.full((4,), float(len(t))) for t in raw_text])
+
+    m = Fake()
+    a = m.encode_text_cached(["walk", "jump", "walk"], "cpu")
+    assert m.calls == [["walk", "jump"]] and a.shape == (3, 4) and torch.equal(a[0], a[2])
+    b = m.encode_text_cached(["jump", "run"], "cpu")
+    assert m.calls == [["walk", "jump"], ["run"]] and float(b[1, 0]) == 3.0
+    m.mst_text_cache_clear()
+    m.encode_text_cached(["jump"], "cpu")
+    assert m.calls[-1] == ["jump"]
