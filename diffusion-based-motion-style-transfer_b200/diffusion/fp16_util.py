@@ -97,7 +97,10 @@ class MixedPrecisionTrainer:
         self.flat.ensure_grad_views()
 
     def optimize(self, opt):
-        grad_norm, param_norm = self._compute_norms()
+        # after a SUM all-reduce the arena holds world_size x the mean gradient; the optimiser applies it scaled by
+        # opt.grad_scale = 1 / world_size, and the logged norm is that of the applied (mean) gradient
+        scale = getattr(opt, "grad_scale", 1.0)
+        grad_norm, param_norm = self._compute_norms(grad_scale=1.0 / scale if scale else 1.0)
         self.last_norms = (grad_norm, param_norm)
         opt.step()
         return True
