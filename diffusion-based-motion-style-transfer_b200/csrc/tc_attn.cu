@@ -336,25 +336,46 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_wait(o_full(slot), par);
       tc_fence_after();
       ATT_STAMP();
+      // O drain in two phases: (1) TMEM -> registers (scaled by 1/sum, packed to bf16: 64 registers for the 128 columns),
+      // double-buffered loads; the TMEM slot is released as soon as the last load has landed, so the Q K^T of the item
+      // after next starts while (2) the rows are staged and stored.  The slot's critical chain
+      // QK -> softmax -> PV -> drain loses the whole store phase.
+      uint32_t ob[64];
       if (warp_valid) {
         const float inv = row_valid ? 1.0f / sum : 0.0f;
-#pragma unroll 1
+        uint32_t va[32], vb[32];
+        auto pack32 = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 2)
+            ob[(c >> 1) + (k >> 1)] = pack_bf16x2(__uint_as_float(v[k]) * inv, __uint_as_float(v[k + 1]) * inv);
+        };
+        tmem_ld32(s_addr + (uint32_t)p_cols, va);
+        tmem_ld_wait();
+        tmem_ld32(s_addr + (uint32_t)(p_cols + 32), vb);
+        pack32(va, 0);
+        tmem_ld_wait();
+        tmem_ld32(s_addr + (uint32_t)(p_cols + 64), va);
+        pack32(vb, 32);
+        tmem_ld_wait();
+        tmem_ld32(s_addr + (uint32_t)(p_cols + 96), vb);
+        pack32(va, 64);
+        tmem_ld_wait();
+        pack32(vb, 96);
+      }
+      tc_fence_before();
+      mbar_arrive(slot_free(slot));
+      ATT_STAMP();
+      if (warp_valid) {
+#pragma unroll
         for (int c = 0; c < ATT_DH; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(s_addr + (uint32_t)(p_cols + c), v);
           const int bx = (c >> 5) & 1;
           if (lane == 0) bulk_wait_read_1();  // the store that last used this box has read it
           __syncwarp();
-          tmem_ld_wait();
           const uint32_t row_smem = my_box + bx * ATT_OBOX_BYTES + lane * 64;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {  // 8 columns -> one 16-byte piece; 64B swizzle: piece ^ ((row >> 1) & 3)
-            const uint32_t* s = &v[q * 8];
-            sts128(row_smem + ((q ^ ((lane >> 1) & 3)) << 4),
-                   make_uint4(pack_bf16x2(__uint_as_float(s[0]) * inv, __uint_as_float(s[1]) * inv),
-                              pack_bf16x2(__uint_as_float(s[2]) * inv, __uint_as_float(s[3]) * inv),
-                              pack_bf16x2(__uint_as_float(s[4]) * inv, __uint_as_float(s[5]) * inv),
-                              pack_bf16x2(__uint_as_float(s[6]) * inv, __uint_as_float(s[7]) * inv)));
+            const uint32_t* o = &ob[(c >> 1) + q * 4];
+            sts128(row_smem + ((q ^ ((lane >> 1) & 3)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -364,9 +385,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(slot_free(slot));
-      ATT_STAMP();
+
     }
     if (lane == 0) bulk_wait_all();
   }
