@@ -58,7 +58,7 @@ class ForwardArgs(C.Structure):
         ("x", C.c_void_p), ("temb", C.c_void_p), ("temb_row_dev", C.c_void_p), ("temb_row_offset", C.c_int32),
         ("text_emb", C.c_void_p), ("out_cond", C.c_void_p), ("out_uncond", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("use_graph", C.c_int32),
-        ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p), ("tape_seqs", C.c_int32), ("tape_seq_offset", C.c_int32),
     ]
 
 
@@ -87,7 +87,7 @@ class BackwardArgs(C.Structure):
         ("batch", C.c_int32), ("n_frames", C.c_int32), ("d_out", C.c_void_p), ("d_x", C.c_void_p),
         ("layer_grads", C.POINTER(LayerGrads)), ("tape", C.c_void_p), ("tape_bytes", C.c_size_t),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t), ("use_graph", C.c_int32),
-        ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p), ("tape_seqs", C.c_int32), ("tape_seq_offset", C.c_int32),
     ]
 
 

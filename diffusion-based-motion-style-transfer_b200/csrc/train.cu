@@ -313,7 +313,10 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------------------
 struct Drop {
   float p = 0.0f;                      // 0 = off
-  const unsigned long long* seed = nullptr;  // device
+  const unsigned long long* seed = nullptr;  // device: one key per sequence of the call (the masks of a sequence do not
+                                             // depend on which other sequences share the launch, so forwards recorded one
+                                             // by one can be back-propagated as one batch)
+  int n_seqs = 1;
   __host__ __device__ bool on() const { return p > 0.0f; }
 };
 
@@ -330,9 +333,9 @@ __device__ __forceinline__ void philox4(uint32_t c0, uint32_t c1, uint32_t k0, u
   o[0] = x; o[1] = y; o[2] = z; o[3] = w;
 }
 
-// scale factors (0 or 1/(1-p)) of elements [4v, 4v+3] of `site`
-__device__ __forceinline__ float4 drop_scale4(const Drop& d, uint32_t site, long long v) {
-  const unsigned long long seed = *d.seed;
+// scale factors (0 or 1/(1-p)) of elements [4v, 4v+3] of `site` of sequence `seq` (v counts inside the sequence)
+__device__ __forceinline__ float4 drop_scale4(const Drop& d, uint32_t site, int seq, long long v) {
+  const unsigned long long seed = d.seed[seq];
   uint32_t r[4];
   philox4((uint32_t)v, site ^ ((uint32_t)(v >> 32) << 16), (uint32_t)seed, (uint32_t)(seed >> 32), r);
   const float keep = 1.0f / (1.0f - d.p);
@@ -342,9 +345,10 @@ __device__ __forceinline__ float4 drop_scale4(const Drop& d, uint32_t site, long
 
 // out[i] = in[i] * mask[i] (+ add[i]); n % 4 == 0, all pointers 16-byte aligned; in may alias out
 __global__ void __launch_bounds__(256) dropout_kernel(const float* in, const float* __restrict__ add, float* out, long long n4,
-                                                      Drop d, uint32_t site) {
+                                                      long long per_seq4, Drop d, uint32_t site) {
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x) {
-    const float4 m = drop_scale4(d, site, v);
+    const int seq = (int)(v / per_seq4);
+    const float4 m = drop_scale4(d, site, seq, v - (long long)seq * per_seq4);
     float4 x = reinterpret_cast<const float4*>(in)[v];
     x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
     if (add) {
@@ -357,9 +361,10 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* in, const flo
 
 // du = dh * mask * gelu'(u), in place in dh
 __global__ void __launch_bounds__(256) gelu_bwd_drop_kernel(const float* __restrict__ u, float* __restrict__ dh, long long n4,
-                                                            Drop d, uint32_t site) {
+                                                            long long per_seq4, Drop d, uint32_t site) {
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x) {
-    const float4 m = drop_scale4(d, site, v);
+    const int seq = (int)(v / per_seq4);
+    const float4 m = drop_scale4(d, site, seq, v - (long long)seq * per_seq4);
     const float4 uu = reinterpret_cast<const float4*>(u)[v];
     float4 g = reinterpret_cast<float4*>(dh)[v];
     g.x *= m.x * gelu_grad_f(uu.x); g.y *= m.y * gelu_grad_f(uu.y);
@@ -470,8 +475,9 @@ static int ew_blocks(long long n) {
 }
 
 static int dropout(const float* in, const float* add, float* out, long long n, const Drop& d, uint32_t site, cudaStream_t s) {
-  if (n % 4 != 0) return fail(MST_ERR_UNSUPPORTED, "dropout: tensor sizes must be multiples of 4 (pad the sequence)");
-  dropout_kernel<<<ew_blocks(n / 4), 256, 0, s>>>(in, add, out, n / 4, d, site);
+  if (n % (4ll * d.n_seqs) != 0)
+    return fail(MST_ERR_UNSUPPORTED, "dropout: per-sequence tensor sizes must be multiples of 4");
+  dropout_kernel<<<ew_blocks(n / 4), 256, 0, s>>>(in, add, out, n / 4, n / 4 / d.n_seqs, d, site);
   MST_LAUNCHED("dropout", s);
   return MST_OK;
 }
@@ -642,6 +648,20 @@ static size_t carve_tape(const mst_model_desc& d, int n_seqs, int S, void* base,
   return align_up(off, 256);
 }
 
+// The tape of `tape_seqs` sequences seen from sequence `k` on: a forward of fewer sequences records into its slice, and
+// one backward over the whole tape later back-propagates all of them together.
+static Tape tape_view(const Tape& full, const mst_model_desc& d, int S, int k) {
+  Tape v = full;
+  const size_t dm = d.d_model, ff = d.d_ff, row = (size_t)k * S, pp = (size_t)k * d.n_heads * S * S;
+  for (int l = 0; l < d.n_layers; ++l) {
+    LayerTape& L = v.l[l];
+    L.x += row * dm; L.qkv += row * 3 * dm; L.p += pp; L.pd += pp; L.ao += row * dm; L.z1 += row * dm; L.y += row * dm;
+    L.u += row * ff; L.h += row * ff; L.z2 += row * dm;
+  }
+  v.x_out += row * dm;
+  return v;
+}
+
 static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const uint8_t* key_valid, const Drop& drop,
                                 cudaStream_t s) {
   const mst_model_desc& d = e->desc;
@@ -759,7 +779,8 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     }
     if ((rc = linear_bwd(tc, w.stage, dz2g, t.h, lf2, nullptr, w.dh, G.w2, G.b2, M, s, "bwd_dh", "bwd_dw2"))) return rc;
     if (drop.on())
-      gelu_bwd_drop_kernel<<<ew_blocks((long long)M * ff / 4), 256, 0, s>>>(t.u, w.dh, (long long)M * ff / 4, drop, drop_site(l, 3));
+      gelu_bwd_drop_kernel<<<ew_blocks((long long)M * ff / 4), 256, 0, s>>>(t.u, w.dh, (long long)M * ff / 4,
+                                                                            (long long)S * ff / 4, drop, drop_site(l, 3));
     else
       gelu_bwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, w.dh, (long long)M * ff);
     MST_LAUNCHED("bwd_gelu", s);
@@ -1045,12 +1066,16 @@ extern "C" int mst_denoiser_forward_train(mst_engine_t h, const mst_forward_args
   MST_CHECK_ARG(a.n_frames + 1 <= e->desc.pe_len, "sequence longer than the positional table");
   const mst_model_desc& d = e->desc;
   const int B = a.batch, T = a.n_frames, S = T + 1, dm = d.d_model;
-  Tape tp;
-  MST_CHECK_ARG(tape_bytes >= carve_tape(d, B, S, tape, &tp), "tape too small");
+  const int tape_seqs = a.tape_seqs > 0 ? a.tape_seqs : B;
+  MST_CHECK_ARG(a.tape_seq_offset >= 0 && a.tape_seq_offset + B <= tape_seqs, "tape_seq_offset + batch exceeds tape_seqs");
+  Tape tp_full;
+  MST_CHECK_ARG(tape_bytes >= carve_tape(d, tape_seqs, S, tape, &tp_full), "tape too small");
+  const Tape tp = tape_view(tp_full, d, S, a.tape_seq_offset);
   MST_CHECK_ARG(a.dropout_p >= 0.0f && a.dropout_p < 1.0f && (a.dropout_p == 0.0f || a.dropout_seed), "bad dropout arguments");
   Drop drop;
   drop.p = a.dropout_p;
   drop.seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
+  drop.n_seqs = B;
   uint64_t key = fnv1a(&a, sizeof(a), 1469598103934665603ull);
   key = fnv1a(e, sizeof(Engine), key);
   key = fnv1a(&tape, sizeof(tape), key) ^ 0x66ull;
@@ -1090,19 +1115,24 @@ extern "C" int mst_denoiser_backward(mst_engine_t h, const mst_backward_args* ap
   MST_CHECK_ARG(a.d_out && a.tape && a.scratch && a.layer_grads, "null tensor pointer");
   const mst_model_desc& d = e->desc;
   const int B = a.batch, T = a.n_frames, S = T + 1, M = B * S, dm = d.d_model;
-  Tape tp;
+  const int tape_seqs = a.tape_seqs > 0 ? a.tape_seqs : B;
+  MST_CHECK_ARG(a.tape_seq_offset >= 0 && a.tape_seq_offset + B <= tape_seqs, "tape_seq_offset + batch exceeds tape_seqs");
+  Tape tp_full;
   BwdScratch w;
-  MST_CHECK_ARG(a.tape_bytes >= carve_tape(d, B, S, const_cast<void*>(a.tape), &tp), "tape too small");
+  MST_CHECK_ARG(a.tape_bytes >= carve_tape(d, tape_seqs, S, const_cast<void*>(a.tape), &tp_full), "tape too small");
+  const Tape tp = tape_view(tp_full, d, S, a.tape_seq_offset);
   MST_CHECK_ARG(a.scratch_bytes >= carve_bwd(d, B, S, a.scratch, &w), "scratch too small");
   MST_CHECK_ARG(a.dropout_p >= 0.0f && a.dropout_p < 1.0f && (a.dropout_p == 0.0f || a.dropout_seed), "bad dropout arguments");
   Drop drop;
   drop.p = a.dropout_p;
   drop.seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
+  drop.n_seqs = B;
   // key: every device pointer / size of the call (not the host address of the layer_grads array, its contents)
   const void* kp[] = {a.d_out, a.d_x, a.tape, a.scratch, a.dropout_seed};
   uint32_t pbits;
   memcpy(&pbits, &a.dropout_p, 4);
-  const size_t kn[] = {(size_t)a.batch, (size_t)a.n_frames, a.tape_bytes, a.scratch_bytes, (size_t)pbits};
+  const size_t kn[] = {(size_t)a.batch, (size_t)a.n_frames, a.tape_bytes, a.scratch_bytes, (size_t)pbits,
+                       (size_t)a.tape_seqs, (size_t)a.tape_seq_offset};
   uint64_t key = fnv1a(kp, sizeof(kp), 1469598103934665603ull);
   key = fnv1a(kn, sizeof(kn), key);
   key = fnv1a(e, sizeof(Engine), key);
@@ -1140,6 +1170,7 @@ extern "C" int mst_motion_encoder_forward(mst_engine_t h, const float* x, const 
   Drop drop;
   drop.p = dropout_p;
   drop.seed = reinterpret_cast<const unsigned long long*>(dropout_seed);
+  drop.n_seqs = batch;
   MST_CHECK_ARG(h && x && mu_query && sigma_query && mu_out && tape, "null argument");
   Engine* e = reinterpret_cast<Engine*>(h);
   int rc;
@@ -1171,6 +1202,7 @@ extern "C" int mst_motion_encoder_backward(mst_engine_t h, const float* d_mu, in
   Drop drop;
   drop.p = dropout_p;
   drop.seed = reinterpret_cast<const unsigned long long*>(dropout_seed);
+  drop.n_seqs = batch;
   MST_CHECK_ARG(h && d_mu && d_x && tape && scratch, "null argument");
   Engine* e = reinterpret_cast<Engine*>(h);
   int rc;
@@ -1197,7 +1229,7 @@ extern "C" int mst_motion_encoder_backward(mst_engine_t h, const float* d_mu, in
 
 __global__ void __launch_bounds__(256) dropout_scale_kernel(float* out, long long n4, mst::Drop d, uint32_t site) {
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x)
-    reinterpret_cast<float4*>(out)[v] = mst::drop_scale4(d, site, v);
+    reinterpret_cast<float4*>(out)[v] = mst::drop_scale4(d, site, 0, v);
 }
 
 extern "C" int mst_test_dropout_scale(float* out, int64_t n, float p, const uint64_t* seed_dev, int32_t site, void* stream) {

@@ -92,8 +92,14 @@ class MixedPrecisionTrainer:
             if hasattr(m, "mst_tape_reset"):
                 m.mst_tape_reset()
 
+    def _flush(self):
+        for m in self.model.modules():
+            if hasattr(m, "mst_flush_backward"):
+                m.mst_flush_backward()
+
     def backward(self, loss: th.Tensor):
         loss.backward()
+        self._flush()   # batched backward passes still waiting for a forward whose output never reached the loss
         self.flat.ensure_grad_views()
 
     def optimize(self, opt):
@@ -107,6 +113,7 @@ class MixedPrecisionTrainer:
 
     def _compute_norms(self, grad_scale=1.0):
         """(||grad||_2 / grad_scale, ||param||_2) over all master params (reference :215-223)."""
+        self._flush()
         sq = K.sumsq2(self.flat.grads, None).cpu()
         sp = K.sumsq2(self.flat.params, None).cpu()
         return float(np.sqrt(sq[0].item())) / grad_scale, float(np.sqrt(sp[0].item()))

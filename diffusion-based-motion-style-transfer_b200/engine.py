@@ -180,7 +180,8 @@ class Engine:
 
     def forward_train(self, x: torch.Tensor, temb: torch.Tensor, text_emb: Optional[torch.Tensor], *,
                       uncond: bool = False, tape: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                      use_graph: bool = False, dropout_p: float = 0.0, dropout_seed: Optional[torch.Tensor] = None):
+                      use_graph: bool = False, dropout_p: float = 0.0, dropout_seed: Optional[torch.Tensor] = None,
+                      tape_seqs: int = 0, tape_seq_offset: int = 0):
         """Denoiser forward that records the activation tape.  Returns (out [B,F,1,T], tape).
         use_graph=True promises that x / temb / text_emb / out / tape are the same buffers on every call with this
         shape (a TapeSlot): the launch sequence is then captured once and replayed as a CUDA graph."""
@@ -188,7 +189,7 @@ class Engine:
         if x.numel() != B * self.n_feats * T:
             raise ValueError(f"x has shape {tuple(x.shape)}, expected [B,{self.n_feats},1,T]")
         if tape is None:
-            tape_bytes, _ = self.train_sizes(B, T + 1)
+            tape_bytes, _ = self.train_sizes(max(B, tape_seqs), T + 1)
             tape = torch.empty(tape_bytes, dtype=torch.uint8, device=self.device)
         if out is None:
             out = torch.empty_like(x)
@@ -196,6 +197,9 @@ class Engine:
         a.use_graph = int(bool(use_graph))
         a.dropout_p = float(dropout_p)
         a.dropout_seed = _ptr(dropout_seed, torch.int64, "dropout_seed") if dropout_p > 0 else None
+        a.tape_seqs, a.tape_seq_offset = int(tape_seqs), int(tape_seq_offset)
+        if dropout_p > 0 and dropout_seed.numel() < B:
+            raise ValueError("dropout_seed needs one key per sequence of the call")
         a.batch, a.n_frames, a.cfg, a.uncond = B, T, 0, int(uncond)
         a.x = _ptr(x, name="x")
         a.temb = _ptr(temb, name="temb")
@@ -208,8 +212,9 @@ class Engine:
         return out, tape
 
     def backward(self, d_out: torch.Tensor, tape: torch.Tensor, layer_grads: list, want_dx: bool = False,
-                 use_graph: bool = False, dropout_p: float = 0.0, dropout_seed: Optional[torch.Tensor] = None):
-        """Back-propagate d_out [B,F,1,T] through the taped forward.  layer_grads: per layer a dict keyed by LAYER_KEYS
+                 use_graph: bool = False, dropout_p: float = 0.0, dropout_seed: Optional[torch.Tensor] = None,
+                 tape_seqs: int = 0, tape_seq_offset: int = 0):
+        """Back-propagate d_out [B,F,1,T] through the taped forward(s) of sequences [tape_seq_offset, +B) of the tape.  layer_grads: per layer a dict keyed by LAYER_KEYS
         of fp32 CUDA tensors (or None) that the gradients are ACCUMULATED into.  Returns d_x or None."""
         B, T = d_out.shape[0], d_out.shape[-1]
         _, scratch_bytes = self.train_sizes(B, T + 1)
@@ -226,6 +231,7 @@ class Engine:
         a.use_graph = int(bool(use_graph))
         a.dropout_p = float(dropout_p)
         a.dropout_seed = _ptr(dropout_seed, torch.int64, "dropout_seed") if dropout_p > 0 else None
+        a.tape_seqs, a.tape_seq_offset = int(tape_seqs), int(tape_seq_offset)
         a.batch, a.n_frames = B, T
         a.d_out, a.d_x = _ptr(d_out, name="d_out"), _ptr(d_x, name="d_x")
         a.layer_grads = arr
@@ -263,20 +269,60 @@ class Engine:
 
 
 class TapeSlot:
-    """Persistent buffers of one taped forward / backward of a given shape: with every pointer stable from one training
-    step to the next, the C side replays the whole launch sequence as a CUDA graph (mst_forward_args.use_graph)."""
+    """Persistent buffers for up to ``capacity`` taped forwards of ``B`` sequences x ``T`` frames each, recorded into
+    slices of ONE tape.  Every pointer is stable from one training step to the next, so the C side replays the launch
+    sequences as CUDA graphs (mst_forward_args.use_graph), and forwards recorded one by one - the six differentiable
+    DDIM steps of the finetune loss - are back-propagated by ONE batched backward over the whole tape."""
 
-    def __init__(self, eng: "Engine", B: int, T: int, has_text: bool):
+    def __init__(self, eng: "Engine", B: int, T: int, has_text: bool, capacity: int = 1):
         dev, f32 = eng.device, torch.float32
-        tape_bytes, _ = eng.train_sizes(B, T + 1)
+        self.eng, self.B, self.T, self.capacity = eng, B, T, capacity
+        n = B * capacity
+        self.tape_seqs = n
+        tape_bytes, _ = eng.train_sizes(n, T + 1)
         self.tape = torch.empty(tape_bytes, dtype=torch.uint8, device=dev)
-        self.x = torch.empty(B, eng.n_feats, 1, T, dtype=f32, device=dev)
-        self.temb = torch.empty(B, eng.d_model, dtype=f32, device=dev)
-        self.text = torch.empty(B, eng.d_model, dtype=f32, device=dev) if has_text else None
-        self.out = torch.empty(B, eng.n_feats, 1, T, dtype=f32, device=dev)
-        self.d_out = torch.empty(B, eng.n_feats, 1, T, dtype=f32, device=dev)
-        self.seed = torch.zeros(1, dtype=torch.int64, device=dev)   # Philox key of this forward's dropout masks
-        self.epoch = 0  # bumped every time the slot is handed out: a stale autograd node can tell its tape is gone
+        self.x = torch.empty(n, eng.n_feats, 1, T, dtype=f32, device=dev)
+        self.temb = torch.empty(n, eng.d_model, dtype=f32, device=dev)
+        self.text = torch.empty(n, eng.d_model, dtype=f32, device=dev) if has_text else None
+        self.out = torch.empty(n, eng.n_feats, 1, T, dtype=f32, device=dev)
+        self.d_out = torch.empty(n, eng.n_feats, 1, T, dtype=f32, device=dev)
+        self.seed = torch.zeros(n, dtype=torch.int64, device=dev)   # one Philox key per sequence (dropout masks)
+        self.epoch = 0      # bumped at every reset: a stale autograd node can tell its tape is gone
+        self.used = 0       # forwards handed out since the last reset
+        self.pending = {}   # call index -> (dropout_p, layer_grads) whose d_out is staged, backward not yet run
+        self.done = set()
+
+    def rows(self, k):
+        return slice(k * self.B, (k + 1) * self.B)
+
+    def reset(self):
+        self.flush()
+        self.used, self.done = 0, set()
+        self.epoch += 1
+
+    def stage_backward(self, k, d_out, dropout_p, grads):
+        """Record the output gradient of call k; run the batched backward once every call of this step has reported."""
+        self.d_out[self.rows(k)].copy_(d_out)
+        self.pending[k] = (dropout_p, grads)
+        if len(self.pending) + len(self.done) == self.used:
+            self.flush()
+
+    def flush(self):
+        """Back-propagate every staged call: one launch sequence (graph) per run of consecutive calls."""
+        ks = sorted(self.pending)
+        i = 0
+        while i < len(ks):
+            j = i
+            while j + 1 < len(ks) and ks[j + 1] == ks[j] + 1 and self.pending[ks[j + 1]][0] == self.pending[ks[i]][0]:
+                j += 1
+            k0, k1 = ks[i], ks[j] + 1
+            p, grads = self.pending[k0]
+            lo, hi = k0 * self.B, k1 * self.B
+            self.eng.backward(self.d_out[lo:hi], self.tape, grads, want_dx=False, use_graph=True, dropout_p=p,
+                              dropout_seed=self.seed[lo:hi], tape_seqs=self.tape_seqs, tape_seq_offset=lo)
+            i = j + 1
+        self.done.update(ks)
+        self.pending = {}
 
 
 # ---------------------------------------------------------------------------------

@@ -161,23 +161,25 @@ class _DenoiserGradFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, native, x, temb, text_emb, uncond, *params):
         eng = native.mst_engine(x.device, precision=native.mst_train_prec())
-        slot = native._mst_tape_acquire(eng, x.shape[0], x.shape[-1], text_emb is not None)
-        ctx.native, ctx.eng, ctx.slot = native, eng, slot
+        B = x.shape[0]
+        slot, k = native._mst_tape_acquire(eng, B, x.shape[-1], text_emb is not None)
+        ctx.native, ctx.eng, ctx.slot, ctx.k = native, eng, slot, k
         p = ctx.drop_p = native.mst_dropout_p()
         key = native.mst_draw_dropout_key() if p > 0 else 0
         if slot is not None:
-            slot.x.copy_(x)
-            slot.temb.copy_(temb)
+            r = slot.rows(k)
+            slot.x[r].copy_(x)
+            slot.temb[r].copy_(temb)
             if text_emb is not None:
-                slot.text.copy_(text_emb)
+                slot.text[r].copy_(text_emb)
             if p > 0:
-                slot.seed.fill_(key)
-            ctx.drop_seed = slot.seed
-            eng.forward_train(slot.x, slot.temb, slot.text if text_emb is not None else None, uncond=uncond,
-                              tape=slot.tape, out=slot.out, use_graph=True, dropout_p=p, dropout_seed=slot.seed)
+                slot.seed[r].copy_(torch.arange(key, key + B, dtype=torch.int64), non_blocking=True)
+            eng.forward_train(slot.x[r], slot.temb[r], slot.text[r] if text_emb is not None else None, uncond=uncond,
+                              tape=slot.tape, out=slot.out[r], use_graph=True, dropout_p=p, dropout_seed=slot.seed[r],
+                              tape_seqs=slot.tape_seqs, tape_seq_offset=k * B)
             ctx.tape, ctx.epoch = slot.tape, slot.epoch
-            return slot.out.clone()
-        ctx.drop_seed = torch.full((1,), key, dtype=torch.int64, device=x.device) if p > 0 else None
+            return slot.out[r].clone()
+        ctx.drop_seed = torch.arange(key, key + B, dtype=torch.int64).to(x.device) if p > 0 else None
         out, tape = eng.forward_train(x, temb, text_emb, uncond=uncond, dropout_p=p, dropout_seed=ctx.drop_seed)
         ctx.tape = tape
         return out
@@ -198,13 +200,23 @@ class _DenoiserGradFn(torch.autograd.Function):
             direct = all((not needs[id(p)]) or (p.grad is not None and p.grad.is_contiguous() and
                                                  p.grad.dtype == torch.float32) for p in flat)
             if direct and not ctx.needs_input_grad[1]:
-                # accumulate straight into .grad (what autograd's AccumulateGrad would do with a returned tensor)
-                grads = [{k: (p.grad if needs[id(p)] else None) for k, p in lp.items()} for lp in layers]
-                slot.d_out.copy_(d_out)
-                ctx.eng.backward(slot.d_out, slot.tape, grads, want_dx=False, use_graph=True, dropout_p=ctx.drop_p,
-                                 dropout_seed=ctx.drop_seed)
+                # accumulate straight into .grad (what autograd's AccumulateGrad would do with a returned tensor); the
+                # kernels run once every forward recorded on this tape has reported its output gradient
+                grads = [{k_: (p.grad if needs[id(p)] else None) for k_, p in lp.items()} for lp in layers]
+                slot.stage_backward(ctx.k, d_out, ctx.drop_p, grads)
                 ctx.tape = None
                 return (None,) * (5 + len(flat))
+            # a gradient w.r.t. x (or parameters without .grad buffers) was requested: plain backward on the pooled tape
+            B = d_out.shape[0]
+            grads = _flat_layer_grads(layers, needs)
+            d_x = ctx.eng.backward(d_out.float().contiguous(), slot.tape, grads, want_dx=bool(ctx.needs_input_grad[1]),
+                                   dropout_p=ctx.drop_p, dropout_seed=slot.seed[slot.rows(ctx.k)],
+                                   tape_seqs=slot.tape_seqs, tape_seq_offset=ctx.k * B)
+            slot.done.add(ctx.k)
+            if len(slot.pending) + len(slot.done) == slot.used:
+                slot.flush()
+            ctx.tape = None
+            return (None, d_x, None, None, None) + tuple(g for lg in grads for g in lg.values())
         grads = _flat_layer_grads(layers, needs)
         d_x = ctx.eng.backward(d_out.float().contiguous(), ctx.tape, grads, want_dx=bool(ctx.needs_input_grad[1]),
                                dropout_p=ctx.drop_p, dropout_seed=ctx.drop_seed)
@@ -219,7 +231,11 @@ class _MotionEncoderGradFn(torch.autograd.Function):
     def forward(ctx, enc, x, key_valid):
         eng = enc.mst_engine(x.device, precision=enc.mst_train_prec())
         p = ctx.drop_p = enc.mst_dropout_p()
-        ctx.drop_seed = torch.full((1,), enc.mst_draw_dropout_key(), dtype=torch.int64, device=x.device) if p > 0 else None
+        if p > 0:
+            key = enc.mst_draw_dropout_key()
+            ctx.drop_seed = torch.arange(key, key + x.shape[0], dtype=torch.int64).to(x.device)
+        else:
+            ctx.drop_seed = None
         mu, tape = eng.motion_encoder_forward(x, key_valid, enc.muQuery.detach().reshape(-1).contiguous(),
                                               enc.sigmaQuery.detach().reshape(-1).contiguous(), dropout_p=p,
                                               dropout_seed=ctx.drop_seed)
@@ -314,24 +330,39 @@ class NativeDenoiser(nn.Module):
     mst_tape_pool = False   # switched on by the trainer (MixedPrecisionTrainer); MST_TRAIN_GRAPH=0 disables replay
 
     def mst_tape_reset(self):
-        """Start of a training step: every pooled slot may be handed out again, in the same order as last step."""
+        """Start of a training step: pending backward work is flushed and every pooled slot may be handed out again, in
+        the same order as last step."""
         for ent in self.__dict__.get("_mst_tape_slots", {}).values():
+            for slot in ent[0]:
+                slot.reset()
             ent[1] = 0
 
+    def mst_flush_backward(self):
+        """Run the batched backward passes that are still waiting for a sibling forward's gradient (a forward whose
+        output never reached the loss).  The trainer calls this after loss.backward() and before reading gradients."""
+        for ent in self.__dict__.get("_mst_tape_slots", {}).values():
+            for slot in ent[0]:
+                slot.flush()
+
     def _mst_tape_acquire(self, eng, B, T, has_text):
+        """(slot, call index) of a pooled tape, or (None, 0).  Single-sequence forwards (the differentiable sampling
+        steps) share one tape of 8 calls so that their backward passes run as one batch."""
         if not self.mst_tape_pool:
-            return None
+            return None, 0
         pools = self.__dict__.setdefault("_mst_tape_slots", {})
         ent = pools.setdefault((id(eng), B, T, has_text), [[], 0])
-        slots, nxt = ent
-        if nxt >= 16:       # more live forwards of one shape than a finetune step ever has: plain path
-            return None
-        if nxt == len(slots):
-            slots.append(TapeSlot(eng, B, T, has_text))
-        slot = slots[nxt]
-        ent[1] = nxt + 1
-        slot.epoch += 1
-        return slot
+        slots, cur = ent
+        capacity = 8 if B == 1 else 1
+        if cur < len(slots) and slots[cur].used == capacity:
+            cur = ent[1] = cur + 1
+        if cur >= 4:        # more live forwards of one shape than a finetune step ever has: plain path
+            return None, 0
+        if cur == len(slots):
+            slots.append(TapeSlot(eng, B, T, has_text, capacity))
+        slot = slots[cur]
+        k = slot.used
+        slot.used += 1
+        return slot, k
 
     def mst_weights_changed(self):
         """Call after parameters were updated behind torch's back (the fused optimizer writes through raw

@@ -35,6 +35,10 @@ class FusedAdamW:
     def step(self):
         g = self.param_groups[0]
         self.step_count += 1
+        if self.model is not None:
+            for m in self.model.modules():
+                if hasattr(m, "mst_flush_backward"):
+                    m.mst_flush_backward()  # deferred (batched) backward passes must have written their gradients
         K.adamw_step(self.flat.train_params, self.flat.grads, self.exp_avg, self.exp_avg_sq, lr=g["lr"],
                      beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], weight_decay=g["weight_decay"],
                      step=self.step_count, grad_scale=self.grad_scale)

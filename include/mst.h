@@ -195,9 +195,15 @@ typedef struct {
                         nn.TransformerEncoderLayer / PositionalEncoding (0.1
                         in the reference once model.train() was called); 0 =
                         identity (eval mode)                              */
-  const uint64_t* dropout_seed; /* device scalar: Philox key of this forward's
-                        masks (read by the kernels, so a graph replay sees
-                        a new value); the backward must get the same      */
+  const uint64_t* dropout_seed; /* device, one Philox key PER SEQUENCE of this
+                        call (read by the kernels, so a graph replay sees
+                        new values); the backward must get the same keys  */
+  int32_t tape_seqs;        /* mst_denoiser_forward_train only: the tape holds
+                        this many sequences (0 = batch) and this call
+                        records sequences [tape_seq_offset, +batch) of it:
+                        forwards recorded one by one can be back-propagated
+                        by ONE mst_denoiser_backward over the whole tape   */
+  int32_t tape_seq_offset;
 } mst_forward_args;
 
 int mst_denoiser_forward(mst_engine_t e, const mst_forward_args* a, void* stream);
@@ -308,7 +314,9 @@ typedef struct {
   int32_t use_graph;        /* as in mst_forward_args: pointers (incl. the
                                gradient buffers) are stable across calls    */
   float dropout_p;          /* the forward's values: the masks are          */
-  const uint64_t* dropout_seed; /* recomputed, not stored                   */
+  const uint64_t* dropout_seed; /* recomputed, not stored (one key / sequence) */
+  int32_t tape_seqs;        /* as in mst_forward_args: back-propagates      */
+  int32_t tape_seq_offset;  /* sequences [tape_seq_offset, +batch) of the tape */
 } mst_backward_args;
 
 int mst_denoiser_backward(mst_engine_t e, const mst_backward_args* a, void* stream);

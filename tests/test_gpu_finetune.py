@@ -418,12 +418,13 @@ def test_dropout_forward_backward_matches_masked_oracle(mu, FI, tmp_path_factory
         (out * d_out.to(DEV)).sum().backward()
         torch.manual_seed(1000 + rep_)
         key = int(torch.randint(0, 2 ** 62, (1,)).item())
-        seed = torch.tensor([key], dtype=torch.int64, device=DEV)
-        sizes = {0: M * 512}
+        sizes = {0: S * 512}   # per sequence: every sequence of a call has its own key (key + index in the call)
         for l in range(8):
-            sizes.update({8 * (l + 1) + 1: B * 4 * S * S, 8 * (l + 1) + 2: M * 512, 8 * (l + 1) + 3: M * 1024,
-                          8 * (l + 1) + 4: M * 512})
-        masks = {site: K.dropout_scale(n, p, seed, site).cpu() for site, n in sizes.items()}
+            sizes.update({8 * (l + 1) + 1: 4 * S * S, 8 * (l + 1) + 2: S * 512, 8 * (l + 1) + 3: S * 1024,
+                          8 * (l + 1) + 4: S * 512})
+        seeds = [torch.tensor([key + b], dtype=torch.int64, device=DEV) for b in range(B)]
+        masks = {site: torch.cat([K.dropout_scale(n, p, seeds[b], site) for b in range(B)]).cpu()
+                 for site, n in sizes.items()}
         w_enc = {k: v.clone().requires_grad_(True) for k, v in enc.items()}
         xo = x.clone().requires_grad_(True)
         out_o = _masked_oracle_forward(front, w_enc, xo, t, feat, masks)
@@ -437,3 +438,52 @@ def test_dropout_forward_backward_matches_masked_oracle(mu, FI, tmp_path_factory
     model.mst_train_dropout = 0.0
     with torch.no_grad():
         assert relerr(model(x.to(DEV), t.to(DEV), y), out_o.detach()) > 1e-2
+
+
+def test_batched_backward_of_sequential_forwards(mu, FI, tmp_path_factory):
+    """Trainer mode: forwards of single sequences recorded one by one on a shared tape (the six differentiable DDIM
+    steps) are back-propagated by ONE batched launch sequence once the last of them reports its output gradient -
+    the accumulated gradients equal the sum of the individual plain backward passes, with and without dropout."""
+    from mst_b200.diffusion.fp16_util import MixedPrecisionTrainer
+    T, n_calls = 76, 5
+    g = torch.Generator().manual_seed(31)
+    xs = [torch.randn(1, 181, 1, T, generator=g) for _ in range(n_calls)]
+    ds = [torch.randn(1, 181, 1, T, generator=g) for _ in range(n_calls)]
+    ts = [torch.randint(0, 1000, (1,), generator=g) for _ in range(n_calls)]
+    feat = text_features(["style"])
+    y = {"text_feat": feat.to(DEV), "text": ["x"]}
+    for p_drop in (0.0, 0.1):
+        # plain: fresh tape per forward, gradients returned to autograd
+        plain, *_ = _style_model(mu, FI, tmp_path_factory, precision="fp32")
+        plain.mst_train_dropout = p_drop
+        plain.zero_grad(set_to_none=True)
+        torch.manual_seed(5)
+        outs_plain = []
+        for x, d_, t in zip(xs, ds, ts):
+            out = plain(x.to(DEV), t.to(DEV), y)
+            outs_plain.append(out.detach().clone())
+            (out * d_.to(DEV)).sum().backward()
+        # pooled: shared tape, deferred batched backward (some gradients staged out of order)
+        pooled, *_ = _style_model(mu, FI, tmp_path_factory, precision="fp32")
+        pooled.mst_train_dropout = p_drop
+        trainer = MixedPrecisionTrainer(model=pooled)
+        for rep_ in range(2):   # second round replays the captured graphs
+            trainer.zero_grad()
+            torch.manual_seed(5)
+            outs = [pooled(x.to(DEV), t.to(DEV), y) for x, t in zip(xs, ts)]
+            for o, ref_o in zip(outs, outs_plain):
+                assert relerr(o.detach(), ref_o) < 1e-6
+            order = [2, 0, 4, 1, 3]
+            slot = next(iter(pooled._mst_tape_slots.values()))[0][0]
+            for i, k in enumerate(order):
+                (outs[k] * ds[k].to(DEV)).sum().backward()
+                assert (len(slot.pending) == i + 1) if i + 1 < n_calls else (len(slot.pending) == 0)
+            for (name, a), (_, b) in zip(pooled.seqTransEncoder.named_parameters(), plain.seqTransEncoder.named_parameters()):
+                assert relerr(a.grad, b.grad) < 2e-5, (name, p_drop, rep_)
+        # a forward whose output never reaches the loss must not block the others: the trainer flushes
+        trainer.zero_grad()
+        torch.manual_seed(5)
+        outs = [pooled(x.to(DEV), t.to(DEV), y) for x, t in zip(xs[:3], ts[:3])]
+        loss = (outs[0] * ds[0].to(DEV)).sum() + (outs[2] * ds[2].to(DEV)).sum()
+        trainer.backward(loss)
+        assert float(pooled.seqTransEncoder.layers[0].linear1.weight.grad.abs().sum()) > 0
