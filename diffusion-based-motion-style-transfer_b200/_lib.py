@@ -150,8 +150,8 @@ def _declare(lib):
         "mst_denoiser_forward_train": [vp, C.POINTER(ForwardArgs), vp, sz, vp],
         "mst_denoiser_backward": [vp, C.POINTER(BackwardArgs), vp],
         "mst_abi_sizes_train": [C.POINTER(sz), C.POINTER(sz)],
-        "mst_motion_encoder_forward": [vp, vp, vp, vp, vp, i32, i32, vp, vp, sz, C.c_float, vp, vp],
-        "mst_motion_encoder_backward": [vp, vp, i32, i32, vp, vp, sz, vp, sz, C.c_float, vp, vp],
+        "mst_motion_encoder_forward": [vp, vp, vp, vp, vp, i32, i32, vp, vp, sz, C.c_float, vp, i32, vp],
+        "mst_motion_encoder_backward": [vp, vp, i32, i32, vp, vp, sz, vp, sz, C.c_float, vp, i32, vp],
         "mst_test_dropout_scale": [vp, i64, C.c_float, vp, i32, vp],
         "mst_masked_l2": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "mst_update_step_backward": [vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp],

@@ -600,6 +600,190 @@ static void layer_lins(Engine* e, int l, Lin* qkv, Lin* o, Lin* f1, Lin* f2) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Fused attention of the training path for short sequences (S <= 80: the 76-frame stylexia clips, 77 / 78 tokens):
+// one CTA per (sequence, head) keeps Q, K, V (and P, dO, dP in the backward) in shared memory and runs the whole
+// chain - scores, masked softmax, dropout, P V / dV, dP, softmax backward, dQ, dK - without the six batched GEMM
+// launches over 77 x 77 x 128 problems (each padded to 128-wide tiles) that the general path needs.
+// fp32; 256 threads as a 16 x 16 grid, every thread a TM x TN register tile with rows / columns interleaved by 16 so
+// that shared-memory reads are conflict-free with the odd leading dimensions used below.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SA_MAXS = 80;          // padded sequence length the tiles cover (5 x 16)
+constexpr int SA_DH = 128;
+constexpr int SA_LDX = SA_DH + 1;    // Q, K, V, dO rows
+constexpr int SA_LDP = SA_MAXS + 1;  // P, dP rows
+
+// C(m, n) = sum_k A(m, k) B(k, n) for m < 16*TM, n < 16*TN (operands zero-padded in shared memory);
+// A(m,k) = TA ? a[k*lda + m] : a[m*lda + k];  B(k,n) = TB ? b[n*ldb + k] : b[k*ldb + n];  thread (ty, tx) owns rows
+// ty + 16 i and columns tx + 16 j and hands every result to `out(m, n, value)`.
+template <bool TA, bool TB, int TM, int TN, typename Out>
+__device__ __forceinline__ void smem_gemm(const float* a, int lda, const float* b, int ldb, int K, Out out) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+  for (int k = 0; k < K; ++k) {
+    float av[TM], bv[TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) av[i] = TA ? a[k * lda + ty + 16 * i] : a[(ty + 16 * i) * lda + k];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = TB ? b[(tx + 16 * j) * ldb + k] : b[k * ldb + tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) out(ty + 16 * i, tx + 16 * j, acc[i][j]);
+}
+
+// rows [0, S) x 128 columns of a global matrix (leading dimension ld) -> smem [SA_MAXS][SA_LDX], rows >= S zero
+__device__ __forceinline__ void sa_load(float* dst, const float* __restrict__ src, int ld, int S) {
+  for (int idx = threadIdx.x; idx < SA_MAXS * SA_DH; idx += blockDim.x) {
+    const int r = idx >> 7, c = idx & 127;
+    dst[r * SA_LDX + c] = r < S ? src[(long long)r * ld + c] : 0.0f;
+  }
+}
+// [S][S] global -> smem [SA_MAXS][SA_LDP], zero padded
+__device__ __forceinline__ void sa_load_p(float* dst, const float* __restrict__ src, int S) {
+  for (int idx = threadIdx.x; idx < SA_MAXS * SA_MAXS; idx += blockDim.x) {
+    const int r = idx / SA_MAXS, c = idx - r * SA_MAXS;
+    dst[r * SA_LDP + c] = (r < S && c < S) ? src[r * S + c] : 0.0f;
+  }
+}
+
+__device__ __forceinline__ float drop_scale1(const Drop& d, uint32_t site, int seq, long long local) {
+  const float4 m = drop_scale4(d, site, seq, local >> 2);
+  const int r = (int)(local & 3);
+  return r == 0 ? m.x : (r == 1 ? m.y : (r == 2 ? m.z : m.w));
+}
+
+// grid (heads, n_seqs).  qkv [n_seqs*S, 3d]; p / pd [n_seqs][H][S][S]; ao [n_seqs*S, d]
+__global__ void __launch_bounds__(256) attn_small_fwd_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ key_valid,
+                                                             float* __restrict__ p_out, float* __restrict__ pd_out,
+                                                             float* __restrict__ ao, int S, int d_model, int H, float scale,
+                                                             Drop drop, uint32_t site) {
+  extern __shared__ float sm[];
+  float* Qs = sm;
+  float* Ks = Qs + SA_MAXS * SA_LDX;
+  float* Vs = Ks + SA_MAXS * SA_LDX;
+  float* Ps = Vs + SA_MAXS * SA_LDX;
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const float* base = qkv + (long long)seq * S * 3 * d_model + head * SA_DH;
+  sa_load(Qs, base, 3 * d_model, S);
+  sa_load(Ks, base + d_model, 3 * d_model, S);
+  sa_load(Vs, base + 2 * d_model, 3 * d_model, S);
+  __syncthreads();
+  smem_gemm<false, true, 5, 5>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v) { Ps[i * SA_LDP + j] = v * scale; });
+  __syncthreads();
+  // masked softmax, one warp per row; then dropout.  P (before dropout) and Pd go to the tape.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint8_t* kv = key_valid ? key_valid + (long long)seq * S : nullptr;
+  float* pg = p_out + ((long long)seq * H + head) * S * S;
+  float* pdg = pd_out + ((long long)seq * H + head) * S * S;
+  for (int i = warp; i < SA_MAXS; i += 8) {
+    float* r = Ps + i * SA_LDP;
+    if (i >= S) {
+      for (int j = lane; j < SA_MAXS; j += 32) r[j] = 0.0f;
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32)
+      if (!kv || kv[j]) mx = fmaxf(mx, r[j]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+    for (int j = lane; j < SA_MAXS; j += 32) {
+      const float e = (j < S && (!kv || kv[j])) ? expf(r[j] - mx) : 0.0f;
+      r[j] = e;
+      sum += e;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < S; j += 32) {
+      float pv = r[j] * inv;
+      pg[i * S + j] = pv;
+      if (drop.on()) {
+        pv *= drop_scale1(drop, site, seq, ((long long)head * S + i) * S + j);
+        pdg[i * S + j] = pv;
+      }
+      r[j] = pv;
+    }
+  }
+  __syncthreads();
+  float* og = ao + (long long)seq * S * d_model + head * SA_DH;
+  smem_gemm<false, false, 5, 8>(Ps, SA_LDP, Vs, SA_LDX, SA_MAXS, [&](int i, int c, float v) {
+    if (i < S) og[(long long)i * d_model + c] = v;
+  });
+}
+
+// grid (heads, n_seqs).  dao [n_seqs*S, d] -> dqkv [n_seqs*S, 3d] (Q | K | V column blocks)
+__global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ p_in,
+                                                             const float* __restrict__ pd_in, const float* __restrict__ dao,
+                                                             float* __restrict__ dqkv, int S, int d_model, int H, float scale,
+                                                             Drop drop, uint32_t site) {
+  extern __shared__ float sm[];
+  float* Qs = sm;
+  float* Ks = Qs + SA_MAXS * SA_LDX;
+  float* Vs = Ks + SA_MAXS * SA_LDX;
+  float* Os = Vs + SA_MAXS * SA_LDX;   // dO
+  float* Ps = Os + SA_MAXS * SA_LDX;   // P after dropout, then P
+  float* Ds = Ps + SA_MAXS * SA_LDP;   // dP, then dS
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const float* base = qkv + (long long)seq * S * 3 * d_model + head * SA_DH;
+  float* dbase = dqkv + (long long)seq * S * 3 * d_model + head * SA_DH;
+  const long long pp = ((long long)seq * H + head) * S * S;
+  sa_load(Qs, base, 3 * d_model, S);
+  sa_load(Ks, base + d_model, 3 * d_model, S);
+  sa_load(Vs, base + 2 * d_model, 3 * d_model, S);
+  sa_load(Os, dao + (long long)seq * S * d_model + head * SA_DH, d_model, S);
+  sa_load_p(Ps, (drop.on() ? pd_in : p_in) + pp, S);
+  __syncthreads();
+  // dV = Pd^T dO
+  smem_gemm<true, false, 5, 8>(Ps, SA_LDP, Os, SA_LDX, SA_MAXS, [&](int j, int c, float v) {
+    if (j < S) dbase[(long long)j * 3 * d_model + 2 * d_model + c] = v;
+  });
+  // dP = dO V^T (masked like the forward's dropout)
+  smem_gemm<false, true, 5, 5>(Os, SA_LDX, Vs, SA_LDX, SA_DH, [&](int i, int j, float v) {
+    if (drop.on() && i < S && j < S) v *= drop_scale1(drop, site, seq, ((long long)head * S + i) * S + j);
+    Ds[i * SA_LDP + j] = v;
+  });
+  __syncthreads();
+  if (drop.on()) {  // the softmax backward needs the probabilities BEFORE dropout
+    sa_load_p(Ps, p_in + pp, S);
+    __syncthreads();
+  }
+  // dS = P * (dP - sum_j P dP)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < SA_MAXS; i += 8) {
+    const float* pr = Ps + i * SA_LDP;
+    float* dr = Ds + i * SA_LDP;
+    float dot = 0.0f;
+    for (int j = lane; j < SA_MAXS; j += 32) dot = fmaf(pr[j], dr[j], dot);
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int j = lane; j < SA_MAXS; j += 32) dr[j] = pr[j] * (dr[j] - dot);
+  }
+  __syncthreads();
+  // dQ = scale dS K ;  dK = scale dS^T Q
+  smem_gemm<false, false, 5, 8>(Ds, SA_LDP, Ks, SA_LDX, SA_MAXS, [&](int i, int c, float v) {
+    if (i < S) dbase[(long long)i * 3 * d_model + c] = v * scale;
+  });
+  smem_gemm<true, false, 5, 8>(Ds, SA_LDP, Qs, SA_LDX, SA_MAXS, [&](int j, int c, float v) {
+    if (j < S) dbase[(long long)j * 3 * d_model + d_model + c] = v * scale;
+  });
+}
+
+constexpr size_t SA_FWD_SMEM = (size_t)(3 * SA_MAXS * SA_LDX + SA_MAXS * SA_LDP) * sizeof(float);
+constexpr size_t SA_BWD_SMEM = (size_t)(4 * SA_MAXS * SA_LDX + 2 * SA_MAXS * SA_LDP) * sizeof(float);
+static_assert(SA_BWD_SMEM <= 227 * 1024, "small-attention backward shared memory");
+
+static bool attn_small_ok(const mst_model_desc& d, int S) {
+  return S <= SA_MAXS && d.d_model / d.n_heads == SA_DH;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // tape: everything the backward needs, per layer
 // ---------------------------------------------------------------------------------------------------------
 struct LayerTape {
@@ -676,25 +860,36 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
     Lin lqkv, lo, lf1, lf2;
     layer_lins(e, l, &lqkv, &lo, &lf1, &lf2);
     if ((rc = linear_fwd(tc, tp.stage, t.x, lqkv, L.qkv_b, nullptr, t.qkv, M, s, "train_qkv"))) return rc;
-    GemmEx sc;  // scores = scale * Q K^T per (seq, head)
-    sc.a = t.qkv; sc.lda = 3 * dm; sc.b = t.qkv + dm; sc.ldb = 3 * dm; sc.trans_b = 1; sc.c = t.p; sc.ldc = S;
-    sc.M = S; sc.N = S; sc.K = dh; sc.alpha = scale; sc.batch = NS; sc.heads = H;
-    sc.a_bs = (long long)S * 3 * dm; sc.a_hs = dh; sc.b_bs = sc.a_bs; sc.b_hs = dh;
-    sc.c_bs = (long long)H * S * S; sc.c_hs = (long long)S * S;
-    if ((rc = gemm_ex(sc, s, "train_scores"))) return rc;
-    const long long rows = (long long)NS * H * S;
-    softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, key_valid, rows, S, H * S);
-    MST_LAUNCHED("train_softmax", s);
-    const float* probs = t.p;
-    if (drop.on()) {
-      if ((rc = dropout(t.p, nullptr, t.pd, rows * S, drop, drop_site(l, 1), s))) return rc;
-      probs = t.pd;
+    if (attn_small_ok(d, S)) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
+        attr_set = true;
+      }
+      attn_small_fwd_kernel<<<dim3(H, NS), 256, SA_FWD_SMEM, s>>>(t.qkv, key_valid, t.p, t.pd, t.ao, S, dm, H, scale, drop,
+                                                                drop_site(l, 1));
+      MST_LAUNCHED("train_attn_small", s);
+    } else {
+      GemmEx sc;  // scores = scale * Q K^T per (seq, head)
+      sc.a = t.qkv; sc.lda = 3 * dm; sc.b = t.qkv + dm; sc.ldb = 3 * dm; sc.trans_b = 1; sc.c = t.p; sc.ldc = S;
+      sc.M = S; sc.N = S; sc.K = dh; sc.alpha = scale; sc.batch = NS; sc.heads = H;
+      sc.a_bs = (long long)S * 3 * dm; sc.a_hs = dh; sc.b_bs = sc.a_bs; sc.b_hs = dh;
+      sc.c_bs = (long long)H * S * S; sc.c_hs = (long long)S * S;
+      if ((rc = gemm_ex(sc, s, "train_scores"))) return rc;
+      const long long rows = (long long)NS * H * S;
+      softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, key_valid, rows, S, H * S);
+      MST_LAUNCHED("train_softmax", s);
+      const float* probs = t.p;
+      if (drop.on()) {
+        if ((rc = dropout(t.p, nullptr, t.pd, rows * S, drop, drop_site(l, 1), s))) return rc;
+        probs = t.pd;
+      }
+      GemmEx pv;  // ao = P V
+      pv.a = probs; pv.lda = S; pv.b = t.qkv + 2 * dm; pv.ldb = 3 * dm; pv.c = t.ao; pv.ldc = dm;
+      pv.M = S; pv.N = dh; pv.K = S; pv.batch = NS; pv.heads = H;
+      pv.a_bs = sc.c_bs; pv.a_hs = sc.c_hs; pv.b_bs = sc.a_bs; pv.b_hs = dh; pv.c_bs = (long long)S * dm; pv.c_hs = dh;
+      if ((rc = gemm_ex(pv, s, "train_pv"))) return rc;
     }
-    GemmEx pv;  // ao = P V
-    pv.a = probs; pv.lda = S; pv.b = t.qkv + 2 * dm; pv.ldb = 3 * dm; pv.c = t.ao; pv.ldc = dm;
-    pv.M = S; pv.N = dh; pv.K = S; pv.batch = NS; pv.heads = H;
-    pv.a_bs = sc.c_bs; pv.a_hs = sc.c_hs; pv.b_bs = sc.a_bs; pv.b_hs = dh; pv.c_bs = (long long)S * dm; pv.c_hs = dh;
-    if ((rc = gemm_ex(pv, s, "train_pv"))) return rc;
     if (drop.on()) {  // z1 = x + dropout1(ao Wo^T + bo)
       if ((rc = linear_fwd(tc, tp.stage, t.ao, lo, L.o_b, nullptr, t.z1, M, s, "train_outproj"))) return rc;
       if ((rc = dropout(t.z1, t.x, t.z1, (long long)M * dm, drop, drop_site(l, 2), s))) return rc;
@@ -798,29 +993,40 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     }
     if ((rc = linear_bwd(tc, w.stage, dz1g, t.ao, lo, nullptr, dao, G.o_w, G.o_b, M, s, "bwd_dao", "bwd_dwo"))) return rc;
     // attention
-    const long long qkv_bs = (long long)S * 3 * dm, pp_bs = (long long)H * S * S, pp_hs = (long long)S * S;
-    GemmEx dp;  // dP = dao V^T
-    dp.a = dao; dp.lda = dm; dp.b = t.qkv + 2 * dm; dp.ldb = 3 * dm; dp.trans_b = 1; dp.c = w.dp; dp.ldc = S;
-    dp.M = S; dp.N = S; dp.K = dh; dp.batch = NS; dp.heads = H;
-    dp.a_bs = (long long)S * dm; dp.a_hs = dh; dp.b_bs = qkv_bs; dp.b_hs = dh; dp.c_bs = pp_bs; dp.c_hs = pp_hs;
-    if ((rc = gemm_ex(dp, s, "bwd_dp"))) return rc;
-    GemmEx dv;  // dV = P^T dao   (the probabilities the forward multiplied with: after dropout)
-    dv.a = drop.on() ? t.pd : t.p; dv.lda = S; dv.a_mode = AX_TRANS; dv.b = dao; dv.ldb = dm; dv.c = w.dqkv + 2 * dm; dv.ldc = 3 * dm;
-    dv.M = S; dv.N = dh; dv.K = S; dv.batch = NS; dv.heads = H;
-    dv.a_bs = pp_bs; dv.a_hs = pp_hs; dv.b_bs = (long long)S * dm; dv.b_hs = dh; dv.c_bs = qkv_bs; dv.c_hs = dh;
-    if ((rc = gemm_ex(dv, s, "bwd_dv"))) return rc;
-    const long long rows = (long long)NS * H * S;
-    if (drop.on() && (rc = dropout(w.dp, nullptr, w.dp, rows * S, drop, drop_site(l, 1), s))) return rc;
-    softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, w.dp, rows, S);
-    MST_LAUNCHED("bwd_softmax", s);
-    GemmEx dq;  // dQ = scale dS K
-    dq.a = w.dp; dq.lda = S; dq.b = t.qkv + dm; dq.ldb = 3 * dm; dq.c = w.dqkv; dq.ldc = 3 * dm; dq.alpha = scale;
-    dq.M = S; dq.N = dh; dq.K = S; dq.batch = NS; dq.heads = H;
-    dq.a_bs = pp_bs; dq.a_hs = pp_hs; dq.b_bs = qkv_bs; dq.b_hs = dh; dq.c_bs = qkv_bs; dq.c_hs = dh;
-    if ((rc = gemm_ex(dq, s, "bwd_dq"))) return rc;
-    GemmEx dk = dq;  // dK = scale dS^T Q
-    dk.a_mode = AX_TRANS; dk.b = t.qkv; dk.c = w.dqkv + dm;
-    if ((rc = gemm_ex(dk, s, "bwd_dk"))) return rc;
+    if (attn_small_ok(d, S)) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_BWD_SMEM));
+        attr_set = true;
+      }
+      attn_small_bwd_kernel<<<dim3(H, NS), 256, SA_BWD_SMEM, s>>>(t.qkv, t.p, t.pd, dao, w.dqkv, S, dm, H, scale, drop,
+                                                                drop_site(l, 1));
+      MST_LAUNCHED("bwd_attn_small", s);
+    } else {
+      const long long qkv_bs = (long long)S * 3 * dm, pp_bs = (long long)H * S * S, pp_hs = (long long)S * S;
+      GemmEx dp;  // dP = dao V^T
+      dp.a = dao; dp.lda = dm; dp.b = t.qkv + 2 * dm; dp.ldb = 3 * dm; dp.trans_b = 1; dp.c = w.dp; dp.ldc = S;
+      dp.M = S; dp.N = S; dp.K = dh; dp.batch = NS; dp.heads = H;
+      dp.a_bs = (long long)S * dm; dp.a_hs = dh; dp.b_bs = qkv_bs; dp.b_hs = dh; dp.c_bs = pp_bs; dp.c_hs = pp_hs;
+      if ((rc = gemm_ex(dp, s, "bwd_dp"))) return rc;
+      GemmEx dv;  // dV = P^T dao   (the probabilities the forward multiplied with: after dropout)
+      dv.a = drop.on() ? t.pd : t.p; dv.lda = S; dv.a_mode = AX_TRANS; dv.b = dao; dv.ldb = dm; dv.c = w.dqkv + 2 * dm; dv.ldc = 3 * dm;
+      dv.M = S; dv.N = dh; dv.K = S; dv.batch = NS; dv.heads = H;
+      dv.a_bs = pp_bs; dv.a_hs = pp_hs; dv.b_bs = (long long)S * dm; dv.b_hs = dh; dv.c_bs = qkv_bs; dv.c_hs = dh;
+      if ((rc = gemm_ex(dv, s, "bwd_dv"))) return rc;
+      const long long rows = (long long)NS * H * S;
+      if (drop.on() && (rc = dropout(w.dp, nullptr, w.dp, rows * S, drop, drop_site(l, 1), s))) return rc;
+      softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, w.dp, rows, S);
+      MST_LAUNCHED("bwd_softmax", s);
+      GemmEx dq;  // dQ = scale dS K
+      dq.a = w.dp; dq.lda = S; dq.b = t.qkv + dm; dq.ldb = 3 * dm; dq.c = w.dqkv; dq.ldc = 3 * dm; dq.alpha = scale;
+      dq.M = S; dq.N = dh; dq.K = S; dq.batch = NS; dq.heads = H;
+      dq.a_bs = pp_bs; dq.a_hs = pp_hs; dq.b_bs = qkv_bs; dq.b_hs = dh; dq.c_bs = qkv_bs; dq.c_hs = dh;
+      if ((rc = gemm_ex(dq, s, "bwd_dq"))) return rc;
+      GemmEx dk = dq;  // dK = scale dS^T Q
+      dk.a_mode = AX_TRANS; dk.b = t.qkv; dk.c = w.dqkv + dm;
+      if ((rc = gemm_ex(dk, s, "bwd_dk"))) return rc;
+    }
     // QKV: gradient w.r.t. the layer input = dz1 + dqkv Wqkv, dWqkv += dqkv^T x, dbqkv += sum dqkv
     if ((rc = linear_bwd(tc, w.stage, w.dqkv, t.x, lqkv, dz1, gx, G.qkv_w, G.qkv_b, M, s, "bwd_dx", "bwd_dwqkv"))) return rc;
   }
@@ -1165,7 +1371,7 @@ extern "C" int mst_denoiser_backward(mst_engine_t h, const mst_backward_args* ap
 extern "C" int mst_motion_encoder_forward(mst_engine_t h, const float* x, const uint8_t* key_valid, const float* mu_query,
                                           const float* sigma_query, int32_t batch, int32_t n_frames, float* mu_out,
                                           void* tape, size_t tape_bytes, float dropout_p, const uint64_t* dropout_seed,
-                                          void* stream) {
+                                          int32_t use_graph, void* stream) {
   MST_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f && (dropout_p == 0.0f || dropout_seed), "bad dropout arguments");
   Drop drop;
   drop.p = dropout_p;
@@ -1180,24 +1386,34 @@ extern "C" int mst_motion_encoder_forward(mst_engine_t h, const float* x, const 
   MST_CHECK_ARG(B > 0 && T > 0 && S <= d.pe_len, "bad geometry");
   Tape tp;
   MST_CHECK_ARG(tape_bytes >= carve_tape(d, B, S, tape, &tp), "tape too small");
-  cudaStream_t s = (cudaStream_t)stream;
-  GemmEx g;  // tokens[(b, t+2)] = x[b,:,t] in_w^T + in_b
-  g.a = x; g.a_mode = AX_MOTION_TOK; g.T = T; g.tok_off = 2; g.b = e->in_w; g.ldb = d.n_feats; g.trans_b = 1;
-  g.bias = e->in_b; g.c = tp.l[0].x; g.ldc = dm; g.M = B * S; g.N = dm; g.K = d.n_feats;
-  if ((rc = gemm_ex(g, s, "menc_inproj"))) return rc;
-  menc_tokens_kernel<<<B * S, 128, 0, s>>>(mu_query, sigma_query, e->pe, tp.l[0].x, S, dm);
-  MST_LAUNCHED("menc_tokens", s);
-  if (drop.on() && (rc = dropout(tp.l[0].x, nullptr, tp.l[0].x, (long long)B * S * dm, drop, 0, s))) return rc;
-  if ((rc = encoder_forward_tape(e, tp, B, S, key_valid, drop, s))) return rc;
-  MST_CUDA_OK(cudaMemcpy2DAsync(mu_out, (size_t)dm * 4, tp.x_out, (size_t)S * dm * 4, (size_t)dm * 4, B,
-                                cudaMemcpyDeviceToDevice, s));
-  return MST_OK;
+  uint32_t pbits;
+  memcpy(&pbits, &dropout_p, 4);
+  const void* kp[] = {x, key_valid, mu_query, sigma_query, mu_out, tape, dropout_seed};
+  const size_t kn[] = {(size_t)B, (size_t)T, tape_bytes, (size_t)pbits};
+  uint64_t key = fnv1a(kp, sizeof(kp), 1469598103934665603ull);
+  key = fnv1a(kn, sizeof(kn), key);
+  key = fnv1a(e, sizeof(Engine), key) ^ 0x3eull;
+  return run_graphed(use_graph != 0, key, (cudaStream_t)stream, [&](cudaStream_t s) -> int {
+    int rc;
+    GemmEx g;  // tokens[(b, t+2)] = x[b,:,t] in_w^T + in_b
+    g.a = x; g.a_mode = AX_MOTION_TOK; g.T = T; g.tok_off = 2; g.b = e->in_w; g.ldb = d.n_feats; g.trans_b = 1;
+    g.bias = e->in_b; g.c = tp.l[0].x; g.ldc = dm; g.M = B * S; g.N = dm; g.K = d.n_feats;
+    if ((rc = gemm_ex(g, s, "menc_inproj"))) return rc;
+    menc_tokens_kernel<<<B * S, 128, 0, s>>>(mu_query, sigma_query, e->pe, tp.l[0].x, S, dm);
+    MST_LAUNCHED("menc_tokens", s);
+    if (drop.on() && (rc = dropout(tp.l[0].x, nullptr, tp.l[0].x, (long long)B * S * dm, drop, 0, s))) return rc;
+    if ((rc = encoder_forward_tape(e, tp, B, S, key_valid, drop, s))) return rc;
+    MST_CUDA_OK(cudaMemcpy2DAsync(mu_out, (size_t)dm * 4, tp.x_out, (size_t)S * dm * 4, (size_t)dm * 4, B,
+                                  cudaMemcpyDeviceToDevice, s));
+    return MST_OK;
+  });
 }
 
 // d_x [B,F,T] = d mu / d x (all MotionEncoder parameters are frozen: the reference only needs the input gradient)
 extern "C" int mst_motion_encoder_backward(mst_engine_t h, const float* d_mu, int32_t batch, int32_t n_frames, float* d_x,
                                            void* tape, size_t tape_bytes, void* scratch, size_t scratch_bytes,
-                                           float dropout_p, const uint64_t* dropout_seed, void* stream) {
+                                           float dropout_p, const uint64_t* dropout_seed, int32_t use_graph,
+                                           void* stream) {
   MST_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f && (dropout_p == 0.0f || dropout_seed), "bad dropout arguments");
   Drop drop;
   drop.p = dropout_p;
@@ -1213,18 +1429,27 @@ extern "C" int mst_motion_encoder_backward(mst_engine_t h, const float* d_mu, in
   BwdScratch w;
   MST_CHECK_ARG(tape_bytes >= carve_tape(d, B, S, tape, &tp), "tape too small");
   MST_CHECK_ARG(scratch_bytes >= carve_bwd(d, B, S, scratch, &w), "scratch too small");
-  cudaStream_t s = (cudaStream_t)stream;
-  float* g = tp.x_out;
-  MST_CUDA_OK(cudaMemsetAsync(g, 0, (size_t)B * S * dm * 4, s));
-  MST_CUDA_OK(cudaMemcpy2DAsync(g, (size_t)S * dm * 4, d_mu, (size_t)dm * 4, (size_t)dm * 4, B, cudaMemcpyDeviceToDevice, s));
-  static const mst_layer_grads kNoGrads[MST_MAX_LAYERS] = {};
-  float* gx = nullptr;
-  if ((rc = encoder_backward(e, tp, kNoGrads, B, S, g, w, &gx, drop, s))) return rc;
-  if (drop.on() && (rc = dropout(gx, nullptr, gx, (long long)B * S * dm, drop, 0, s))) return rc;
-  GemmEx gi;
-  gi.a = gx; gi.lda = dm; gi.a_mode = AX_TOKROWS; gi.T = T; gi.tok_off = 2; gi.b = e->in_w; gi.ldb = d.n_feats;
-  gi.c = d_x; gi.c_mode = CX_MOTION; gi.M = B * T; gi.N = d.n_feats; gi.K = dm;
-  return gemm_ex(gi, s, "menc_bwd_inproj");
+  uint32_t pbits;
+  memcpy(&pbits, &dropout_p, 4);
+  const void* kp[] = {d_mu, d_x, tape, scratch, dropout_seed};
+  const size_t kn[] = {(size_t)B, (size_t)T, tape_bytes, scratch_bytes, (size_t)pbits};
+  uint64_t key = fnv1a(kp, sizeof(kp), 1469598103934665603ull);
+  key = fnv1a(kn, sizeof(kn), key);
+  key = fnv1a(e, sizeof(Engine), key) ^ 0x9dull;
+  return run_graphed(use_graph != 0, key, (cudaStream_t)stream, [&](cudaStream_t s) -> int {
+    int rc;
+    float* g = tp.x_out;
+    MST_CUDA_OK(cudaMemsetAsync(g, 0, (size_t)B * S * dm * 4, s));
+    MST_CUDA_OK(cudaMemcpy2DAsync(g, (size_t)S * dm * 4, d_mu, (size_t)dm * 4, (size_t)dm * 4, B, cudaMemcpyDeviceToDevice, s));
+    static const mst_layer_grads kNoGrads[MST_MAX_LAYERS] = {};
+    float* gx = nullptr;
+    if ((rc = encoder_backward(e, tp, kNoGrads, B, S, g, w, &gx, drop, s))) return rc;
+    if (drop.on() && (rc = dropout(gx, nullptr, gx, (long long)B * S * dm, drop, 0, s))) return rc;
+    GemmEx gi;
+    gi.a = gx; gi.lda = dm; gi.a_mode = AX_TOKROWS; gi.T = T; gi.tok_off = 2; gi.b = e->in_w; gi.ldb = d.n_feats;
+    gi.c = d_x; gi.c_mode = CX_MOTION; gi.M = B * T; gi.N = d.n_feats; gi.K = dm;
+    return gemm_ex(gi, s, "menc_bwd_inproj");
+  });
 }
 
 __global__ void __launch_bounds__(256) dropout_scale_kernel(float* out, long long n4, mst::Drop d, uint32_t site) {

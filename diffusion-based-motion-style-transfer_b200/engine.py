@@ -242,29 +242,34 @@ class Engine:
 
     def motion_encoder_forward(self, x: torch.Tensor, key_valid: Optional[torch.Tensor], mu_query: torch.Tensor,
                                sigma_query: torch.Tensor, dropout_p: float = 0.0,
-                               dropout_seed: Optional[torch.Tensor] = None):
+                               dropout_seed: Optional[torch.Tensor] = None, tape: Optional[torch.Tensor] = None,
+                               mu: Optional[torch.Tensor] = None, use_graph: bool = False):
         """MotionEncoder.forward on this engine's stack.  Returns (mu [B,d], tape)."""
         B, T = x.shape[0], x.shape[-1]
-        tape_bytes, _ = self.train_sizes(B, T + 2)
-        tape = torch.empty(tape_bytes, dtype=torch.uint8, device=self.device)
-        mu = torch.empty(B, self.d_model, dtype=torch.float32, device=self.device)
+        if tape is None:
+            tape_bytes, _ = self.train_sizes(B, T + 2)
+            tape = torch.empty(tape_bytes, dtype=torch.uint8, device=self.device)
+        if mu is None:
+            mu = torch.empty(B, self.d_model, dtype=torch.float32, device=self.device)
         L.check(self.lib.mst_motion_encoder_forward(
             self._h, _ptr(x, name="x"), _ptr(key_valid, torch.uint8, "key_valid"), _ptr(mu_query, name="muQuery"),
             _ptr(sigma_query, name="sigmaQuery"), B, T, mu.data_ptr(), tape.data_ptr(), tape.numel(), float(dropout_p),
-            _ptr(dropout_seed, torch.int64, "dropout_seed") if dropout_p > 0 else None, _stream_ptr()),
-            "mst_motion_encoder_forward")
+            _ptr(dropout_seed, torch.int64, "dropout_seed") if dropout_p > 0 else None, int(bool(use_graph)),
+            _stream_ptr()), "mst_motion_encoder_forward")
         return mu, tape
 
     def motion_encoder_backward(self, d_mu: torch.Tensor, tape: torch.Tensor, shape, dropout_p: float = 0.0,
-                                dropout_seed: Optional[torch.Tensor] = None):
+                                dropout_seed: Optional[torch.Tensor] = None, d_x: Optional[torch.Tensor] = None,
+                                use_graph: bool = False):
         B, T = shape[0], shape[-1]
         _, scratch_bytes = self.train_sizes(B, T + 2)
         scratch = self._scratch(scratch_bytes)
-        d_x = torch.empty(shape, dtype=torch.float32, device=self.device)
+        if d_x is None:
+            d_x = torch.empty(shape, dtype=torch.float32, device=self.device)
         L.check(self.lib.mst_motion_encoder_backward(
             self._h, _ptr(d_mu, name="d_mu"), B, T, d_x.data_ptr(), tape.data_ptr(), tape.numel(), scratch.data_ptr(),
             scratch.numel(), float(dropout_p), _ptr(dropout_seed, torch.int64, "dropout_seed") if dropout_p > 0 else None,
-            _stream_ptr()), "mst_motion_encoder_backward")
+            int(bool(use_graph)), _stream_ptr()), "mst_motion_encoder_backward")
         return d_x
 
 

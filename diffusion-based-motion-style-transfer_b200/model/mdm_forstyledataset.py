@@ -224,6 +224,22 @@ class _DenoiserGradFn(torch.autograd.Function):
         return (None, d_x, None, None, None) + tuple(g for lg in grads for g in lg.values())
 
 
+class _MencSlot:
+    """Persistent buffers of one MotionEncoder forward / backward (trainer mode: CUDA-graph replay)."""
+
+    def __init__(self, eng, shape):
+        dev, B, T = eng.device, shape[0], shape[-1]
+        tape_bytes, _ = eng.train_sizes(B, T + 2)
+        self.tape = torch.empty(tape_bytes, dtype=torch.uint8, device=dev)
+        self.x = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.key_valid = torch.empty(B, T + 2, dtype=torch.uint8, device=dev)
+        self.mu = torch.empty(B, eng.d_model, dtype=torch.float32, device=dev)
+        self.d_mu = torch.empty(B, eng.d_model, dtype=torch.float32, device=dev)
+        self.d_x = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.seed = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.used = False
+
+
 class _MotionEncoderGradFn(torch.autograd.Function):
     """mu of MotionEncoder.forward with a gradient path to its input motion only (its parameters are frozen)."""
 
@@ -231,23 +247,40 @@ class _MotionEncoderGradFn(torch.autograd.Function):
     def forward(ctx, enc, x, key_valid):
         eng = enc.mst_engine(x.device, precision=enc.mst_train_prec())
         p = ctx.drop_p = enc.mst_dropout_p()
-        if p > 0:
-            key = enc.mst_draw_dropout_key()
-            ctx.drop_seed = torch.arange(key, key + x.shape[0], dtype=torch.int64).to(x.device)
-        else:
-            ctx.drop_seed = None
-        mu, tape = eng.motion_encoder_forward(x, key_valid, enc.muQuery.detach().reshape(-1).contiguous(),
-                                              enc.sigmaQuery.detach().reshape(-1).contiguous(), dropout_p=p,
-                                              dropout_seed=ctx.drop_seed)
-        ctx.eng, ctx.tape, ctx.shape = eng, tape, tuple(x.shape)
+        key = enc.mst_draw_dropout_key() if p > 0 else 0
+        mq, sq = enc.muQuery.detach().reshape(-1).contiguous(), enc.sigmaQuery.detach().reshape(-1).contiguous()
+        slot = ctx.slot = enc._mst_menc_acquire(eng, tuple(x.shape))
+        ctx.eng, ctx.shape = eng, tuple(x.shape)
+        if slot is not None:
+            slot.x.copy_(x)
+            slot.key_valid.copy_(key_valid)
+            if p > 0:
+                slot.seed.copy_(torch.arange(key, key + x.shape[0], dtype=torch.int64), non_blocking=True)
+            ctx.queries = (mq, sq)   # keep the operand tensors alive: the captured graph reads their addresses
+            eng.motion_encoder_forward(slot.x, slot.key_valid, mq, sq, dropout_p=p, dropout_seed=slot.seed,
+                                       tape=slot.tape, mu=slot.mu, use_graph=True)
+            ctx.tape, ctx.drop_seed = slot.tape, slot.seed
+            return slot.mu.clone()
+        ctx.drop_seed = torch.arange(key, key + x.shape[0], dtype=torch.int64).to(x.device) if p > 0 else None
+        mu, tape = eng.motion_encoder_forward(x, key_valid, mq, sq, dropout_p=p, dropout_seed=ctx.drop_seed)
+        ctx.tape = tape
         return mu
 
     @staticmethod
     def backward(ctx, d_mu):
         if ctx.tape is None:
             raise RuntimeError("the mst activation tape of this forward was already consumed by a backward pass")
-        d_x = ctx.eng.motion_encoder_backward(d_mu.float().contiguous(), ctx.tape, ctx.shape, dropout_p=ctx.drop_p,
-                                              dropout_seed=ctx.drop_seed) if ctx.needs_input_grad[1] else None
+        d_x = None
+        if ctx.needs_input_grad[1]:
+            slot = ctx.slot
+            if slot is not None:
+                slot.d_mu.copy_(d_mu)
+                ctx.eng.motion_encoder_backward(slot.d_mu, slot.tape, ctx.shape, dropout_p=ctx.drop_p,
+                                                dropout_seed=ctx.drop_seed, d_x=slot.d_x, use_graph=True)
+                d_x = slot.d_x.clone()
+            else:
+                d_x = ctx.eng.motion_encoder_backward(d_mu.float().contiguous(), ctx.tape, ctx.shape, dropout_p=ctx.drop_p,
+                                                      dropout_seed=ctx.drop_seed)
         ctx.tape = None
         return None, d_x, None
 
@@ -336,6 +369,23 @@ class NativeDenoiser(nn.Module):
             for slot in ent[0]:
                 slot.reset()
             ent[1] = 0
+        for slot in self.__dict__.get("_mst_menc_slots", {}).values():
+            slot.used = False
+
+    def _mst_menc_acquire(self, eng, shape):
+        """Persistent MotionEncoder buffers for this input shape (trainer mode, one forward per step), else None."""
+        if not self.mst_tape_pool:
+            return None
+        slots = self.__dict__.setdefault("_mst_menc_slots", {})
+        slot = slots.get((id(eng), shape))
+        if slot is None:
+            if len(slots) >= 4:
+                return None
+            slot = slots[(id(eng), shape)] = _MencSlot(eng, shape)
+        if slot.used:
+            return None      # a second forward of this shape in the same step: plain path
+        slot.used = True
+        return slot
 
     def mst_flush_backward(self):
         """Run the batched backward passes that are still waiting for a sibling forward's gradient (a forward whose

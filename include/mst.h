@@ -332,10 +332,11 @@ int mst_abi_sizes_train(size_t* layer_grads, size_t* backward_args);
  * parameter is frozen in the finetune loss.                                 */
 int mst_motion_encoder_forward(mst_engine_t e, const float* x, const uint8_t* key_valid, const float* mu_query,
                                const float* sigma_query, int32_t batch, int32_t n_frames, float* mu_out, void* tape,
-                               size_t tape_bytes, float dropout_p, const uint64_t* dropout_seed, void* stream);
+                               size_t tape_bytes, float dropout_p, const uint64_t* dropout_seed, int32_t use_graph,
+                               void* stream);
 int mst_motion_encoder_backward(mst_engine_t e, const float* d_mu, int32_t batch, int32_t n_frames, float* d_x,
                                 void* tape, size_t tape_bytes, void* scratch, size_t scratch_bytes, float dropout_p,
-                                const uint64_t* dropout_seed, void* stream);
+                                const uint64_t* dropout_seed, int32_t use_graph, void* stream);
 
 /* Test hook: the multiplier (0 or 1/(1-p)) the training kernels apply to element i of dropout site `site`
  * (0 = token sequence after the positional encoding; 8*(layer+1) + {1: attention probabilities [seq][head][q][k],
