@@ -14,3 +14,9 @@ echo "ncu update rc=$?"
 python tools/ncu_raw_summary.py gpurun_out/prof_step.ncu-rep > gpurun_out/prof_step_summary.txt 2>&1
 python tools/ncu_raw_summary.py gpurun_out/prof_update.ncu-rep > gpurun_out/prof_update_summary.txt 2>&1
 du -sh gpurun_out; cat gpurun_out/profile_update.log; tail -12 gpurun_out/profile_step.log
+# the finetune step's kernels (eager launches): the tensor-core training GEMM, the fused short-sequence attention, conversions
+MST_TRAIN_GRAPH=0 timeout 200 python tools/bench_finetune.py --sg 1 --steps 1 --warmup 1 > gpurun_out/ft_plain.log 2>&1 || { echo "plain finetune run failed"; tail -20 gpurun_out/ft_plain.log; exit 1; }
+MST_TRAIN_GRAPH=0 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:tc_gemm_kernel|attn_small|layernorm_bwd" -s 40 -c 8 -o gpurun_out/prof_finetune python tools/bench_finetune.py --sg 1 --steps 1 --warmup 1 > gpurun_out/ncu_finetune.log 2>&1
+echo "ncu finetune rc=$?"
+python tools/ncu_raw_summary.py gpurun_out/prof_finetune.ncu-rep > gpurun_out/prof_finetune_summary.txt 2>&1
+du -sh gpurun_out
