@@ -623,6 +623,7 @@ __device__ __forceinline__ void smem_gemm(const float* a, int lda, const float* 
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+#pragma unroll 4
   for (int k = 0; k < K; ++k) {
     float av[TM], bv[TN];
 #pragma unroll
