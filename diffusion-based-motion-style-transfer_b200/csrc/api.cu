@@ -357,12 +357,12 @@ extern "C" int mst_time_embed(mst_engine_t h, const int64_t* t_dev, int n, float
   GemmF32Params p;
   p.a = e->pe; p.lda = d; p.a_mode = A_GATHER_ROWS; p.gather = t_dev;
   p.w = e->t_w1; p.ldw = d; p.bias = e->t_b1; p.c = hid; p.ldc = d;
-  p.M = n; p.N = d; p.K = d; p.epi = EPI_SILU;
+  p.M = n; p.N = d; p.K = d; p.epi = EPI_SILU; p.row_invariant = 1;
   int rc = gemm_f32(p, s);
   if (rc) return rc;
   GemmF32Params q;
   q.a = hid; q.lda = d; q.w = e->t_w2; q.ldw = d; q.bias = e->t_b2; q.c = out_dev; q.ldc = d;
-  q.M = n; q.N = d; q.K = d; q.epi = EPI_PLAIN;
+  q.M = n; q.N = d; q.K = d; q.epi = EPI_PLAIN; q.row_invariant = 1;
   return gemm_f32(q, s);
 }
 
@@ -375,7 +375,7 @@ extern "C" int mst_text_embed(mst_engine_t h, const float* feat_dev, int n, floa
   const int d = e->desc.d_model;
   GemmF32Params p;
   p.a = feat_dev; p.lda = e->desc.clip_dim; p.w = e->txt_w; p.ldw = e->desc.clip_dim; p.bias = e->txt_b;
-  p.c = out_dev; p.ldc = d; p.M = n; p.N = d; p.K = e->desc.clip_dim; p.epi = EPI_PLAIN;
+  p.c = out_dev; p.ldc = d; p.M = n; p.N = d; p.K = e->desc.clip_dim; p.epi = EPI_PLAIN; p.row_invariant = 1;
   return gemm_f32(p, (cudaStream_t)stream);
 }
 

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) gemm_f32_skinny_kernel(GemmF32Params p) {
 }
 
 int gemm_f32(const GemmF32Params& p, cudaStream_t s) {
-  if ((long long)p.M * p.N <= 65536 && p.M <= 128 && (long long)p.M * p.N * p.K <= (24ll << 20)) {
+  if (p.row_invariant || ((long long)p.M * p.N <= 65536 && p.M <= 128 && (long long)p.M * p.N * p.K <= (24ll << 20))) {
     const long long warps = (long long)p.M * p.N;
     const int blocks = (int)((warps + 7) / 8 < 4096 ? (warps + 7) / 8 : 4096);
     gemm_f32_skinny_kernel<<<blocks, 256, 0, s>>>(p);

@@ -21,6 +21,8 @@ struct GemmF32Params {
   const float* pe = nullptr;        // EPI_INPROJ: positional table [*, N]
   int B = 0, T = 0;                 // A_MOTION / EPI_INPROJ / EPI_OUTPROJ geometry
   int n_pass = 1;                   // EPI_INPROJ: write rows of `n_pass` passes (cond, uncond)
+  int row_invariant = 0;            // 1: always the one-warp-per-output kernel, so a row's result does not depend on how
+                                    // many rows share the launch (time / text embeddings: bit-identical for any batch split)
 };
 
 int gemm_f32(const GemmF32Params& p, cudaStream_t s);
