@@ -43,10 +43,12 @@ __device__ __forceinline__ U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
 __device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  // SFU forms (lg2 / sin / cos approximations, ~1e-6 absolute on the result): the accurate logf / sincospif sequences made
+  // the update kernel issue-bound at B >= 2048 (73 % issue-active, 0.77 of the HBM copy peak; profiles/r01e_*)
   float u1 = u01(a), u2 = u01(b);
-  float rad = sqrtf(-2.0f * logf(u1));
+  float rad = sqrtf(-2.0f * __logf(u1));
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(6.283185307179586f * u2, &s, &c);
   n0 = rad * c;
   n1 = rad * s;
 }
