@@ -488,3 +488,37 @@ def test_batched_backward_of_sequential_forwards(mu, FI, tmp_path_factory):
         loss = (outs[0] * ds[0].to(DEV)).sum() + (outs[2] * ds[2].to(DEV)).sum()
         trainer.backward(loss)
         assert float(pooled.seqTransEncoder.layers[0].linear1.weight.grad.abs().sum()) > 0
+
+
+def test_backward_humanml_feature_width(mu):
+    """F = 263 (humanml) and T = 196: the taped forward / backward of an MDM whose front end is frozen (only the feature
+    width of the in / out projections changes; S = 197 takes the general attention path)."""
+    from mst_b200.model.mdm_forstyledataset import MDM
+
+    class A(Args):
+        dataset = "humanml"
+
+    state = mdm_state_dict(263, seed=3)
+    model = MDM(**mu.get_transfer_args(A()))
+    model.load_state_dict(state, strict=False)
+    model.to(DEV).eval()
+    for name, p in model.named_parameters():
+        p.requires_grad_(name.startswith("seqTransEncoder."))
+    model.mst_train_precision = "fp32"
+    B, T = 2, 196
+    g = torch.Generator().manual_seed(9)
+    x, d_out = torch.randn(B, 263, 1, T, generator=g), torch.randn(B, 263, 1, T, generator=g)
+    t = torch.tensor([10, 900])
+    feat = text_features(["a", "b"])
+    w_enc = {k: v.clone().requires_grad_(True) for k, v in state.items() if k.startswith("seqTransEncoder.")}
+    xo = x.clone().requires_grad_(True)
+    out_o = OD.mdm_forward(state, xo, t, feat, enc_w=w_enc)
+    (out_o * d_out).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    out = model(xg, t.to(DEV), {"text_feat": feat.to(DEV), "text": ["x"] * B})
+    assert relerr(out.detach(), out_o.detach()) < 1e-4
+    (out * d_out.to(DEV)).sum().backward()
+    assert relerr(xg.grad, xo.grad) < TOL
+    for name, p in model.named_parameters():
+        if p.requires_grad:
+            assert relerr(p.grad, w_enc[name].grad) < TOL, name

@@ -281,7 +281,18 @@ def test_tc_gemm_fused_epilogues(L, epi, m, n, k):
     assert relerr(out.float(), want) < 6e-3
 
 
-@pytest.mark.parametrize("n_seqs,S", [(1, 197), (5, 197), (3, 77), (2, 61), (4, 21), (2, 128), (2, 129)])
+def test_tc_attention_longest_sequence_and_limit(K, L, state):
+    """S = 208 tokens is the longest sequence the tcgen05 attention holds in one TMEM slot; 209 must fail loudly."""
+    lib = L.load()
+    eng = _engine(K, state, "bf16")
+    qkv = _rand((2 * 209, 1536), 12).to(DEV).bfloat16().contiguous()
+    out = torch.empty(2 * 209, 512, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="208"):
+        L.check(lib.mst_test_attention_bf16(eng._h, qkv.data_ptr(), out.data_ptr(), 2, 209, None, 0,
+                                            torch.cuda.current_stream().cuda_stream))
+
+
+@pytest.mark.parametrize("n_seqs,S", [(1, 197), (5, 197), (3, 77), (2, 61), (4, 21), (2, 128), (2, 129), (3, 208), (2, 1)])
 def test_tc_attention_bf16(K, L, state, n_seqs, S):
     lib = L.load()
     eng = _engine(K, state, "bf16")
