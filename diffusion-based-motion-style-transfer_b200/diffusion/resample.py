@@ -21,20 +21,22 @@ class ScheduleSampler(ABC):
         """numpy array of positive weights, one per diffusion step"""
 
     def sample(self, batch_size, device, data_range=None):
-        """(timesteps int64 [batch], importance weights fp32 [batch]); ``data_range`` restricts the support
-        (the finetune loop passes range(num_timesteps - skip), training_loop.py:242-244)."""
-        w = self.weights()
-        p = w / np.sum(w)
+        """(timesteps int64 [batch], importance weights fp32 [batch]).  ``data_range`` restricts the support to those
+        steps (the finetune loop passes range(num_timesteps - skip), training_loop.py:242-244).  One
+        ``np.random.choice`` call with the normalised weights, exactly as the reference draws them (:42-63), so a seeded
+        ``np.random`` reproduces its timesteps."""
+        weights_all = np.asarray(self.weights(), dtype=np.float64)
         if data_range is None:
-            indices_np = np.random.choice(len(p), size=(batch_size,), p=p)
+            support = len(weights_all)
+            prob = weights_all / weights_all.sum()
         else:
-            w_1 = self.weights()[data_range]
-            p = w_1 / np.sum(w_1)
-            indices_np = np.random.choice(data_range, size=(batch_size,), p=p)
-        indices = th.from_numpy(indices_np).long().to(device)
-        weights_np = 1 / (len(p) * p[indices_np])
-        weights = th.from_numpy(weights_np).float().to(device)
-        return indices, weights
+            support = data_range
+            restricted = weights_all[data_range]
+            prob = restricted / restricted.sum()
+        drawn = np.random.choice(support, size=(batch_size,), p=prob)
+        timesteps = th.from_numpy(drawn).long().to(device)
+        importance = th.from_numpy(1 / (len(prob) * prob[drawn])).float().to(device)
+        return timesteps, importance
 
 
 class UniformSampler(ScheduleSampler):

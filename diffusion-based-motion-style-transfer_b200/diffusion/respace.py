@@ -48,18 +48,16 @@ class SpacedDiffusion(GaussianDiffusion):
     """Diffusion over a subset of the base process' timesteps (reference respace.py:64-115)."""
 
     def __init__(self, use_timesteps, **kwargs):
+        base_betas = np.asarray(kwargs["betas"], dtype=np.float64)
+        self.original_num_steps = len(base_betas)
         self.use_timesteps = set(use_timesteps)
-        self.timestep_map = []
-        self.original_num_steps = len(kwargs["betas"])
-        base = GaussianDiffusion(**kwargs)
-        prev = 1.0
-        new_betas = []
-        for i, abar in enumerate(base.alphas_cumprod):
-            if i in self.use_timesteps:
-                new_betas.append(1 - abar / prev)
-                prev = abar
-                self.timestep_map.append(i)
-        kwargs["betas"] = np.array(new_betas)
+        # retained steps in increasing order; beta'_j = 1 - abar[i_j] / abar[i_{j-1}] with abar[i_{-1}] = 1.  Same float64
+        # operations, element by element, as the reference's loop over base_diffusion.alphas_cumprod (respace.py:73-87).
+        kept = np.array(sorted(t for t in self.use_timesteps if 0 <= t < self.original_num_steps), dtype=np.int64)
+        abar = np.cumprod(1.0 - base_betas, axis=0)[kept]
+        abar_before = np.concatenate(([1.0], abar[:-1]))
+        self.timestep_map = [int(t) for t in kept]
+        kwargs["betas"] = 1 - abar / abar_before
         super().__init__(**kwargs)
         self._map_dev = {}
 

@@ -17,19 +17,13 @@ class ClassifierFreeSampleModel(nn.Module):
 
     def __init__(self, model):
         super().__init__()
-        self.model = model  # the actual denoiser
-        assert self.model.cond_mask_prob > 0, \
-            'Cannot run a guided diffusion on a model that has not been trained with no conditions'
-        # pointers to the inner model (reference cfg_sampler.py:17-25)
-        try:
-            self.rot2xyz = self.model.rot2xyz
-        except Exception:
-            self.rot2xyz = None
-        self.translation = self.model.translation
-        self.njoints = self.model.njoints
-        self.nfeats = self.model.nfeats
-        self.data_rep = self.model.data_rep
-        self.cond_mode = self.model.cond_mode
+        if not model.cond_mask_prob > 0:  # the reference asserts the same (cfg_sampler.py:12-13)
+            raise AssertionError('Cannot run a guided diffusion on a model that has not been trained with no conditions')
+        self.model = model
+        # what callers read off the wrapper instead of the wrapped denoiser (reference cfg_sampler.py:17-25)
+        self.rot2xyz = getattr(model, "rot2xyz", None)
+        for name in ("translation", "njoints", "nfeats", "data_rep", "cond_mode"):
+            setattr(self, name, getattr(model, name))
 
     def forward(self, x, timesteps, y=None):
         cond_mode = self.model.cond_mode
