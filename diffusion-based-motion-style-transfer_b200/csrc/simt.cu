@@ -60,6 +60,8 @@ __device__ __forceinline__ void store_c(const GemmF32Params& p, int m, int n, fl
 }
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32Params p) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -115,6 +117,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32Params p) {
 // Few output rows (time / text embedding of a handful of samples, the B=1 style example of the finetune step): the
 // 128 x 128 tiling would run on a handful of CTAs with a long serial k-loop; one warp per output element instead.
 __global__ void __launch_bounds__(256) gemm_f32_skinny_kernel(GemmF32Params p) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   const int lane = threadIdx.x & 31;
   const long long total = (long long)p.M * p.N;
   for (long long o = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; o < total;
@@ -132,12 +136,12 @@ int gemm_f32(const GemmF32Params& p, cudaStream_t s) {
   if (p.row_invariant || ((long long)p.M * p.N <= 65536 && p.M <= 128 && (long long)p.M * p.N * p.K <= (24ll << 20))) {
     const long long warps = (long long)p.M * p.N;
     const int blocks = (int)((warps + 7) / 8 < 4096 ? (warps + 7) / 8 : 4096);
-    gemm_f32_skinny_kernel<<<blocks, 256, 0, s>>>(p);
+    MST_CUDA_OK(launch_pdl(gemm_f32_skinny_kernel, dim3(blocks), dim3(256), 0, s, p));
     MST_LAUNCHED("gemm_f32_skinny", s);
     return MST_OK;
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-  gemm_f32_kernel<<<grid, 256, 0, s>>>(p);
+  MST_CUDA_OK(launch_pdl(gemm_f32_kernel, grid, dim3(256), 0, s, p));
   MST_LAUNCHED("gemm_f32", s);
   return MST_OK;
 }
@@ -177,6 +181,8 @@ int token0(const Token0Params& p, int n_seqs, cudaStream_t s) {
 __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                             const float* __restrict__ bt, float* __restrict__ y, int M,
                                                             int d) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= M) return;
   const float* xr = x + (int64_t)warp * d;
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
 int layernorm_f32(const float* x, const float* g, const float* b, float* y, int M, int d, cudaStream_t s) {
   if (d % 32 != 0 || d > 1024) return fail(MST_ERR_UNSUPPORTED, "layernorm_f32: d must be a multiple of 32 and <= 1024");
   int warps_per_block = 8;
-  layernorm_f32_kernel<<<ceil_div(M, warps_per_block), warps_per_block * 32, 0, s>>>(x, g, b, y, M, d);
+  MST_CUDA_OK(launch_pdl(layernorm_f32_kernel, dim3(ceil_div(M, warps_per_block)), dim3(warps_per_block * 32), 0, s, x, g, b, y, M, d));
   MST_LAUNCHED("layernorm_f32", s);
   return MST_OK;
 }

@@ -1203,6 +1203,8 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__ src, int rows, int cols, int ld,
                                                        __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_t,
                                                        int rows_pad) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -1223,7 +1225,7 @@ __global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__
 int cvt_bf16(const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, __nv_bfloat16* dst_t, int rows_pad,
              cudaStream_t s) {
   const int rgrid = dst_t ? ceil_div(rows_pad, 32) : ceil_div(rows, 32);
-  cvt_bf16_kernel<<<dim3(ceil_div(cols, 32), rgrid), 256, 0, s>>>(src, rows, cols, ld, dst, dst_t, rows_pad);
+  MST_CUDA_OK(launch_pdl(cvt_bf16_kernel, dim3(ceil_div(cols, 32), rgrid), dim3(256), 0, s, src, rows, cols, ld, dst, dst_t, rows_pad));
   MST_LAUNCHED("cvt_bf16", s);
   return MST_OK;
 }

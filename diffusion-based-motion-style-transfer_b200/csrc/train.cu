@@ -53,6 +53,8 @@ struct GemmEx {
 
 template <int TM>
 __global__ void __launch_bounds__(256) gemm_ex_kernel(GemmEx p) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   constexpr int BT = 16 * TM;  // square tile
   constexpr int BK = 16;
   __shared__ float As[BK][BT + 4];
@@ -169,6 +171,8 @@ __device__ __forceinline__ float gemm_ex_a(const GemmEx& p, const float* a, int 
 // Small problems (the B=1 style example: 77-token sequences, per-head 77 x 77 products): one warp per output element,
 // lanes stride the reduction - hundreds of warps in flight instead of a dozen CTAs with a serial k-loop.
 __global__ void __launch_bounds__(256) gemm_ex_skinny_kernel(GemmEx p) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   const int lane = threadIdx.x & 31;
   const int S = p.T + p.tok_off;
   const long long per = (long long)p.M * p.N, total = per * p.batch * p.heads;
@@ -212,7 +216,7 @@ static int gemm_ex(GemmEx p, cudaStream_t s, const char* name) {
   if ((long long)p.M * p.N * z <= 131072 && (long long)p.M * p.N * z * p.K <= (24ll << 20)) {
     const long long warps = (long long)p.M * p.N * z;
     const int blocks = (int)((warps + 7) / 8 < 8192 ? (warps + 7) / 8 : 8192);
-    gemm_ex_skinny_kernel<<<blocks, 256, 0, s>>>(p);
+    MST_CUDA_OK(launch_pdl(gemm_ex_skinny_kernel, dim3(blocks), dim3(256), 0, s, p));
     MST_LAUNCHED(name, s);
     return MST_OK;
   }
@@ -229,10 +233,10 @@ static int gemm_ex(GemmEx p, cudaStream_t s, const char* name) {
   }
   if (tiles128 >= 120) {
     dim3 grid(ceil_div(p.N, 128), ceil_div(p.M, 128), (unsigned)(z * p.split_k));
-    gemm_ex_kernel<8><<<grid, 256, 0, s>>>(p);
+    MST_CUDA_OK(launch_pdl(gemm_ex_kernel<8>, grid, dim3(256), 0, s, p));
   } else {
     dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64), (unsigned)(z * p.split_k));
-    gemm_ex_kernel<4><<<grid, 256, 0, s>>>(p);
+    MST_CUDA_OK(launch_pdl(gemm_ex_kernel<4>, grid, dim3(256), 0, s, p));
   }
   MST_LAUNCHED(name, s);
   return MST_OK;
@@ -252,6 +256,8 @@ static int pick_split(int M, int N, int K) {
 // rows of scores [rows, S] -> softmax in place; key_valid [n_seqs, S] (1 = attend) or NULL; row -> seq = row / (heads*S)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ p, const uint8_t* __restrict__ key_valid,
                                                            long long rows, int S, int rows_per_seq) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -275,6 +281,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ p
 // dS = P * (dP - sum_j P dP), in place in dP
 __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* __restrict__ p, float* __restrict__ dp,
                                                                long long rows, int S) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -294,11 +302,15 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ u, float* __restrict__ h, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     h[i] = gelu_f(u[i]);
 }
 // du = dh * gelu'(u), in place in dh
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ u, float* __restrict__ dh, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dh[i] *= gelu_grad_f(u[i]);
 }
@@ -346,6 +358,8 @@ __device__ __forceinline__ float4 drop_scale4(const Drop& d, uint32_t site, int 
 // out[i] = in[i] * mask[i] (+ add[i]); n % 4 == 0, all pointers 16-byte aligned; in may alias out
 __global__ void __launch_bounds__(256) dropout_kernel(const float* in, const float* __restrict__ add, float* out, long long n4,
                                                       long long per_seq4, Drop d, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x) {
     const int seq = (int)(v / per_seq4);
     const float4 m = drop_scale4(d, site, seq, v - (long long)seq * per_seq4);
@@ -362,6 +376,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* in, const flo
 // du = dh * mask * gelu'(u), in place in dh
 __global__ void __launch_bounds__(256) gelu_bwd_drop_kernel(const float* __restrict__ u, float* __restrict__ dh, long long n4,
                                                             long long per_seq4, Drop d, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x) {
     const int seq = (int)(v / per_seq4);
     const float4 m = drop_scale4(d, site, seq, v - (long long)seq * per_seq4);
@@ -378,6 +394,8 @@ __global__ void __launch_bounds__(256) gelu_bwd_drop_kernel(const float* __restr
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                             const float* __restrict__ gamma, float* __restrict__ dz,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int d) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   __shared__ float red[8][64];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int per = d / 32;
@@ -443,6 +461,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // out[n] += sum_m x[m*ld + n]
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int ld,
                                                      int rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -463,7 +483,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 static int colsum(const float* x, float* out, int M, int N, int ld, cudaStream_t s) {
   int rows_per_block = 256;
   dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_block));
-  colsum_kernel<<<grid, 256, 0, s>>>(x, out, M, N, ld, rows_per_block);
+  MST_CUDA_OK(launch_pdl(colsum_kernel, grid, dim3(256), 0, s, x, out, M, N, ld, rows_per_block));
   MST_LAUNCHED("colsum", s);
   return MST_OK;
 }
@@ -477,7 +497,7 @@ static int ew_blocks(long long n) {
 static int dropout(const float* in, const float* add, float* out, long long n, const Drop& d, uint32_t site, cudaStream_t s) {
   if (n % (4ll * d.n_seqs) != 0)
     return fail(MST_ERR_UNSUPPORTED, "dropout: per-sequence tensor sizes must be multiples of 4");
-  dropout_kernel<<<ew_blocks(n / 4), 256, 0, s>>>(in, add, out, n / 4, n / 4 / d.n_seqs, d, site);
+  MST_CUDA_OK(launch_pdl(dropout_kernel, dim3(ew_blocks(n / 4)), dim3(256), 0, s, in, add, out, n / 4, n / 4 / d.n_seqs, d, site));
   MST_LAUNCHED("dropout", s);
   return MST_OK;
 }
@@ -487,6 +507,8 @@ static inline uint32_t drop_site(int layer, int which) { return (uint32_t)(8 * (
 // InputProcess(x)) += pe[row]
 __global__ void __launch_bounds__(128) menc_tokens_kernel(const float* __restrict__ q0, const float* __restrict__ q1,
                                                           const float* __restrict__ pe, float* __restrict__ x, int S, int d) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   const int seq = blockIdx.x / S, r = blockIdx.x - seq * S;
   float* xr = x + ((long long)seq * S + r) * d;
   const float* per = pe + (long long)r * d;
@@ -667,6 +689,8 @@ __global__ void __launch_bounds__(256) attn_small_fwd_kernel(const float* __rest
                                                              float* __restrict__ p_out, float* __restrict__ pd_out,
                                                              float* __restrict__ ao, int S, int d_model, int H, float scale,
                                                              Drop drop, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   extern __shared__ float sm[];
   float* Qs = sm;
   float* Ks = Qs + SA_MAXS * SA_LDX;
@@ -725,6 +749,8 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
                                                              const float* __restrict__ pd_in, const float* __restrict__ dao,
                                                              float* __restrict__ dqkv, int S, int d_model, int H, float scale,
                                                              Drop drop, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   extern __shared__ float sm[];
   float* Qs = sm;
   float* Ks = Qs + SA_MAXS * SA_LDX;
@@ -867,8 +893,8 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
         MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
         attr_set = true;
       }
-      attn_small_fwd_kernel<<<dim3(H, NS), 256, SA_FWD_SMEM, s>>>(t.qkv, key_valid, t.p, t.pd, t.ao, S, dm, H, scale, drop,
-                                                                drop_site(l, 1));
+      MST_CUDA_OK(launch_pdl(attn_small_fwd_kernel, dim3(H, NS), dim3(256), SA_FWD_SMEM, s, (const float*)t.qkv, key_valid, t.p, t.pd,
+                             t.ao, S, dm, H, scale, drop, drop_site(l, 1)));
       MST_LAUNCHED("train_attn_small", s);
     } else {
       GemmEx sc;  // scores = scale * Q K^T per (seq, head)
@@ -878,7 +904,7 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
       sc.c_bs = (long long)H * S * S; sc.c_hs = (long long)S * S;
       if ((rc = gemm_ex(sc, s, "train_scores"))) return rc;
       const long long rows = (long long)NS * H * S;
-      softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, key_valid, rows, S, H * S);
+      MST_CUDA_OK(launch_pdl(softmax_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, t.p, key_valid, rows, S, H * S));
       MST_LAUNCHED("train_softmax", s);
       const float* probs = t.p;
       if (drop.on()) {
@@ -899,7 +925,7 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
     }
     if ((rc = layernorm_f32(t.z1, L.ln1_g, L.ln1_b, t.y, M, dm, s))) return rc;
     if ((rc = linear_fwd(tc, tp.stage, t.y, lf1, L.b1, nullptr, t.u, M, s, "train_ffn1"))) return rc;
-    gelu_fwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, t.h, (long long)M * ff);
+    MST_CUDA_OK(launch_pdl(gelu_fwd_kernel, dim3(ew_blocks((long long)M * ff)), dim3(256), 0, s, (const float*)t.u, t.h, (long long)M * ff));
     MST_LAUNCHED("train_gelu", s);
     if (drop.on()) {  // h = dropout(gelu(u)); z2 = y + dropout2(h W2^T + b2)
       if ((rc = dropout(t.h, nullptr, t.h, (long long)M * ff, drop, drop_site(l, 3), s))) return rc;
@@ -965,7 +991,7 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     const int ln_blocks = ceil_div(M, 8) < 4 * sm_count() ? ceil_div(M, 8) : 4 * sm_count();
     // LN2
     float* dz2 = spare;
-    layernorm_bwd_kernel<<<ln_blocks, 256, 0, s>>>(gx, t.z2, L.ln2_g, dz2, G.ln2_g, G.ln2_b, M, dm);
+    MST_CUDA_OK(launch_pdl(layernorm_bwd_kernel, dim3(ln_blocks), dim3(256), 0, s, (const float*)gx, (const float*)t.z2, L.ln2_g, dz2, G.ln2_g, G.ln2_b, M, dm));
     MST_LAUNCHED("bwd_ln2", s);
     // FFN2: dh = dz2 W2, dW2 += dz2^T h, db2 += sum dz2   (dropout2: the GEMM path sees the masked gradient)
     const float* dz2g = dz2;
@@ -975,16 +1001,16 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     }
     if ((rc = linear_bwd(tc, w.stage, dz2g, t.h, lf2, nullptr, w.dh, G.w2, G.b2, M, s, "bwd_dh", "bwd_dw2"))) return rc;
     if (drop.on())
-      gelu_bwd_drop_kernel<<<ew_blocks((long long)M * ff / 4), 256, 0, s>>>(t.u, w.dh, (long long)M * ff / 4,
-                                                                            (long long)S * ff / 4, drop, drop_site(l, 3));
+      MST_CUDA_OK(launch_pdl(gelu_bwd_drop_kernel, dim3(ew_blocks((long long)M * ff / 4)), dim3(256), 0, s, (const float*)t.u, w.dh,
+                             (long long)M * ff / 4, (long long)S * ff / 4, drop, drop_site(l, 3)));
     else
-      gelu_bwd_kernel<<<ew_blocks((long long)M * ff), 256, 0, s>>>(t.u, w.dh, (long long)M * ff);
+      MST_CUDA_OK(launch_pdl(gelu_bwd_kernel, dim3(ew_blocks((long long)M * ff)), dim3(256), 0, s, (const float*)t.u, w.dh, (long long)M * ff));
     MST_LAUNCHED("bwd_gelu", s);
     // FFN1: dy = dz2 + du W1 (into gx: the incoming gradient is no longer needed), dW1 += du^T y, db1 += sum du
     if ((rc = linear_bwd(tc, w.stage, w.dh, t.y, lf1, dz2, gx, G.w1, G.b1, M, s, "bwd_dy", "bwd_dw1"))) return rc;
     // LN1
     float* dz1 = spare;  // dz2 is dead
-    layernorm_bwd_kernel<<<ln_blocks, 256, 0, s>>>(gx, t.z1, L.ln1_g, dz1, G.ln1_g, G.ln1_b, M, dm);
+    MST_CUDA_OK(launch_pdl(layernorm_bwd_kernel, dim3(ln_blocks), dim3(256), 0, s, (const float*)gx, (const float*)t.z1, L.ln1_g, dz1, G.ln1_g, G.ln1_b, M, dm));
     MST_LAUNCHED("bwd_ln1", s);
     float* dao = spare2;  // out-proj: dao = dz1 Wo, dWo += dz1^T ao, dbo += sum dz1   (dropout1: masked gradient)
     const float* dz1g = dz1;
@@ -1000,8 +1026,8 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
         MST_CUDA_OK(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_BWD_SMEM));
         attr_set = true;
       }
-      attn_small_bwd_kernel<<<dim3(H, NS), 256, SA_BWD_SMEM, s>>>(t.qkv, t.p, t.pd, dao, w.dqkv, S, dm, H, scale, drop,
-                                                                drop_site(l, 1));
+      MST_CUDA_OK(launch_pdl(attn_small_bwd_kernel, dim3(H, NS), dim3(256), SA_BWD_SMEM, s, (const float*)t.qkv, (const float*)t.p,
+                             (const float*)t.pd, (const float*)dao, w.dqkv, S, dm, H, scale, drop, drop_site(l, 1)));
       MST_LAUNCHED("bwd_attn_small", s);
     } else {
       const long long qkv_bs = (long long)S * 3 * dm, pp_bs = (long long)H * S * S, pp_hs = (long long)S * S;
@@ -1017,7 +1043,7 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
       if ((rc = gemm_ex(dv, s, "bwd_dv"))) return rc;
       const long long rows = (long long)NS * H * S;
       if (drop.on() && (rc = dropout(w.dp, nullptr, w.dp, rows * S, drop, drop_site(l, 1), s))) return rc;
-      softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(t.p, w.dp, rows, S);
+      MST_CUDA_OK(launch_pdl(softmax_bwd_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, (const float*)t.p, w.dp, rows, S));
       MST_LAUNCHED("bwd_softmax", s);
       GemmEx dq;  // dQ = scale dS K
       dq.a = w.dp; dq.lda = S; dq.b = t.qkv + dm; dq.ldb = 3 * dm; dq.c = w.dqkv; dq.ldc = 3 * dm; dq.alpha = scale;
@@ -1400,7 +1426,7 @@ extern "C" int mst_motion_encoder_forward(mst_engine_t h, const float* x, const 
     g.a = x; g.a_mode = AX_MOTION_TOK; g.T = T; g.tok_off = 2; g.b = e->in_w; g.ldb = d.n_feats; g.trans_b = 1;
     g.bias = e->in_b; g.c = tp.l[0].x; g.ldc = dm; g.M = B * S; g.N = dm; g.K = d.n_feats;
     if ((rc = gemm_ex(g, s, "menc_inproj"))) return rc;
-    menc_tokens_kernel<<<B * S, 128, 0, s>>>(mu_query, sigma_query, e->pe, tp.l[0].x, S, dm);
+    MST_CUDA_OK(launch_pdl(menc_tokens_kernel, dim3(B * S), dim3(128), 0, s, mu_query, sigma_query, e->pe, tp.l[0].x, S, dm));
     MST_LAUNCHED("menc_tokens", s);
     if (drop.on() && (rc = dropout(tp.l[0].x, nullptr, tp.l[0].x, (long long)B * S * dm, drop, 0, s))) return rc;
     if ((rc = encoder_forward_tape(e, tp, B, S, key_valid, drop, s))) return rc;
