@@ -14,8 +14,8 @@ import threading
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libmst_b200.so")
-SOURCES = ["api.cu", "update.cu", "simt.cu", "tc_gemm.cu", "tc_attn.cu", "train.cu"]
-HEADERS = ["common.cuh", "simt.cuh", "tc.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "mst.h")]
+SOURCES = ["api.cu", "update.cu", "simt.cu", "tc_gemm.cu", "tc_attn.cu", "train.cu", "text.cu"]
+HEADERS = ["common.cuh", "simt.cuh", "tc.cuh", "tc_ptx.cuh", "smem_gemm.cuh", os.path.join("..", "..", "include", "mst.h")]
 
 MAX_LAYERS = 32
 PREC_FP32, PREC_BF16 = 0, 1
@@ -30,7 +30,9 @@ EXPORTED = [
     "mst_text_embed", "mst_denoiser_forward", "mst_update_step", "mst_q_sample", "mst_cfg_combine",
     "mst_philox_normal", "mst_train_sizes", "mst_denoiser_forward_train", "mst_denoiser_backward", "mst_abi_sizes_train",
     "mst_motion_encoder_forward", "mst_motion_encoder_backward", "mst_masked_l2", "mst_update_step_backward",
-    "mst_adamw_step", "mst_sumsq2", "mst_recover_from_ric", "mst_test_dropout_scale", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
+    "mst_adamw_step", "mst_sumsq2", "mst_recover_from_ric",
+    "mst_clip_text_create", "mst_clip_text_destroy", "mst_abi_sizes_clip_text", "mst_clip_text_packed_weight_bytes",
+    "mst_clip_text_workspace_bytes", "mst_clip_text_load_weights", "mst_clip_text_encode", "mst_test_dropout_scale", "mst_test_gemm_bf16", "mst_test_gemm_epi_bf16", "mst_test_set_gemm_debug", "mst_test_attention_bf16",
 ]
 
 
@@ -89,6 +91,23 @@ class BackwardArgs(C.Structure):
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t), ("use_graph", C.c_int32),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p), ("tape_seqs", C.c_int32), ("tape_seq_offset", C.c_int32),
     ]
+
+
+class ClipTextDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("vocab", "ctx", "width", "n_heads", "n_layers", "d_ff", "d_out", "precision")]
+
+
+_CLIP_LAYER_FIELDS = ("ln1_g", "ln1_b", "qkv_w", "qkv_b", "o_w", "o_b", "ln2_g", "ln2_b", "fc_w", "fc_b", "proj_w", "proj_b")
+
+
+class ClipTextLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _CLIP_LAYER_FIELDS]
+
+
+class ClipTextWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("token_embedding", "positional_embedding", "lnf_g", "lnf_b", "text_projection")] + \
+               [("layers", ClipTextLayer * MAX_LAYERS)]
 
 
 def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
@@ -158,6 +177,13 @@ def _declare(lib):
         "mst_adamw_step": [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.c_float, vp],
         "mst_sumsq2": [vp, vp, i64, vp, vp],
         "mst_recover_from_ric": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "mst_clip_text_create": [vp, vp],
+        "mst_clip_text_destroy": [vp],
+        "mst_abi_sizes_clip_text": [vp, vp],
+        "mst_clip_text_packed_weight_bytes": [vp, vp],
+        "mst_clip_text_workspace_bytes": [vp, i32, vp],
+        "mst_clip_text_load_weights": [vp, vp, vp, sz, vp],
+        "mst_clip_text_encode": [vp, vp, i32, vp, vp, sz, vp],
         "mst_test_gemm_bf16": [vp, vp, vp, vp, i32, i32, i32, vp],
         "mst_test_gemm_epi_bf16": [i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "mst_test_set_gemm_debug": [vp],

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "simt.cuh"
 #include "tc.cuh"
+#include "smem_gemm.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -633,35 +634,6 @@ constexpr int SA_MAXS = 80;          // padded sequence length the tiles cover (
 constexpr int SA_DH = 128;
 constexpr int SA_LDX = SA_DH + 1;    // Q, K, V, dO rows
 constexpr int SA_LDP = SA_MAXS + 1;  // P, dP rows
-
-// C(m, n) = sum_k A(m, k) B(k, n) for m < 16*TM, n < 16*TN (operands zero-padded in shared memory);
-// A(m,k) = TA ? a[k*lda + m] : a[m*lda + k];  B(k,n) = TB ? b[n*ldb + k] : b[k*ldb + n];  thread (ty, tx) owns rows
-// ty + 16 i and columns tx + 16 j and hands every result to `out(m, n, value)`.
-template <bool TA, bool TB, int TM, int TN, typename Out>
-__device__ __forceinline__ void smem_gemm(const float* a, int lda, const float* b, int ldb, int K, Out out) {
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[TM][TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    float av[TM], bv[TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) av[i] = TA ? a[k * lda + ty + 16 * i] : a[(ty + 16 * i) * lda + k];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) bv[j] = TB ? b[(tx + 16 * j) * ldb + k] : b[k * ldb + tx + 16 * j];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-  }
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) out(ty + 16 * i, tx + 16 * j, acc[i][j]);
-}
 
 // rows [0, S) x 128 columns of a global matrix (leading dimension ld) -> smem [SA_MAXS][SA_LDX], rows >= S zero
 __device__ __forceinline__ void sa_load(float* dst, const float* __restrict__ src, int ld, int S) {

@@ -273,6 +273,83 @@ class Engine:
         return d_x
 
 
+class ClipTextEngine:
+    """The CLIP text tower on one GPU (`mst_clip_text_*`, csrc/text.cu)."""
+
+    LAYER_KEYS = L._CLIP_LAYER_FIELDS
+    TOP_KEYS = ("token_embedding", "positional_embedding", "lnf_g", "lnf_b", "text_projection")
+
+    def __init__(self, vocab: int = 49408, ctx: int = 77, width: int = 512, n_heads: int = 8, n_layers: int = 12,
+                 d_ff: Optional[int] = None, d_out: int = 512, precision: Optional[str] = None,
+                 device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mst ClipTextEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        self.precision = precision or default_precision()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.desc = L.ClipTextDesc(vocab, ctx, width, n_heads, n_layers, d_ff or 4 * width, d_out,
+                                   L.PREC_BF16 if self.precision == "bf16" else L.PREC_FP32)
+        h = C.c_void_p()
+        L.check(self.lib.mst_clip_text_create(C.byref(self.desc), C.byref(h)), "mst_clip_text_create")
+        self._h = h
+        self._packed = None
+        self._keep = None
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.mst_clip_text_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def load_weights(self, top: dict, layers: list):
+        """top: TOP_KEYS -> fp32 CUDA tensors; layers: list of dicts keyed by LAYER_KEYS."""
+        w = L.ClipTextWeights()
+        keep = []
+
+        def dev(t):
+            t = t.detach()
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(self.device, torch.float32).contiguous()
+            keep.append(t)
+            return t
+
+        if len(layers) != self.desc.n_layers:
+            raise ValueError(f"expected {self.desc.n_layers} layers, got {len(layers)}")
+        with torch.cuda.device(self.device):
+            for k in self.TOP_KEYS:
+                setattr(w, k, _ptr(dev(top[k]), name=k))
+            for i, lw in enumerate(layers):
+                for k in self.LAYER_KEYS:
+                    setattr(w.layers[i], k, _ptr(dev(lw[k]), name=f"layer{i}.{k}"))
+            nbytes = C.c_size_t()
+            L.check(self.lib.mst_clip_text_packed_weight_bytes(self._h, C.byref(nbytes)))
+            if nbytes.value and (self._packed is None or self._packed.numel() < nbytes.value):
+                self._packed = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            L.check(self.lib.mst_clip_text_load_weights(self._h, C.byref(w),
+                                                        self._packed.data_ptr() if nbytes.value else None, nbytes.value,
+                                                        _stream_ptr()), "mst_clip_text_load_weights")
+        self._keep = keep
+
+    def encode(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens int32 [B, ctx] CUDA -> text features fp32 [B, d_out]."""
+        if tokens.dim() != 2 or tokens.shape[1] != self.desc.ctx:
+            raise ValueError(f"tokens: expected [B, {self.desc.ctx}], got {tuple(tokens.shape)}")
+        B = tokens.shape[0]
+        with torch.cuda.device(self.device):
+            nbytes = C.c_size_t()
+            L.check(self.lib.mst_clip_text_workspace_bytes(self._h, B, C.byref(nbytes)))
+            if self._ws is None or self._ws.numel() < nbytes.value:
+                self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            out = torch.empty(B, self.desc.d_out, dtype=torch.float32, device=self.device)
+            L.check(self.lib.mst_clip_text_encode(self._h, _ptr(tokens, torch.int32, "tokens"), B, out.data_ptr(),
+                                                  self._ws.data_ptr(), self._ws.numel(), _stream_ptr()),
+                    "mst_clip_text_encode")
+        return out
+
+
 class TapeSlot:
     """Persistent buffers for up to ``capacity`` taped forwards of ``B`` sequences x ``T`` frames each, recorded into
     slices of ONE tape.  Every pointer is stable from one training step to the next, so the C side replays the launch

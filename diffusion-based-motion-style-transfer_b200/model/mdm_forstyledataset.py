@@ -125,6 +125,10 @@ def _load_clip(clip_version):
     clip_model.eval()
     for p in clip_model.parameters():
         p.requires_grad = False
+    if os.environ.get("MST_NATIVE_CLIP", "1") != "0":
+        # scope row N1: the text side of the loaded model on the mst kernels (csrc/text.cu); same .encode_text()
+        from .clip_text import CLIPTextTower
+        return CLIPTextTower.from_clip(clip_model)
     return clip_model
 
 
@@ -451,18 +455,21 @@ class NativeDenoiser(nn.Module):
         if clip_model is None:
             raise RuntimeError("no CLIP text encoder is attached to this model (the `clip` package is not installed); "
                                "provide precomputed features as y['text_feat'] with shape [B, clip_dim]")
-        import clip  # type: ignore
+        tokenize = getattr(f, "mst_tokenize", None)  # hook: any callable with clip.tokenize's signature
+        if tokenize is None:
+            import clip  # type: ignore
+            tokenize = clip.tokenize
         device = next(self.parameters()).device
         max_text_len = 20 if self.dataset in ['humanml', 'kit'] else None
         if max_text_len is not None:
             default_context_length = 77
             context_length = max_text_len + 2
-            texts = clip.tokenize(raw_text, context_length=context_length, truncate=True).to(device)
+            texts = tokenize(raw_text, context_length=context_length, truncate=True).to(device)
             zero_pad = torch.zeros([texts.shape[0], default_context_length - context_length], dtype=texts.dtype,
                                    device=texts.device)
             texts = torch.cat([texts, zero_pad], dim=1)
         else:
-            texts = clip.tokenize(raw_text, truncate=True).to(device)
+            texts = tokenize(raw_text, truncate=True).to(device)
         return clip_model.encode_text(texts).float()
 
     def mask_cond(self, cond, force_mask=False):

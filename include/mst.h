@@ -384,6 +384,69 @@ int mst_recover_from_ric(const float* x, const float* mean, const float* stdv, f
                          int32_t n_feats, int32_t n_frames, int32_t joints_num, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * CLIP text tower (scope row N1) - what `self.clip_model.encode_text(texts)`
+ * computes in MDM.encode_text (model/mdm_forstyledataset.py:298-313, loaded
+ * by load_and_freeze_clip :275-286).  The arithmetic is third-party:
+ * openai/CLIP @ a9b1bf59 (requirements.txt:26), clip/model.py
+ * CLIP.encode_text: token_embedding + positional_embedding -> `layers`
+ * pre-norm residual blocks (x += MHA(ln_1 x, causal mask); x += c_proj(
+ * QuickGELU(c_fc(ln_2 x)))) -> ln_final -> the row of the highest token id
+ * (end-of-text) times text_projection.  Tokenising stays with the caller
+ * (clip.tokenize needs the BPE vocabulary file, which is not redistributed
+ * here).  fp32 weights in the CLIP state_dict layout.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t vocab;     /* 49408                                               */
+  int32_t ctx;       /* context length 77 (<= 80)                           */
+  int32_t width;     /* transformer_width 512                               */
+  int32_t n_heads;   /* 8  (head_dim must be 64)                            */
+  int32_t n_layers;  /* 12                                                  */
+  int32_t d_ff;      /* 4 * width                                           */
+  int32_t d_out;     /* embed_dim 512 (= MDM clip_dim)                      */
+  int32_t precision; /* MST_PREC_*                                          */
+} mst_clip_text_desc;
+
+typedef struct {
+  const float* ln1_g;  /* transformer.resblocks.{l}.ln_1.weight [w]          */
+  const float* ln1_b;
+  const float* qkv_w;  /* .attn.in_proj_weight [3w, w]                       */
+  const float* qkv_b;
+  const float* o_w;    /* .attn.out_proj.weight [w, w]                       */
+  const float* o_b;
+  const float* ln2_g;  /* .ln_2.weight [w]                                   */
+  const float* ln2_b;
+  const float* fc_w;   /* .mlp.c_fc.weight [ff, w]                           */
+  const float* fc_b;
+  const float* proj_w; /* .mlp.c_proj.weight [w, ff]                         */
+  const float* proj_b;
+} mst_clip_text_layer;
+
+typedef struct {
+  const float* token_embedding;      /* token_embedding.weight [vocab, w]    */
+  const float* positional_embedding; /* [ctx, w]                             */
+  const float* lnf_g;                /* ln_final.weight [w]                  */
+  const float* lnf_b;
+  const float* text_projection;      /* [w, d_out]                           */
+  mst_clip_text_layer layers[MST_MAX_LAYERS];
+} mst_clip_text_weights;
+
+typedef struct mst_clip_text_s* mst_clip_text_t;
+
+int mst_clip_text_create(const mst_clip_text_desc* desc, mst_clip_text_t* out);
+int mst_clip_text_destroy(mst_clip_text_t h);
+int mst_abi_sizes_clip_text(size_t* desc, size_t* weights);
+/* device bytes for the bf16 weight packs (0 in MST_PREC_FP32) and for the
+ * activations of `batch` token rows                                         */
+int mst_clip_text_packed_weight_bytes(mst_clip_text_t h, size_t* bytes);
+int mst_clip_text_workspace_bytes(mst_clip_text_t h, int32_t batch, size_t* bytes);
+int mst_clip_text_load_weights(mst_clip_text_t h, const mst_clip_text_weights* w, void* packed_dev,
+                               size_t packed_bytes, void* stream);
+/* tokens int32 [batch, ctx] device (ids outside [0, vocab) are an error the
+ * host mirror checks; the kernel clamps) -> features fp32 [batch, d_out].   */
+int mst_clip_text_encode(mst_clip_text_t h, const int32_t* tokens, int32_t batch, float* features,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Kernel-level test hooks (used by tests/ and bench.py roofline legs only).
  * ------------------------------------------------------------------------ */
 /* C[M,N] (fp32) = A[M,K](bf16) * W[N,K](bf16)^T + bias[N], tcgen05 path.    */

@@ -221,3 +221,37 @@ def test_text_feature_cache_encodes_each_caption_once():
     m.mst_text_cache_clear()
     m.encode_text_cached(["jump"], "cpu")
     assert m.calls[-1] == ["jump"]
+
+
+def test_clip_text_abi_and_module_layout():
+    """Scope row N1 without a GPU: struct sizes, argument validation, and the CLIP state_dict layout of the host mirror."""
+    lib = L.load()
+    a, b = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.mst_abi_sizes_clip_text(ctypes.byref(a), ctypes.byref(b)) == 0
+    assert (a.value, b.value) == (ctypes.sizeof(L.ClipTextDesc), ctypes.sizeof(L.ClipTextWeights))
+    h = ctypes.c_void_p()
+    bad = L.ClipTextDesc(49408, 77, 512, 4, 12, 2048, 512, L.PREC_FP32)  # head_dim 128
+    assert lib.mst_clip_text_create(ctypes.byref(bad), ctypes.byref(h)) == 3 and b"head_dim" in lib.mst_last_error()
+    bad = L.ClipTextDesc(49408, 128, 512, 8, 12, 2048, 512, L.PREC_FP32)
+    assert lib.mst_clip_text_create(ctypes.byref(bad), ctypes.byref(h)) == 3 and b"context" in lib.mst_last_error()
+    ok = L.ClipTextDesc(49408, 77, 512, 8, 12, 2048, 512, L.PREC_BF16)
+    assert lib.mst_clip_text_create(ctypes.byref(ok), ctypes.byref(h)) == 0
+    n = ctypes.c_size_t()
+    assert lib.mst_clip_text_packed_weight_bytes(h, ctypes.byref(n)) == 0
+    assert n.value == 12 * (3 * 512 * 512 + 512 * 512 + 2 * 2048 * 512) * 2
+    assert lib.mst_clip_text_workspace_bytes(h, 64, ctypes.byref(n)) == 0 and n.value > 64 * 77 * 512 * 4 * 4
+    assert lib.mst_clip_text_encode(h, None, 1, None, None, 0, None) == 1  # null arguments are refused before any launch
+    assert lib.mst_clip_text_destroy(h) == 0
+
+    from mst_b200.model.clip_text import CLIPTextTower
+    tower = CLIPTextTower(transformer_layers=2)
+    keys = set(tower.state_dict())
+    assert {"token_embedding.weight", "positional_embedding", "ln_final.weight", "ln_final.bias", "text_projection",
+            "transformer.resblocks.1.attn.in_proj_weight", "transformer.resblocks.1.attn.out_proj.bias",
+            "transformer.resblocks.0.mlp.c_fc.weight", "transformer.resblocks.0.mlp.c_proj.bias",
+            "transformer.resblocks.0.ln_1.weight", "transformer.resblocks.0.ln_2.bias"} <= keys and len(keys) == 29
+    assert not any(p.requires_grad for p in tower.parameters())
+    rebuilt = CLIPTextTower.from_state_dict({**tower.state_dict(), "visual.proj": torch.zeros(1)})
+    assert rebuilt.transformer.layers == 2 and rebuilt.heads == 8
+    with pytest.raises(RuntimeError, match="CUDA"):  # no CPU fallback
+        tower.encode_text(torch.zeros(1, 77, dtype=torch.long))

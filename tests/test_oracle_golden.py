@@ -100,3 +100,30 @@ def test_oracle_decode_matches_reference_golden():
         got = OD.decode_motion(sample, mean, std, J)
         want = torch.from_numpy(gold[f"{name}/joints"])
         assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max())
+
+
+def test_oracle_clip_text_matches_independent_golden():
+    """oracle/clip_text.py (the restated openai/CLIP text tower, scope row N1) against tests/golden/clip_text.npz, which
+    tests/golden/make_golden_clip_text.py produced with Hugging Face transformers' CLIPTextModelWithProjection on the
+    same seeded weights.  Tolerance: 2e-5 of the largest feature (two fp32 implementations, 12 layers)."""
+    import os
+    import sys
+    import numpy as np
+    import torch
+    from oracle import clip_text as OC
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import clip_text_inputs as CI
+    gold = np.load(os.path.join(here, "golden", "clip_text.npz"))
+    sd = CI.state_dict()
+    for name, lengths in CI.CASES.items():
+        tok = CI.tokens(lengths)
+        assert np.array_equal(tok.numpy().astype(np.int32), gold[f"{name}/tokens"])  # the generator is reproducible
+        got = OC.encode_text(sd, tok)
+        want = torch.from_numpy(gold[f"{name}/features"])
+        assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
+    # the causal mask: features of a prompt do not depend on what follows its end-of-text token
+    tok = CI.tokens([9])
+    tok2 = tok.clone()
+    tok2[0, 20:30] = 5
+    assert torch.equal(OC.encode_text(sd, tok), OC.encode_text(sd, tok2))
