@@ -107,12 +107,25 @@ __global__ void __launch_bounds__(256) ct_attention_kernel(const float* __restri
   float* Ps = Vs + CT_MAXS * CT_LDX;
   const int head = blockIdx.x, seq = blockIdx.y;
   const float* base = qkv + (long long)seq * S * 3 * width + head * CT_DH;
-  for (int idx = threadIdx.x; idx < CT_MAXS * CT_DH; idx += blockDim.x) {
-    const int r = idx >> 6, c = idx & 63;
-    const float* src = base + (long long)r * 3 * width + c;
-    Qs[r * CT_LDX + c] = r < S ? src[0] : 0.0f;
-    Ks[r * CT_LDX + c] = r < S ? src[width] : 0.0f;
-    Vs[r * CT_LDX + c] = r < S ? src[2 * width] : 0.0f;
+  {  // 80 rows x 16 float4 per matrix = 5 per thread; all 15 loads in flight before the first shared-memory store
+    constexpr int PER = CT_MAXS * (CT_DH / 4) / 256;
+    float4 v[3][PER];
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int idx = threadIdx.x + 256 * i, r = idx >> 4, c4 = idx & 15;
+        v[m][i] = r < S ? __ldg(reinterpret_cast<const float4*>(base + (long long)r * 3 * width + m * width) + c4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int idx = threadIdx.x + 256 * i, r = idx >> 4, c4 = idx & 15;
+        float* d = (m == 0 ? Qs : (m == 1 ? Ks : Vs)) + r * CT_LDX + 4 * c4;
+        d[0] = v[m][i].x; d[1] = v[m][i].y; d[2] = v[m][i].z; d[3] = v[m][i].w;
+      }
   }
   __syncthreads();
   smem_gemm<false, true, 5, 5>(Qs, CT_LDX, Ks, CT_LDX, CT_DH, [&](int i, int j, float v) { Ps[i * CT_LDP + j] = v * 0.125f; });

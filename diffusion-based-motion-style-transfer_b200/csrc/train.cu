@@ -390,6 +390,91 @@ __global__ void __launch_bounds__(256) gelu_bwd_drop_kernel(const float* __restr
   }
 }
 
+__device__ __forceinline__ uint2 bf16x4(const float4& x) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+
+// h = dropout(gelu(u)) (+ a bf16 copy: the A operand of the next tensor-core GEMM) in one pass
+__global__ void __launch_bounds__(256) gelu_drop_fwd_kernel(const float* __restrict__ u, float* __restrict__ h,
+                                                            __nv_bfloat16* __restrict__ h_bf, long long n4, long long per_seq4,
+                                                            Drop d, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (long long)gridDim.x * blockDim.x) {
+    const float4 uu = reinterpret_cast<const float4*>(u)[v];
+    float4 x = make_float4(gelu_f(uu.x), gelu_f(uu.y), gelu_f(uu.z), gelu_f(uu.w));
+    if (d.on()) {
+      const int seq = (int)(v / per_seq4);
+      const float4 m = drop_scale4(d, site, seq, v - (long long)seq * per_seq4);
+      x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+    }
+    reinterpret_cast<float4*>(h)[v] = x;
+    if (h_bf) reinterpret_cast<uint2*>(h_bf)[v] = bf16x4(x);
+  }
+}
+
+// z = res + dropout(t) (res / dropout optional; t may alias z), y = LayerNorm(z) * g + b (+ a bf16 copy of y): the
+// residual + dropout + LayerNorm tail of both halves of an encoder layer in one pass, one warp per row.
+// d % 128 == 0, d <= 1024; rows are grouped S per sequence for the dropout counters.
+__global__ void __launch_bounds__(256) add_drop_ln_kernel(const float* t, const float* __restrict__ res, float* z,
+                                                          const float* __restrict__ g, const float* __restrict__ bt,
+                                                          float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf, int M, int d,
+                                                          int S, Drop drop, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int per4 = d >> 7;  // float4 per lane
+  const int seq = row / S;
+  const long long local4 = (long long)(row - seq * S) * (d >> 2);
+  const float4* t4 = reinterpret_cast<const float4*>(t + (long long)row * d);
+  const float4* r4 = res ? reinterpret_cast<const float4*>(res + (long long)row * d) : nullptr;
+  float4* z4 = z ? reinterpret_cast<float4*>(z + (long long)row * d) : nullptr;
+  float4 v[8];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < per4) {
+      const int c4 = lane + 32 * i;
+      float4 x = t4[c4];
+      if (drop.on()) {
+        const float4 m = drop_scale4(drop, site, seq, local4 + c4);
+        x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+      }
+      if (r4) {
+        const float4 a = r4[c4];
+        x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+      }
+      if (z4) z4[c4] = x;
+      v[i] = x;
+      sum += (x.x + x.y) + (x.z + x.w);
+    }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)d;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < per4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + e * e);
+    }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)d + 1e-5f);
+  float4* y4 = reinterpret_cast<float4*>(y + (long long)row * d);
+  uint2* yb = y_bf ? reinterpret_cast<uint2*>(y_bf + (long long)row * d) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < per4) {
+      const int c4 = lane + 32 * i;
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + c4), bb = __ldg(reinterpret_cast<const float4*>(bt) + c4);
+      const float4 o = make_float4((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
+                                   (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+      y4[c4] = o;
+      if (yb) yb[c4] = bf16x4(o);
+    }
+}
+
 // LayerNorm backward over rows of width d (d % 32 == 0, d <= 1024): dz = rstd * (g - mean(g) - xhat * mean(g xhat)),
 // g = dy * gamma; dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (block partials, then atomics).
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
@@ -559,8 +644,9 @@ static void carve_stage(const mst_model_desc& d, int M, void* base, Stage* st) {
   st->m_pad = mp;
 }
 
+// a_staged: the producer of x already left its bf16 copy in st.a (fused conversions of the forward chain)
 static int linear_fwd(bool tc, const Stage& st, const float* x, const Lin& L, const float* bias, const float* add, float* out,
-                      int M, cudaStream_t s, const char* name) {
+                      int M, cudaStream_t s, const char* name, bool a_staged = false) {
   if (!tc) {
     GemmEx g;
     g.a = x; g.lda = L.n_in; g.b = L.w; g.ldb = L.n_in; g.trans_b = 1; g.bias = bias; g.add = add; g.c = out; g.ldc = L.n_out;
@@ -568,7 +654,7 @@ static int linear_fwd(bool tc, const Stage& st, const float* x, const Lin& L, co
     return gemm_ex(g, s, name);
   }
   int rc;
-  if ((rc = cvt_bf16(x, M, L.n_in, L.n_in, st.a, nullptr, 0, s))) return rc;
+  if (!a_staged && (rc = cvt_bf16(x, M, L.n_in, L.n_in, st.a, nullptr, 0, s))) return rc;
   TcGemmParams p;
   p.a = st.a; p.w = L.w_bf; p.bias = bias; p.add = add; p.out = out; p.ldo = L.n_out; p.M = M; p.N = L.n_out; p.K = L.n_in;
   p.epi = TC_EPI_TRAIN_F32;
@@ -635,18 +721,42 @@ constexpr int SA_DH = 128;
 constexpr int SA_LDX = SA_DH + 1;    // Q, K, V, dO rows
 constexpr int SA_LDP = SA_MAXS + 1;  // P, dP rows
 
-// rows [0, S) x 128 columns of a global matrix (leading dimension ld) -> smem [SA_MAXS][SA_LDX], rows >= S zero
-__device__ __forceinline__ void sa_load(float* dst, const float* __restrict__ src, int ld, int S) {
-  for (int idx = threadIdx.x; idx < SA_MAXS * SA_DH; idx += blockDim.x) {
-    const int r = idx >> 7, c = idx & 127;
-    dst[r * SA_LDX + c] = r < S ? src[(long long)r * ld + c] : 0.0f;
-  }
+// rows [0, S) x 128 columns of N global matrices (leading dimension ld, 16-byte aligned rows) -> smem [SA_MAXS][SA_LDX],
+// rows >= S zero.  256 threads; every thread issues its 10 float4 loads per matrix before the first shared-memory store, so
+// the CTA pays the global latency once instead of once per element (the scalar loop was ~60 % of the kernel).
+template <int N>
+__device__ __forceinline__ void sa_load(float* const (&dst)[N], const float* const (&src)[N], int ld, int S) {
+  constexpr int PER = SA_MAXS * (SA_DH / 4) / 256;  // 10
+  float4 v[N][PER];
+#pragma unroll
+  for (int m = 0; m < N; ++m)
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + 256 * i, r = idx >> 5, c4 = idx & 31;
+      v[m][i] = r < S ? __ldg(reinterpret_cast<const float4*>(src[m] + (long long)r * ld) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+  for (int m = 0; m < N; ++m)
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + 256 * i, r = idx >> 5, c4 = idx & 31;
+      float* d = dst[m] + r * SA_LDX + 4 * c4;
+      d[0] = v[m][i].x; d[1] = v[m][i].y; d[2] = v[m][i].z; d[3] = v[m][i].w;
+    }
 }
-// [S][S] global -> smem [SA_MAXS][SA_LDP], zero padded
+// [S][S] global -> smem [SA_MAXS][SA_LDP], zero padded (25 independent loads per thread)
 __device__ __forceinline__ void sa_load_p(float* dst, const float* __restrict__ src, int S) {
-  for (int idx = threadIdx.x; idx < SA_MAXS * SA_MAXS; idx += blockDim.x) {
-    const int r = idx / SA_MAXS, c = idx - r * SA_MAXS;
-    dst[r * SA_LDP + c] = (r < S && c < S) ? src[r * S + c] : 0.0f;
+  constexpr int PER = SA_MAXS * SA_MAXS / 256;  // 25
+  float v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int idx = threadIdx.x + 256 * i, r = idx / SA_MAXS, c = idx - r * SA_MAXS;
+    v[i] = (r < S && c < S) ? __ldg(src + r * S + c) : 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int idx = threadIdx.x + 256 * i, r = idx / SA_MAXS, c = idx - r * SA_MAXS;
+    dst[r * SA_LDP + c] = v[i];
   }
 }
 
@@ -659,8 +769,8 @@ __device__ __forceinline__ float drop_scale1(const Drop& d, uint32_t site, int s
 // grid (heads, n_seqs).  qkv [n_seqs*S, 3d]; p / pd [n_seqs][H][S][S]; ao [n_seqs*S, d]
 __global__ void __launch_bounds__(256) attn_small_fwd_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ key_valid,
                                                              float* __restrict__ p_out, float* __restrict__ pd_out,
-                                                             float* __restrict__ ao, int S, int d_model, int H, float scale,
-                                                             Drop drop, uint32_t site) {
+                                                             float* __restrict__ ao, __nv_bfloat16* __restrict__ ao_bf, int S,
+                                                             int d_model, int H, float scale, Drop drop, uint32_t site) {
   pdl_launch_dependents();
   pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   extern __shared__ float sm[];
@@ -670,9 +780,11 @@ __global__ void __launch_bounds__(256) attn_small_fwd_kernel(const float* __rest
   float* Ps = Vs + SA_MAXS * SA_LDX;
   const int head = blockIdx.x, seq = blockIdx.y;
   const float* base = qkv + (long long)seq * S * 3 * d_model + head * SA_DH;
-  sa_load(Qs, base, 3 * d_model, S);
-  sa_load(Ks, base + d_model, 3 * d_model, S);
-  sa_load(Vs, base + 2 * d_model, 3 * d_model, S);
+  {
+    float* const dst[3] = {Qs, Ks, Vs};
+    const float* const src[3] = {base, base + d_model, base + 2 * d_model};
+    sa_load<3>(dst, src, 3 * d_model, S);
+  }
   __syncthreads();
   smem_gemm<false, true, 5, 5>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v) { Ps[i * SA_LDP + j] = v * scale; });
   __syncthreads();
@@ -711,8 +823,12 @@ __global__ void __launch_bounds__(256) attn_small_fwd_kernel(const float* __rest
   }
   __syncthreads();
   float* og = ao + (long long)seq * S * d_model + head * SA_DH;
+  __nv_bfloat16* ob = ao_bf ? ao_bf + (long long)seq * S * d_model + head * SA_DH : nullptr;  // operand of the out-projection
   smem_gemm<false, false, 5, 8>(Ps, SA_LDP, Vs, SA_LDX, SA_MAXS, [&](int i, int c, float v) {
-    if (i < S) og[(long long)i * d_model + c] = v;
+    if (i < S) {
+      og[(long long)i * d_model + c] = v;
+      if (ob) ob[(long long)i * d_model + c] = __float2bfloat16_rn(v);
+    }
   });
 }
 
@@ -734,10 +850,14 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   const float* base = qkv + (long long)seq * S * 3 * d_model + head * SA_DH;
   float* dbase = dqkv + (long long)seq * S * 3 * d_model + head * SA_DH;
   const long long pp = ((long long)seq * H + head) * S * S;
-  sa_load(Qs, base, 3 * d_model, S);
-  sa_load(Ks, base + d_model, 3 * d_model, S);
-  sa_load(Vs, base + 2 * d_model, 3 * d_model, S);
-  sa_load(Os, dao + (long long)seq * S * d_model + head * SA_DH, d_model, S);
+  {
+    float* const dst[3] = {Qs, Ks, Vs};
+    const float* const src[3] = {base, base + d_model, base + 2 * d_model};
+    sa_load<3>(dst, src, 3 * d_model, S);
+    float* const dst_o[1] = {Os};
+    const float* const src_o[1] = {dao + (long long)seq * S * d_model + head * SA_DH};
+    sa_load<1>(dst_o, src_o, d_model, S);
+  }
   sa_load_p(Ps, (drop.on() ? pd_in : p_in) + pp, S);
   __syncthreads();
   // dV = Pd^T dO
@@ -858,7 +978,12 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
     float* x_next = l + 1 < d.n_layers ? tp.l[l + 1].x : tp.x_out;
     Lin lqkv, lo, lf1, lf2;
     layer_lins(e, l, &lqkv, &lo, &lf1, &lf2);
-    if ((rc = linear_fwd(tc, tp.stage, t.x, lqkv, L.qkv_b, nullptr, t.qkv, M, s, "train_qkv"))) return rc;
+    // fused tail kernels (residual + dropout + LayerNorm, GELU + dropout) that also leave the bf16 operand of the next
+    // tensor-core GEMM in the staging buffer: 8 kernels per layer instead of 16 on the latency-bound B=1 chain
+    const bool fused = dm % 128 == 0 && ff % 4 == 0;
+    __nv_bfloat16* bf = tc ? tp.stage.a : nullptr;
+    const bool x_staged = tc && fused && l > 0;  // the previous layer's LayerNorm kernel staged it
+    if ((rc = linear_fwd(tc, tp.stage, t.x, lqkv, L.qkv_b, nullptr, t.qkv, M, s, "train_qkv", x_staged))) return rc;
     if (attn_small_ok(d, S)) {
       static bool attr_set = false;
       if (!attr_set) {
@@ -866,7 +991,7 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
         attr_set = true;
       }
       MST_CUDA_OK(launch_pdl(attn_small_fwd_kernel, dim3(H, NS), dim3(256), SA_FWD_SMEM, s, (const float*)t.qkv, key_valid, t.p, t.pd,
-                             t.ao, S, dm, H, scale, drop, drop_site(l, 1)));
+                             t.ao, bf, S, dm, H, scale, drop, drop_site(l, 1)));
       MST_LAUNCHED("train_attn_small", s);
     } else {
       GemmEx sc;  // scores = scale * Q K^T per (seq, head)
@@ -888,6 +1013,30 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
       pv.M = S; pv.N = dh; pv.K = S; pv.batch = NS; pv.heads = H;
       pv.a_bs = sc.c_bs; pv.a_hs = sc.c_hs; pv.b_bs = sc.a_bs; pv.b_hs = dh; pv.c_bs = (long long)S * dm; pv.c_hs = dh;
       if ((rc = gemm_ex(pv, s, "train_pv"))) return rc;
+    }
+    const bool ao_staged = tc && attn_small_ok(d, S);
+    if (fused) {
+      const int ln_grid = ceil_div(M, 8);
+      // z1 = x + dropout1(ao Wo^T + bo); y = LN1(z1)
+      if ((rc = linear_fwd(tc, tp.stage, t.ao, lo, L.o_b, drop.on() ? nullptr : t.x, t.z1, M, s, "train_outproj", ao_staged)))
+        return rc;
+      MST_CUDA_OK(launch_pdl(add_drop_ln_kernel, dim3(ln_grid), dim3(256), 0, s, (const float*)t.z1,
+                             drop.on() ? (const float*)t.x : (const float*)nullptr, drop.on() ? t.z1 : (float*)nullptr, L.ln1_g,
+                             L.ln1_b, t.y, bf, M, dm, S, drop, drop_site(l, 2)));
+      MST_LAUNCHED("train_add_drop_ln", s);
+      if ((rc = linear_fwd(tc, tp.stage, t.y, lf1, L.b1, nullptr, t.u, M, s, "train_ffn1", tc))) return rc;
+      // h = dropout(gelu(u)); z2 = y + dropout2(h W2^T + b2); x' = LN2(z2)
+      const long long n4 = (long long)M * ff / 4;
+      MST_CUDA_OK(launch_pdl(gelu_drop_fwd_kernel, dim3(ew_blocks(n4)), dim3(256), 0, s, (const float*)t.u, t.h, bf, n4,
+                             (long long)S * ff / 4, drop, drop_site(l, 3)));
+      MST_LAUNCHED("train_gelu_drop", s);
+      if ((rc = linear_fwd(tc, tp.stage, t.h, lf2, L.b2, drop.on() ? nullptr : t.y, t.z2, M, s, "train_ffn2", tc))) return rc;
+      MST_CUDA_OK(launch_pdl(add_drop_ln_kernel, dim3(ln_grid), dim3(256), 0, s, (const float*)t.z2,
+                             drop.on() ? (const float*)t.y : (const float*)nullptr, drop.on() ? t.z2 : (float*)nullptr, L.ln2_g,
+                             L.ln2_b, x_next, l + 1 < d.n_layers ? bf : (__nv_bfloat16*)nullptr, M, dm, S, drop,
+                             drop_site(l, 4)));
+      MST_LAUNCHED("train_add_drop_ln", s);
+      continue;
     }
     if (drop.on()) {  // z1 = x + dropout1(ao Wo^T + bo)
       if ((rc = linear_fwd(tc, tp.stage, t.ao, lo, L.o_b, nullptr, t.z1, M, s, "train_outproj"))) return rc;

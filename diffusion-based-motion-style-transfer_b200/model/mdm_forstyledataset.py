@@ -193,7 +193,7 @@ class _DenoiserGradFn(torch.autograd.Function):
         if ctx.tape is None:
             raise RuntimeError("the mst activation tape of this forward was already consumed by a backward pass "
                                "(retain_graph is not supported: run the forward again)")
-        layers = [l.mst_tensors() for l in ctx.native._mst_encoder().layers]
+        layers = ctx.native._mst_cached_tensors()[1]
         flat = [p for lp in layers for p in lp.values()]
         needs = {id(p): bool(ctx.needs_input_grad[5 + i]) for i, p in enumerate(flat)}
         slot = ctx.slot
@@ -329,6 +329,43 @@ class NativeDenoiser(nn.Module):
         layers = [l.mst_tensors() for l in self._mst_encoder().layers]
         return top, layers
 
+    def __setattr__(self, name, value):
+        if isinstance(value, (nn.Module, nn.Parameter)):  # a replaced sub-module / parameter invalidates the cached walk
+            self.__dict__.pop("_mst_tensor_cache", None)
+            self.__dict__.pop("_mst_grad_cache", None)
+        super().__setattr__(name, value)
+
+    def _mst_cached_tensors(self):
+        """(top, layers, flat list) of the weight tensors.  Walking the module tree costs ~0.2 ms and every forward /
+        embedding call asks for the engine (18 times per finetune step), so the walk is cached; the per-call check is
+        (data_ptr, _version) of the cached tensors, which sees in-place updates, load_state_dict and .data swaps.  The
+        cache is dropped by .to()/.cuda()/.float() (``_apply``), ``load_state_dict``, ``mst_weights_changed`` and when a
+        sub-module or Parameter is assigned on a module of this tree through ``add_module`` / attribute assignment
+        on the denoiser itself; after deeper module surgery call ``mst_weights_changed()``."""
+        c = self.__dict__.get("_mst_tensor_cache")
+        if c is None:
+            top, layers = self._mst_all_tensors()
+            flat = [t for d in [top] + layers for t in d.values() if t is not None]
+            c = (top, layers, flat)
+            self.__dict__["_mst_tensor_cache"] = c
+        return c
+
+    def _mst_drop_tensor_cache(self):
+        self.__dict__.pop("_mst_tensor_cache", None)
+        self.__dict__.pop("_mst_grad_cache", None)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._mst_drop_tensor_cache()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._mst_drop_tensor_cache()
+        return super().load_state_dict(*args, **kwargs)
+
+    def requires_grad_(self, requires_grad=True):
+        self._mst_drop_tensor_cache()
+        return super().requires_grad_(requires_grad)
+
     def _mst_signature(self, top, layers):
         sig = []
         for d in [top] + layers:
@@ -418,9 +455,12 @@ class NativeDenoiser(nn.Module):
         slot.used += 1
         return slot, k
 
-    def mst_weights_changed(self):
+    def mst_weights_changed(self, structure=True):
         """Call after parameters were updated behind torch's back (the fused optimizer writes through raw
-        pointers, which does not bump the tensors' version counters): forces a re-pack on next use."""
+        pointers, which does not bump the tensors' version counters): forces a re-pack on next use.
+        ``structure=False`` (the optimizer's per-step call) keeps the cached walk of the module tree."""
+        if structure:
+            self._mst_drop_tensor_cache()
         for ent in self.__dict__.get("_mst_engines", {}).values():
             ent[1] = None
 
@@ -429,8 +469,8 @@ class NativeDenoiser(nn.Module):
         prec = precision or self.mst_precision or default_precision()
         key = (str(device), prec)
         cache = self.__dict__.setdefault("_mst_engines", {})
-        top, layers = self._mst_all_tensors()
-        sig = self._mst_signature(top, layers)
+        top, layers, flat = self._mst_cached_tensors()
+        sig = tuple([(t.data_ptr(), t._version) for t in flat])
         ent = cache.get(key)
         if ent is None:
             f = self._mst_front()
@@ -540,7 +580,7 @@ class NativeDenoiser(nn.Module):
         xc = x.float().contiguous()
         if self._mst_wants_grad(xc):
             # training / differentiable-sampling path (fp32 engine with an activation tape)
-            enc_params = [p for l in self._mst_encoder().layers for p in l.mst_tensors().values()]
+            enc_params = [p for lp in self._mst_cached_tensors()[1] for p in lp.values()]
             with torch.no_grad():
                 eng = self.mst_engine(x.device, precision=self.mst_train_prec())
                 temb = eng.time_embed(timesteps)
@@ -561,12 +601,16 @@ class NativeDenoiser(nn.Module):
         every other module frozen, mdm_forstyledataset.py:562-567); trainable projections / embedders raise."""
         if not torch.is_grad_enabled():
             return False
-        enc = any(p.requires_grad for l in self._mst_encoder().layers for p in l.parameters())
+        gc = self.__dict__.get("_mst_grad_cache")
+        if gc is None:  # parameter lists of the encoder stack / the front end (walked once; the flags are read per call)
+            f = self._mst_front()
+            front = [f.input_process, f.output_process, f.embed_timestep] + ([f.embed_text] if hasattr(f, "embed_text") else [])
+            gc = ([p for l in self._mst_encoder().layers for p in l.parameters()], [p for m in front for p in m.parameters()])
+            self.__dict__["_mst_grad_cache"] = gc
+        enc = any([p.requires_grad for p in gc[0]])
         if not (enc or x.requires_grad):
             return False
-        f = self._mst_front()
-        front = [f.input_process, f.output_process, f.embed_timestep] + ([f.embed_text] if hasattr(f, "embed_text") else [])
-        if any(p.requires_grad for m in front for p in m.parameters()):
+        if any([p.requires_grad for p in gc[1]]):
             # e.g. a freshly constructed MDM evaluated without torch.no_grad(): run the inference kernels; the result
             # carries no grad_fn, so an attempted backward() fails loudly in torch instead of training half a model
             if not getattr(self, "_mst_warned_front_grad", False):

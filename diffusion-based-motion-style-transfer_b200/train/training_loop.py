@@ -36,14 +36,16 @@ class FusedAdamW:
         g = self.param_groups[0]
         self.step_count += 1
         if self.model is not None:
-            for m in self.model.modules():
-                if hasattr(m, "mst_flush_backward"):
-                    m.mst_flush_backward()  # deferred (batched) backward passes must have written their gradients
+            den = self.__dict__.get("_denoisers")
+            if den is None:
+                den = self._denoisers = [m for m in self.model.modules() if hasattr(m, "mst_flush_backward")]
+            for m in den:
+                m.mst_flush_backward()  # deferred (batched) backward passes must have written their gradients
         K.adamw_step(self.flat.train_params, self.flat.grads, self.exp_avg, self.exp_avg_sq, lr=g["lr"],
                      beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], weight_decay=g["weight_decay"],
                      step=self.step_count, grad_scale=self.grad_scale)
         if self.model is not None and hasattr(self.model, "mst_weights_changed"):
-            self.model.mst_weights_changed()  # the kernel wrote through raw pointers: engines must re-pack
+            self.model.mst_weights_changed(structure=False)  # the kernel wrote through raw pointers: engines must re-pack
 
     def zero_grad(self, set_to_none=False):
         self.flat.grads.zero_()

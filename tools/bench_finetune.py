@@ -91,9 +91,12 @@ def main():
         dist.barrier()
     n0 = K.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(a.steps):
         loop.run_step(*batch)
+    host_ms = (time.perf_counter() - h0) * 1e3 / a.steps  # host time to ISSUE a step (no final sync): ~ value => host-bound
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
@@ -105,7 +108,7 @@ def main():
            "config": {"workload": f"few-shot style finetune step: t2m batch B={a.batch} x T={a.frames} (sharded over "
                                   f"{world} GPU), style example B=1 x 6 DDIM steps with grad, semantic_guidance={a.sg}, "
                                   "AdamW lr 1e-4 (BASELINE configs[3])"},
-           "gpu_launches_per_step": int(launches), "loss": float(loop.last_losses["loss"]),
+           "gpu_launches_per_step": int(launches), "host_issue_ms_per_step": round(host_ms, 3), "loss": float(loop.last_losses["loss"]),
            "grad_norm": loop.mp_trainer.last_norms[0], "param_norm": loop.mp_trainer.last_norms[1]}
     if a.profile and rank == 0:
         with K.profile(cap=8192) as p:
