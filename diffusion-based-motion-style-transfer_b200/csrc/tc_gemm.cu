@@ -1144,7 +1144,13 @@ int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
       return launch_gemm_ln(p, s);
     case TC_EPI_INPROJ:
       MST_CHECK_ARG(p.N % 256 == 0 && p.pe && p.B > 0 && p.T > 0 && p.ldo % 8 == 0, "bad in-projection geometry");
-      return launch_gemm<256, TC_EPI_INPROJ>(p, s);
+      // K is only 3 k-blocks, so a tile is all epilogue: 128-wide tiles (392 of them at B=64, 2.65 waves of half the
+      // work) beat 256-wide ones (196 tiles, 2 waves): 34 -> 29 us.  MST_INPROJ_BN=256 restores the wide tile.
+      {
+        static const int bn = getenv("MST_INPROJ_BN") ? atoi(getenv("MST_INPROJ_BN")) : 128;
+        if (bn == 256) return launch_gemm<256, TC_EPI_INPROJ>(p, s);
+      }
+      return launch_gemm<128, TC_EPI_INPROJ>(p, s);
     case TC_EPI_OUTPROJ_F32:
       MST_CHECK_ARG(p.N % 64 == 0 && p.B > 0 && p.T > 0 && p.n_valid > 0, "bad out-projection geometry");
       return launch_gemm<64, TC_EPI_OUTPROJ_F32>(p, s);
