@@ -767,7 +767,9 @@ __device__ __forceinline__ float drop_scale1(const Drop& d, uint32_t site, int s
 }
 
 // grid (heads, n_seqs).  qkv [n_seqs*S, 3d]; p / pd [n_seqs][H][S][S]; ao [n_seqs*S, d]
-__global__ void __launch_bounds__(256) attn_small_fwd_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ key_valid,
+// Shared memory: Q and V share one buffer (V is fetched once the scores are done), so two CTAs fit on an SM - the kernel is
+// latency-bound with 8 warps per SM (2 per scheduler), and at B=64 all 256 CTAs are then co-resident instead of 2 waves.
+__global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ key_valid,
                                                              float* __restrict__ p_out, float* __restrict__ pd_out,
                                                              float* __restrict__ ao, __nv_bfloat16* __restrict__ ao_bf, int S,
                                                              int d_model, int H, float scale, Drop drop, uint32_t site) {
@@ -776,18 +778,23 @@ __global__ void __launch_bounds__(256) attn_small_fwd_kernel(const float* __rest
   extern __shared__ float sm[];
   float* Qs = sm;
   float* Ks = Qs + SA_MAXS * SA_LDX;
-  float* Vs = Ks + SA_MAXS * SA_LDX;
-  float* Ps = Vs + SA_MAXS * SA_LDX;
+  float* Vs = Qs;  // overlays Q
+  float* Ps = Ks + SA_MAXS * SA_LDX;
   const int head = blockIdx.x, seq = blockIdx.y;
   const float* base = qkv + (long long)seq * S * 3 * d_model + head * SA_DH;
   {
-    float* const dst[3] = {Qs, Ks, Vs};
-    const float* const src[3] = {base, base + d_model, base + 2 * d_model};
-    sa_load<3>(dst, src, 3 * d_model, S);
+    float* const dst[2] = {Qs, Ks};
+    const float* const src[2] = {base, base + d_model};
+    sa_load<2>(dst, src, 3 * d_model, S);
   }
   __syncthreads();
   smem_gemm<false, true, 5, 5>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v) { Ps[i * SA_LDP + j] = v * scale; });
   __syncthreads();
+  {
+    float* const dst[1] = {Vs};
+    const float* const src[1] = {base + 2 * d_model};
+    sa_load<1>(dst, src, 3 * d_model, S);  // visible to the P V product after the barrier that follows the softmax
+  }
   // masked softmax, one warp per row; then dropout.  P (before dropout) and Pd go to the tape.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint8_t* kv = key_valid ? key_valid + (long long)seq * S : nullptr;
@@ -894,7 +901,7 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   });
 }
 
-constexpr size_t SA_FWD_SMEM = (size_t)(3 * SA_MAXS * SA_LDX + SA_MAXS * SA_LDP) * sizeof(float);
+constexpr size_t SA_FWD_SMEM = (size_t)(2 * SA_MAXS * SA_LDX + SA_MAXS * SA_LDP) * sizeof(float);  // 108 KB: 2 CTAs per SM
 constexpr size_t SA_BWD_SMEM = (size_t)(4 * SA_MAXS * SA_LDX + 2 * SA_MAXS * SA_LDP) * sizeof(float);
 static_assert(SA_BWD_SMEM <= 227 * 1024, "small-attention backward shared memory");
 
