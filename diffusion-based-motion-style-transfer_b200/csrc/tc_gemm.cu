@@ -1160,7 +1160,13 @@ int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
       return launch_gemm<64, TC_EPI_BIAS_F32>(p, s);
     case TC_EPI_TRAIN_F32:
       MST_CHECK_ARG(p.N % 64 == 0 && p.ldo % 4 == 0, "N must be a multiple of 64");
-      if (p.N % 256 == 0) return launch_gemm<256, TC_EPI_TRAIN_F32>(p, s);
+      {
+        // small problems (the 77-row B=1 steps of the finetune loop, their batched backward): 64-wide tiles put 4x more
+        // CTAs on the work and shorten every CTA's serial TMA -> MMA -> epilogue chain (MST_TRAIN_BN64=0 switches it off)
+        static const bool narrow = !(getenv("MST_TRAIN_BN64") && atoi(getenv("MST_TRAIN_BN64")) == 0);
+        const int tiles256 = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, 256);
+        if (p.N % 256 == 0 && !(narrow && tiles256 <= sm_count() / 4)) return launch_gemm<256, TC_EPI_TRAIN_F32>(p, s);
+      }
       return launch_gemm<64, TC_EPI_TRAIN_F32>(p, s);
     default:
       return fail(MST_ERR_INVALID, "tc_gemm: unknown epilogue");

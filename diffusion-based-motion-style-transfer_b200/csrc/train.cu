@@ -766,9 +766,13 @@ __device__ __forceinline__ float drop_scale1(const Drop& d, uint32_t site, int s
   return r == 0 ? m.x : (r == 1 ? m.y : (r == 2 ? m.z : m.w));
 }
 
-// grid (heads, n_seqs).  qkv [n_seqs*S, 3d]; p / pd [n_seqs][H][S][S]; ao [n_seqs*S, d]
+// grid (heads, n_seqs, 5 / TM).  qkv [n_seqs*S, 3d]; p / pd [n_seqs][H][S][S]; ao [n_seqs*S, d]
+// TM = 5: one CTA per (sequence, head), all 80 query rows.  TM = 1: five CTAs per (sequence, head), 16 query rows each -
+// the B=1 steps of the finetune loop have only 4 (sequence, head) pairs, and one CTA's serial chain (30 us) was the longest
+// kernel of their forward.
 // Shared memory: Q and V share one buffer (V is fetched once the scores are done), so two CTAs fit on an SM - the kernel is
 // latency-bound with 8 warps per SM (2 per scheduler), and at B=64 all 256 CTAs are then co-resident instead of 2 waves.
+template <int TM>
 __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ key_valid,
                                                              float* __restrict__ p_out, float* __restrict__ pd_out,
                                                              float* __restrict__ ao, __nv_bfloat16* __restrict__ ao_bf, int S,
@@ -780,15 +784,32 @@ __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __r
   float* Ks = Qs + SA_MAXS * SA_LDX;
   float* Vs = Qs;  // overlays Q
   float* Ps = Ks + SA_MAXS * SA_LDX;
-  const int head = blockIdx.x, seq = blockIdx.y;
+  constexpr int ROWS = 16 * TM;                    // query rows of this CTA
+  const int head = blockIdx.x, seq = blockIdx.y, r0 = ROWS * (int)blockIdx.z;
   const float* base = qkv + (long long)seq * S * 3 * d_model + head * SA_DH;
-  {
+  if (TM == 5) {
     float* const dst[2] = {Qs, Ks};
     const float* const src[2] = {base, base + d_model};
     sa_load<2>(dst, src, 3 * d_model, S);
+  } else {
+    float4 q[ROWS * (SA_DH / 4) / 256];  // this CTA's query rows, in flight together with K
+#pragma unroll
+    for (int i = 0; i < ROWS * (SA_DH / 4) / 256; ++i) {
+      const int idx = threadIdx.x + 256 * i, r = r0 + (idx >> 5), c4 = idx & 31;
+      q[i] = r < S ? __ldg(reinterpret_cast<const float4*>(base + (long long)r * 3 * d_model) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float* const dst[1] = {Ks};
+    const float* const src[1] = {base + d_model};
+    sa_load<1>(dst, src, 3 * d_model, S);
+#pragma unroll
+    for (int i = 0; i < ROWS * (SA_DH / 4) / 256; ++i) {
+      const int idx = threadIdx.x + 256 * i;
+      float* d = Qs + (idx >> 5) * SA_LDX + 4 * (idx & 31);
+      d[0] = q[i].x; d[1] = q[i].y; d[2] = q[i].z; d[3] = q[i].w;
+    }
   }
   __syncthreads();
-  smem_gemm<false, true, 5, 5>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v) { Ps[i * SA_LDP + j] = v * scale; });
+  smem_gemm<false, true, TM, 5>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v) { Ps[i * SA_LDP + j] = v * scale; });
   __syncthreads();
   {
     float* const dst[1] = {Vs};
@@ -800,8 +821,9 @@ __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __r
   const uint8_t* kv = key_valid ? key_valid + (long long)seq * S : nullptr;
   float* pg = p_out + ((long long)seq * H + head) * S * S;
   float* pdg = pd_out + ((long long)seq * H + head) * S * S;
-  for (int i = warp; i < SA_MAXS; i += 8) {
-    float* r = Ps + i * SA_LDP;
+  for (int li = warp; li < ROWS; li += 8) {
+    float* r = Ps + li * SA_LDP;
+    const int i = r0 + li;  // row of the sequence
     if (i >= S) {
       for (int j = lane; j < SA_MAXS; j += 32) r[j] = 0.0f;
       continue;
@@ -831,7 +853,8 @@ __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __r
   __syncthreads();
   float* og = ao + (long long)seq * S * d_model + head * SA_DH;
   __nv_bfloat16* ob = ao_bf ? ao_bf + (long long)seq * S * d_model + head * SA_DH : nullptr;  // operand of the out-projection
-  smem_gemm<false, false, 5, 8>(Ps, SA_LDP, Vs, SA_LDX, SA_MAXS, [&](int i, int c, float v) {
+  smem_gemm<false, false, TM, 8>(Ps, SA_LDP, Vs, SA_LDX, SA_MAXS, [&](int li, int c, float v) {
+    const int i = r0 + li;
     if (i < S) {
       og[(long long)i * d_model + c] = v;
       if (ob) ob[(long long)i * d_model + c] = __float2bfloat16_rn(v);
@@ -994,11 +1017,17 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
     if (attn_small_ok(d, S)) {
       static bool attr_set = false;
       if (!attr_set) {
-        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
         attr_set = true;
       }
-      MST_CUDA_OK(launch_pdl(attn_small_fwd_kernel, dim3(H, NS), dim3(256), SA_FWD_SMEM, s, (const float*)t.qkv, key_valid, t.p, t.pd,
-                             t.ao, bf, S, dm, H, scale, drop, drop_site(l, 1)));
+      if (NS * H <= 32) {  // a handful of (sequence, head) pairs: five CTAs each
+        MST_CUDA_OK(launch_pdl(attn_small_fwd_kernel<1>, dim3(H, NS, 5), dim3(256), SA_FWD_SMEM, s, (const float*)t.qkv, key_valid,
+                               t.p, t.pd, t.ao, bf, S, dm, H, scale, drop, drop_site(l, 1)));
+      } else {
+        MST_CUDA_OK(launch_pdl(attn_small_fwd_kernel<5>, dim3(H, NS, 1), dim3(256), SA_FWD_SMEM, s, (const float*)t.qkv, key_valid,
+                               t.p, t.pd, t.ao, bf, S, dm, H, scale, drop, drop_site(l, 1)));
+      }
       MST_LAUNCHED("train_attn_small", s);
     } else {
       GemmEx sc;  // scores = scale * Q K^T per (seq, head)
