@@ -1161,11 +1161,22 @@ int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
     case TC_EPI_TRAIN_F32:
       MST_CHECK_ARG(p.N % 64 == 0 && p.ldo % 4 == 0, "N must be a multiple of 64");
       {
-        // small problems (the 77-row B=1 steps of the finetune loop, their batched backward): 64-wide tiles put 4x more
-        // CTAs on the work and shorten every CTA's serial TMA -> MMA -> epilogue chain (MST_TRAIN_BN64=0 switches it off)
-        static const bool narrow = !(getenv("MST_TRAIN_BN64") && atoi(getenv("MST_TRAIN_BN64")) == 0);
-        const int tiles256 = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, 256);
-        if (p.N % 256 == 0 && !(narrow && tiles256 <= sm_count() / 4)) return launch_gemm<256, TC_EPI_TRAIN_F32>(p, s);
+        // Tile width by a wave model: a tile of width BN costs BN/256 + 0.1 (fixed TMA -> MMA -> epilogue latency) and the
+        // kernel takes ceil(tiles / SMs) of them.  Small problems (the 77-row B=1 steps of the finetune loop, their batched
+        // backward, the weight-gradient GEMMs with 12 x 2 wide tiles and a 77-block reduction) get 4x more, 4x shorter
+        // CTAs; problems of many waves keep the 256-wide tile and its operand reuse.  MST_TRAIN_BN pins a width.
+        static const int pin = getenv("MST_TRAIN_BN") ? atoi(getenv("MST_TRAIN_BN")) : 0;
+        int best = 64;
+        float best_cost = 1e30f;
+        for (int bn = 256; bn >= 64; bn >>= 1) {
+          if (p.N % bn != 0) continue;
+          const int tiles = ceil_div(p.M, BLOCK_M) * (p.N / bn);
+          const float cost = (float)ceil_div(tiles, sm_count()) * ((float)bn / 256.0f + 0.1f);
+          if (cost < best_cost) { best_cost = cost; best = bn; }
+        }
+        if (pin == 256 || pin == 128 || pin == 64) best = (p.N % pin == 0) ? pin : 64;
+        if (best == 256) return launch_gemm<256, TC_EPI_TRAIN_F32>(p, s);
+        if (best == 128) return launch_gemm<128, TC_EPI_TRAIN_F32>(p, s);
       }
       return launch_gemm<64, TC_EPI_TRAIN_F32>(p, s);
     default:
