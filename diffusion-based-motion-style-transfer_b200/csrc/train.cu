@@ -529,18 +529,22 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       if (i < per) dr[lane + 32 * i] = rstd * (g[i] - mg - v[i] * mgx);
   }
   // block reduction of the per-warp column partials, one 32-column slab at a time
-  for (int i = 0; i < per; ++i) {
-    red[wib][lane] = dg[i];
-    red[wib][32 + lane] = db[i];
-    __syncthreads();
-    if (wib == 0) {
-      float a = 0.0f, b2 = 0.0f;
+  // (fully unrolled: a run-time index into dg / db would put both arrays in local memory for the whole kernel)
 #pragma unroll
-      for (int w = 0; w < 8; ++w) { a += red[w][lane]; b2 += red[w][32 + lane]; }
-      if (dgamma) atomicAdd(dgamma + lane + 32 * i, a);
-      if (dbeta) atomicAdd(dbeta + lane + 32 * i, b2);
+  for (int i = 0; i < 32; ++i) {
+    if (i < per) {  // uniform over the block
+      red[wib][lane] = dg[i];
+      red[wib][32 + lane] = db[i];
+      __syncthreads();
+      if (wib == 0) {
+        float a = 0.0f, b2 = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += red[w][lane]; b2 += red[w][32 + lane]; }
+        if (dgamma) atomicAdd(dgamma + lane + 32 * i, a);
+        if (dbeta) atomicAdd(dbeta + lane + 32 * i, b2);
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -1145,7 +1149,7 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     const mst_layer_grads& G = grads[l];
     Lin lqkv, lo, lf1, lf2;
     layer_lins(e, l, &lqkv, &lo, &lf1, &lf2);
-    const int ln_blocks = ceil_div(M, 8) < 4 * sm_count() ? ceil_div(M, 8) : 4 * sm_count();
+    const int ln_blocks = ceil_div(M, 8) < sm_count() ? ceil_div(M, 8) : sm_count();  // few blocks: 1024 atomics each at the end
     // LN2
     float* dz2 = spare;
     MST_CUDA_OK(launch_pdl(layernorm_bwd_kernel, dim3(ln_blocks), dim3(256), 0, s, (const float*)gx, (const float*)t.z2, L.ln2_g, dz2, G.ln2_g, G.ln2_b, M, dm));
