@@ -722,8 +722,8 @@ static void layer_lins(Engine* e, int l, Lin* qkv, Lin* o, Lin* f1, Lin* f2) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SA_MAXS = 80;          // padded sequence length the tiles cover (5 x 16)
 constexpr int SA_DH = 128;
-constexpr int SA_LDX = SA_DH + 1;    // Q, K, V, dO rows
-constexpr int SA_LDP = SA_MAXS + 1;  // P, dP rows
+constexpr int SA_LDX = SA_DH + 4;    // Q, K, V, dO rows: 16-byte aligned, conflict-free for the 128-bit loads of smem_gemm_*2
+constexpr int SA_LDP = SA_MAXS + 4;  // P, dP rows
 
 // rows [0, S) x 128 columns of N global matrices (leading dimension ld, 16-byte aligned rows) -> smem [SA_MAXS][SA_LDX],
 // rows >= S zero.  256 threads; every thread issues its 10 float4 loads per matrix before the first shared-memory store, so
@@ -744,8 +744,7 @@ __device__ __forceinline__ void sa_load(float* const (&dst)[N], const float* con
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       const int idx = threadIdx.x + 256 * i, r = idx >> 5, c4 = idx & 31;
-      float* d = dst[m] + r * SA_LDX + 4 * c4;
-      d[0] = v[m][i].x; d[1] = v[m][i].y; d[2] = v[m][i].z; d[3] = v[m][i].w;
+      *reinterpret_cast<float4*>(dst[m] + r * SA_LDX + 4 * c4) = v[m][i];
     }
 }
 // [S][S] global -> smem [SA_MAXS][SA_LDP], zero padded (25 independent loads per thread)
@@ -808,12 +807,11 @@ __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __r
 #pragma unroll
     for (int i = 0; i < ROWS * (SA_DH / 4) / 256; ++i) {
       const int idx = threadIdx.x + 256 * i;
-      float* d = Qs + (idx >> 5) * SA_LDX + 4 * (idx & 31);
-      d[0] = q[i].x; d[1] = q[i].y; d[2] = q[i].z; d[3] = q[i].w;
+      *reinterpret_cast<float4*>(Qs + (idx >> 5) * SA_LDX + 4 * (idx & 31)) = q[i];
     }
   }
   __syncthreads();
-  smem_gemm<false, true, TM, 5>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v) { Ps[i * SA_LDP + j] = v * scale; });
+  smem_gemm_nt2<TM, 5>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v) { Ps[i * SA_LDP + j] = v * scale; });
   __syncthreads();
   {
     float* const dst[1] = {Vs};
@@ -857,7 +855,7 @@ __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __r
   __syncthreads();
   float* og = ao + (long long)seq * S * d_model + head * SA_DH;
   __nv_bfloat16* ob = ao_bf ? ao_bf + (long long)seq * S * d_model + head * SA_DH : nullptr;  // operand of the out-projection
-  smem_gemm<false, false, TM, 8>(Ps, SA_LDP, Vs, SA_LDX, SA_MAXS, [&](int li, int c, float v) {
+  smem_gemm_n128<false, TM>(Ps, SA_LDP, Vs, SA_LDX, SA_MAXS, [&](int li, int c, float v) {
     const int i = r0 + li;
     if (i < S) {
       og[(long long)i * d_model + c] = v;
@@ -895,11 +893,11 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   sa_load_p(Ps, (drop.on() ? pd_in : p_in) + pp, S);
   __syncthreads();
   // dV = Pd^T dO
-  smem_gemm<true, false, 5, 8>(Ps, SA_LDP, Os, SA_LDX, SA_MAXS, [&](int j, int c, float v) {
+  smem_gemm_n128<true, 5>(Ps, SA_LDP, Os, SA_LDX, SA_MAXS, [&](int j, int c, float v) {
     if (j < S) dbase[(long long)j * 3 * d_model + 2 * d_model + c] = v;
   });
   // dP = dO V^T (masked like the forward's dropout)
-  smem_gemm<false, true, 5, 5>(Os, SA_LDX, Vs, SA_LDX, SA_DH, [&](int i, int j, float v) {
+  smem_gemm_nt2<5, 5>(Os, SA_LDX, Vs, SA_LDX, SA_DH, [&](int i, int j, float v) {
     if (drop.on() && i < S && j < S) v *= drop_scale1(drop, site, seq, ((long long)head * S + i) * S + j);
     Ds[i * SA_LDP + j] = v;
   });
@@ -920,15 +918,15 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   }
   __syncthreads();
   // dQ = scale dS K ;  dK = scale dS^T Q
-  smem_gemm<false, false, 5, 8>(Ds, SA_LDP, Ks, SA_LDX, SA_MAXS, [&](int i, int c, float v) {
+  smem_gemm_n128<false, 5>(Ds, SA_LDP, Ks, SA_LDX, SA_MAXS, [&](int i, int c, float v) {
     if (i < S) dbase[(long long)i * 3 * d_model + c] = v * scale;
   });
-  smem_gemm<true, false, 5, 8>(Ds, SA_LDP, Qs, SA_LDX, SA_MAXS, [&](int j, int c, float v) {
+  smem_gemm_n128<true, 5>(Ds, SA_LDP, Qs, SA_LDX, SA_MAXS, [&](int j, int c, float v) {
     if (j < S) dbase[(long long)j * 3 * d_model + d_model + c] = v * scale;
   });
 }
 
-constexpr size_t SA_FWD_SMEM = (size_t)(2 * SA_MAXS * SA_LDX + SA_MAXS * SA_LDP) * sizeof(float);  // 108 KB: 2 CTAs per SM
+constexpr size_t SA_FWD_SMEM = (size_t)(2 * SA_MAXS * SA_LDX + SA_MAXS * SA_LDP) * sizeof(float);  // 111 KB: 2 CTAs per SM
 constexpr size_t SA_BWD_SMEM = (size_t)(4 * SA_MAXS * SA_LDX + 2 * SA_MAXS * SA_LDP) * sizeof(float);
 static_assert(SA_BWD_SMEM <= 227 * 1024, "small-attention backward shared memory");
 
