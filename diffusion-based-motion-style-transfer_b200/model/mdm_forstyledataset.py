@@ -164,7 +164,7 @@ class _DenoiserGradFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, native, x, temb, text_emb, uncond, *params):
-        eng = native.mst_engine(x.device, precision=native.mst_train_prec())
+        eng = native.__dict__.pop("_mst_eng_hint", None) or native.mst_engine(x.device, precision=native.mst_train_prec())
         B = x.shape[0]
         slot, k = native._mst_tape_acquire(eng, B, x.shape[-1], text_emb is not None)
         ctx.native, ctx.eng, ctx.slot, ctx.k = native, eng, slot, k
@@ -548,12 +548,12 @@ class NativeDenoiser(nn.Module):
     def mst_text_cache_clear(self):
         self.__dict__.pop("_mst_text_cache", None)
 
-    def text_embedding(self, y, device, precision=None):
+    def text_embedding(self, y, device, precision=None, eng=None):
         """embed_text(mask_cond(clip(text))) [B, d]; computed once per trajectory by the sampler."""
         feat = self.text_features(y, device)
         if feat is None:
             return None
-        return self.mst_engine(device, precision).text_embed(feat)
+        return (eng or self.mst_engine(device, precision)).text_embed(feat)
 
     @staticmethod
     def compact_mask(mask):
@@ -584,9 +584,10 @@ class NativeDenoiser(nn.Module):
             with torch.no_grad():
                 eng = self.mst_engine(x.device, precision=self.mst_train_prec())
                 temb = eng.time_embed(timesteps)
-                text_emb = None if force_mask else self.text_embedding(y, x.device, precision=self.mst_train_prec())
+                text_emb = None if force_mask else self.text_embedding(y, x.device, eng=eng)
             if 'text' in self.cond_mode and text_emb is None and not force_mask:
                 raise RuntimeError("text-conditioned model called without text")
+            self.__dict__["_mst_eng_hint"] = eng  # the bridge below would otherwise fingerprint the weights a third time
             return _DenoiserGradFn.apply(self, xc, temb, text_emb, force_mask or text_emb is None, *enc_params)
         eng = self.mst_engine(x.device)
         temb = eng.time_embed(timesteps)
