@@ -71,6 +71,20 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 int sm_count();  // cached multiProcessorCount of the current device
 
+// first() is true once per CUDA device: per-function attributes (cudaFuncSetAttribute) belong to a device, so a process
+// that touches a second GPU must set them again there
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // ---------------------------------------------------------------------------
 // engine (defined in api.cu); kernels get what they need through these structs
 // ---------------------------------------------------------------------------

@@ -281,10 +281,9 @@ int attention_f32(const float* qkv, float* out, int n_seqs, int S, int d, int n_
   const int dh = d / n_heads;
   size_t smem = ((size_t)S * (dh + 1) + (size_t)ATT_QROWS * dh + (size_t)ATT_QROWS * S) * sizeof(float);
   if (smem > 220 * 1024) return fail(MST_ERR_UNSUPPORTED, "attention_f32: sequence too long for shared memory");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
+  if (attr_set.first()) {
     MST_CUDA_OK(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
   }
   dim3 grid(ceil_div(S, ATT_QROWS), n_heads, n_seqs);
   attention_f32_kernel<<<grid, 128, smem, s>>>(qkv, out, S, d, dh, 1.0f / sqrtf((float)dh));

@@ -414,10 +414,9 @@ int tc_attention(const TcAttnParams& p, cudaStream_t s) {
   if ((rc = make_tmap_bf16_3d(&tkv, p.qkv, p.n_seqs, p.S, ld, ld, (uint64_t)p.S * ld, (uint32_t)s_pad, 64, 128))) return rc;
   if ((rc = make_tmap_bf16_3d(&to, p.out, p.n_seqs, p.S, p.d_model, p.d_model, (uint64_t)p.S * p.d_model, 32, 32, 64)))
     return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
+  if (attr_set.first()) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    attr_set = true;
   }
   AttnGeom g;
   g.S = p.S;

@@ -1036,10 +1036,9 @@ static int launch_gemm(const TcGemmParams& p, cudaStream_t s) {
   int rc;
   if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, BN, BLOCK_K))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
+  if (attr_set.first()) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int tiles = ceil_div(p.M, BLOCK_M) * (p.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -1083,10 +1082,9 @@ static int launch_gemm_pair(const TcGemmParams& p, cudaStream_t s) {
   if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN / 2, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16_3d(&to, p.out, 1, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, (uint64_t)p.M * p.ldo, 32, 32, 64)))
     return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
+  if (attr_set.first()) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int tiles = ceil_div(ceil_div(p.M, BLOCK_M), 2) * (p.N / Cfg::BN);
   static const int max_clusters = max_active_clusters(tc_gemm_pair_kernel<EPI>, 2, Cfg::THREADS, Cfg::SMEM_BYTES);
@@ -1105,10 +1103,9 @@ static int launch_gemm_ln(const TcGemmParams& p, cudaStream_t s) {
   if ((rc = make_tmap_bf16(&tr, p.residual, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, BLOCK_M, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&to, p.out, 1, (uint64_t)p.M, (uint64_t)LN_N, (uint64_t)LN_N, (uint64_t)p.M * LN_N, 32, 32, 64)))
     return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
+  if (attr_set.first()) {
     MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int m_pairs = ceil_div(ceil_div(p.M, BLOCK_M), 2);
   static const int max_clusters = max_active_clusters(tc_gemm_ln_kernel, 4, GEMM_THREADS, Cfg::SMEM_BYTES);

@@ -264,11 +264,10 @@ static int ct_forward(ClipText* e, const int32_t* tokens, int batch, float* feat
   MST_CUDA_OK(launch_pdl(ct_embed_kernel, dim3(d.ctx, batch), dim3(128), 0, s, tokens, e->w.token_embedding,
                          e->w.positional_embedding, wk.x, d.ctx, d.width, d.vocab));
   MST_LAUNCHED("clip_text_embed", s);
-  static bool smem_set = false;
-  if (!smem_set) {
+  static PerDeviceOnce smem_set;  // cudaFuncSetAttribute is per device
+  if (smem_set.first()) {
     MST_CUDA_OK(cudaFuncSetAttribute(ct_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_ATTN_SMEM));
     MST_CUDA_OK(cudaFuncSetAttribute(ct_attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_ATTN_SMEM));
-    smem_set = true;
   }
   float* x = wk.x;
   float* x2 = wk.x2;

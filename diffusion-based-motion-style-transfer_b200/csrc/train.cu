@@ -1017,11 +1017,10 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
     const bool x_staged = tc && fused && l > 0;  // the previous layer's LayerNorm kernel staged it
     if ((rc = linear_fwd(tc, tp.stage, t.x, lqkv, L.qkv_b, nullptr, t.qkv, M, s, "train_qkv", x_staged))) return rc;
     if (attn_small_ok(d, S)) {
-      static bool attr_set = false;
-      if (!attr_set) {
+      static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
+      if (attr_set.first()) {
         MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
         MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
-        attr_set = true;
       }
       if (NS * H <= 32) {  // a handful of (sequence, head) pairs: five CTAs each
         MST_CUDA_OK(launch_pdl(attn_small_fwd_kernel<1>, dim3(H, NS, 5), dim3(256), SA_FWD_SMEM, s, (const float*)t.qkv, key_valid,
@@ -1180,10 +1179,9 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     if ((rc = linear_bwd(tc, w.stage, dz1g, t.ao, lo, nullptr, dao, G.o_w, G.o_b, M, s, "bwd_dao", "bwd_dwo"))) return rc;
     // attention
     if (attn_small_ok(d, S)) {
-      static bool attr_set = false;
-      if (!attr_set) {
+      static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
+      if (attr_set.first()) {
         MST_CUDA_OK(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_BWD_SMEM));
-        attr_set = true;
       }
       MST_CUDA_OK(launch_pdl(attn_small_bwd_kernel, dim3(H, NS), dim3(256), SA_BWD_SMEM, s, (const float*)t.qkv, (const float*)t.p,
                              (const float*)t.pd, (const float*)dao, w.dqkv, S, dm, H, scale, drop, drop_site(l, 1)));
