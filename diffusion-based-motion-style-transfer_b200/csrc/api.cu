@@ -149,6 +149,11 @@ static size_t packed_bytes(const mst_model_desc& d, int f_pad) {
     c.take<__nv_bfloat16>((size_t)d.d_ff * d.d_model);
     c.take<__nv_bfloat16>((size_t)d.d_model * d.d_ff);
   }
+  c.take<__half>((size_t)f_pad * d.d_model);  // fp16 residual stream: final projection, QKV and linear1 weights
+  for (int l = 0; l < d.n_layers; ++l) {
+    c.take<__half>((size_t)3 * d.d_model * d.d_model);
+    c.take<__half>((size_t)d.d_ff * d.d_model);
+  }
   return align_up(c.off, 1024);
 }
 
@@ -330,6 +335,21 @@ extern "C" int mst_engine_load_weights(mst_engine_t h, const mst_weights* w, voi
       if ((rc = cvt_bf16(L.w2, d.d_model, d.d_ff, d.d_ff, nullptr, w2, d.d_model, s))) return rc;
       e->lbt[l] = LayerBF16T{qkv, o, w1, w2};
     }
+    {
+      auto* out_h = c.take<__half>((size_t)e->f_pad * d.d_model);
+      if ((rc = pack_f16(w->out_w, out_h, d.n_feats, d.d_model, e->f_pad, d.d_model, s))) return rc;
+      e->out_w_h = out_h;
+      for (int l = 0; l < d.n_layers; ++l) {
+        const mst_layer_weights& L = w->layers[l];
+        auto* qkv = c.take<__half>((size_t)3 * d.d_model * d.d_model);
+        auto* w1 = c.take<__half>((size_t)d.d_ff * d.d_model);
+        if ((rc = pack_f16(L.qkv_w, qkv, 3 * d.d_model, d.d_model, 3 * d.d_model, d.d_model, s))) return rc;
+        if ((rc = pack_f16(L.w1, w1, d.d_ff, d.d_model, d.d_ff, d.d_model, s))) return rc;
+        e->lh[l] = LayerF16{qkv, w1};
+      }
+      const char* env = getenv("MST_STREAM_F16");
+      e->stream_f16 = !(env && env[0] == '0');
+    }
   }
   e->weights_loaded = true;
   return MST_OK;
@@ -436,13 +456,15 @@ static int forward_bf16(Engine* e, const mst_forward_args& a, cudaStream_t s) {
   const mst_model_desc& d = e->desc;
   const int B = a.batch, T = a.n_frames, S = T + 1, n_pass = a.cfg ? 2 : 1, NS = B * n_pass;
   const int M = NS * S, dm = d.d_model;
+  const int f16 = e->stream_f16 ? 1 : 0;  // fp16 residual stream (x, y)
   WsBF16 w;
   size_t need = carve_bf16(d, e->f_pad, NS, T, a.workspace, &w);
   MST_CHECK_ARG(a.workspace_bytes >= need, "workspace too small");
   int rc;
   Token0Params t0;
   t0.temb = a.temb; t0.temb_row_dev = a.temb_row_dev; t0.temb_row_offset = a.temb_row_offset;
-  t0.text_emb = a.text_emb; t0.txt_b = e->txt_b; t0.pe = e->pe; t0.x_bf16 = w.x;
+  t0.text_emb = a.text_emb; t0.txt_b = e->txt_b; t0.pe = e->pe;
+  if (f16) t0.x_f16 = reinterpret_cast<__half*>(w.x); else t0.x_bf16 = w.x;
   t0.B = B; t0.T = T; t0.d = dm; t0.cfg = a.cfg; t0.uncond = a.uncond;
   if ((rc = token0(t0, NS, s))) return rc;
   if ((rc = motion_to_tokens_bf16(a.x, w.xa, B, d.n_feats, T, e->f_pad, s))) return rc;
@@ -450,13 +472,15 @@ static int forward_bf16(Engine* e, const mst_forward_args& a, cudaStream_t s) {
     TcGemmParams p;
     p.a = w.xa; p.w = e->in_w_bf; p.bias = e->in_b; p.out = w.x; p.ldo = dm;
     p.M = B * T; p.N = dm; p.K = e->f_pad; p.epi = TC_EPI_INPROJ; p.pe = e->pe; p.B = B; p.T = T; p.n_pass = n_pass;
+    p.io_f16 = f16;
     if ((rc = tc_gemm(p, s))) return rc;
   }
   for (int l = 0; l < d.n_layers; ++l) {
     const LayerF32& L = e->lf[l];
     const LayerBF16& Lb = e->lb[l];
     TcGemmParams p;
-    p.a = w.x; p.w = Lb.qkv_w; p.bias = L.qkv_b; p.out = w.qkv; p.ldo = 3 * dm;
+    p.a = w.x; p.w = f16 ? reinterpret_cast<const __nv_bfloat16*>(e->lh[l].qkv_w) : Lb.qkv_w; p.bias = L.qkv_b;
+    p.out = w.qkv; p.ldo = 3 * dm; p.ab_f16 = f16;
     p.M = M; p.N = 3 * dm; p.K = dm; p.epi = TC_EPI_BIAS_BF16;
     if ((rc = tc_gemm(p, s))) return rc;
     TcAttnParams at;
@@ -464,20 +488,22 @@ static int forward_bf16(Engine* e, const mst_forward_args& a, cudaStream_t s) {
     if ((rc = tc_attention(at, s))) return rc;
     TcGemmParams o;
     o.a = w.ao; o.w = Lb.o_w; o.bias = L.o_b; o.out = w.y; o.ldo = dm; o.M = M; o.N = dm; o.K = dm;
-    o.epi = TC_EPI_BIAS_RES_LN; o.residual = w.x; o.ln_g = L.ln1_g; o.ln_b = L.ln1_b;
+    o.epi = TC_EPI_BIAS_RES_LN; o.residual = w.x; o.ln_g = L.ln1_g; o.ln_b = L.ln1_b; o.io_f16 = f16;
     if ((rc = tc_gemm(o, s))) return rc;
     TcGemmParams f1;
-    f1.a = w.y; f1.w = Lb.w1; f1.bias = L.b1; f1.out = w.h; f1.ldo = d.d_ff; f1.M = M; f1.N = d.d_ff; f1.K = dm;
+    f1.a = w.y; f1.w = f16 ? reinterpret_cast<const __nv_bfloat16*>(e->lh[l].w1) : Lb.w1; f1.bias = L.b1; f1.out = w.h;
+    f1.ldo = d.d_ff; f1.M = M; f1.N = d.d_ff; f1.K = dm; f1.ab_f16 = f16;
     f1.epi = TC_EPI_BIAS_GELU_BF16;
     if ((rc = tc_gemm(f1, s))) return rc;
     TcGemmParams f2;
     f2.a = w.h; f2.w = Lb.w2; f2.bias = L.b2; f2.out = w.x; f2.ldo = dm; f2.M = M; f2.N = dm; f2.K = d.d_ff;
-    f2.epi = TC_EPI_BIAS_RES_LN; f2.residual = w.y; f2.ln_g = L.ln2_g; f2.ln_b = L.ln2_b;
+    f2.epi = TC_EPI_BIAS_RES_LN; f2.residual = w.y; f2.ln_g = L.ln2_g; f2.ln_b = L.ln2_b; f2.io_f16 = f16;
     if ((rc = tc_gemm(f2, s))) return rc;
   }
   {
     TcGemmParams p;
-    p.a = w.x; p.w = e->out_w_bf; p.bias = e->out_b_pad; p.out = a.out_cond; p.out2 = a.out_uncond;
+    p.a = w.x; p.w = f16 ? reinterpret_cast<const __nv_bfloat16*>(e->out_w_h) : e->out_w_bf; p.ab_f16 = f16;
+    p.bias = e->out_b_pad; p.out = a.out_cond; p.out2 = a.out_uncond;
     p.M = M; p.N = e->f_pad; p.K = dm; p.epi = TC_EPI_OUTPROJ_F32; p.B = B; p.T = T; p.n_valid = d.n_feats;
     if ((rc = tc_gemm(p, s))) return rc;
   }

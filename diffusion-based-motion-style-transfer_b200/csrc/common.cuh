@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -95,6 +96,9 @@ struct LayerF32 {
 struct LayerBF16 {
   const __nv_bfloat16 *qkv_w, *o_w, *w1, *w2;  // [N, K] row-major bf16
 };
+struct LayerF16 {
+  const __half *qkv_w, *w1;  // fp16 copies of the two weights that multiply the fp16 residual stream (sampler only)
+};
 struct LayerBF16T {
   const __nv_bfloat16 *qkv_w, *o_w, *w1, *w2;  // the same weights transposed, [K, N] row-major (dX = dY W)
 };
@@ -111,6 +115,11 @@ struct Engine {
   const float* out_b_pad = nullptr;         // [Fpad]
   LayerBF16 lb[MST_MAX_LAYERS];
   LayerBF16T lbt[MST_MAX_LAYERS];
+  // fp16 residual stream of the sampler (MST_STREAM_F16, default on): LayerNorm outputs / in-projection output are
+  // written in IEEE fp16, and the GEMMs that read them (QKV, FFN linear1, final projection) use fp16 weights
+  bool stream_f16 = false;
+  LayerF16 lh[MST_MAX_LAYERS];
+  const __half* out_w_h = nullptr;  // [Fpad, d]
   int f_pad = 0;  // F rounded up to 64
 };
 

@@ -165,6 +165,7 @@ __global__ void token0_kernel(Token0Params p) {
     int64_t o = (int64_t)seq * S * p.d + n;
     if (p.x_f32) p.x_f32[o] = v;
     if (p.x_bf16) p.x_bf16[o] = __float2bfloat16_rn(v);
+    if (p.x_f16) p.x_f16[o] = __float2half_rn(v);
   }
 }
 

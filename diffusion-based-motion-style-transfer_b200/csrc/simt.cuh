@@ -36,6 +36,7 @@ struct Token0Params {
   const float* pe = nullptr;
   float* x_f32 = nullptr;
   __nv_bfloat16* x_bf16 = nullptr;
+  __half* x_f16 = nullptr;  // fp16 residual stream of the sampler
   int B = 0, T = 0, d = 0, cfg = 0, uncond = 0;
 };
 

@@ -35,6 +35,9 @@ struct TcGemmParams {
   float* out2 = nullptr;  // OUTPROJ: rows of sequences >= B go here (uncond pass)
   const float* add = nullptr;  // TRAIN_F32: fp32 tensor with out's layout added to the result (residual paths)
   int accumulate = 0;          // TRAIN_F32: out += result (gradient accumulation)
+  // 16-bit format switches of the sampler's residual stream (see tc_gemm_ln5_kernel): IEEE fp16 instead of bf16
+  int ab_f16 = 0;  // A and W hold fp16 (QKV, FFN1 and the final projection read the fp16 stream)
+  int io_f16 = 0;  // RES_LN: residual and output are fp16;  INPROJ: output is fp16
 };
 
 int tc_gemm(const TcGemmParams& p, cudaStream_t s);
@@ -45,6 +48,9 @@ int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T,
 
 // fp32 [rows, cols] -> bf16 [rows_pad, cols_pad] zero padded (weight packing)
 int pack_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, int rows_pad, int cols_pad, cudaStream_t s);
+
+// the same into IEEE fp16
+int pack_f16(const float* src, __half* dst, int rows, int cols, int rows_pad, int cols_pad, cudaStream_t s);
 
 // fp32 [rows, cols] (leading dimension ld) -> bf16 copy dst [rows, cols] and / or transposed copy dst_t [cols, rows_pad]
 // (columns [rows, rows_pad) zero): operands of the training GEMMs (dX needs W^T, dW needs dY^T and X^T)

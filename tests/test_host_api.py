@@ -180,8 +180,10 @@ def test_argument_validation_without_gpu():
     assert lib.mst_engine_packed_weight_bytes(h, ctypes.byref(nbytes)) == 0
     # bf16 [N,K] packs of the six GEMM weights per layer + the in/out projections, plus the transposed [K,N] packs
     # of the layer weights that the training backward (dX = dY W) reads
+    # ... plus the fp16 copies of the three weights that multiply the sampler's fp16 residual stream (QKV, linear1, final)
     layer_w = 16822272 - 8 * 6656
-    assert abs(nbytes.value - (2 * layer_w + 2 * 192 * 512) * 2) < 64 * 1024
+    f16_w = 8 * (3 * 512 * 512 + 1024 * 512) + 192 * 512
+    assert abs(nbytes.value - (2 * layer_w + 2 * 192 * 512 + f16_w) * 2) < 64 * 1024
     assert lib.mst_engine_destroy(h) == 0
     a = L.UpdateArgs()
     assert lib.mst_update_step(ctypes.byref(a), None) == 1 and b"empty shape" in lib.mst_last_error()

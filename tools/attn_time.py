@@ -48,6 +48,7 @@ print("MMA thread stamps (QK issue / PV issue, in issue order), cycles since fir
 for grp in range(2):
     e = [int(v) - t0 for v in d[2 + grp] if v != 0]
     print(f"softmax group {grp} (warp quad 0 lane 0): per item: top | s_full wait | pass1 (max) | pass2 (exp, P) | o_full wait | O drain+store")
-    for i in range(0, len(e) - 6, 7):
-        q = e[i:i + 7]
-        print(f"   item {i // 7}: top {q[0]:7d} | " + " | ".join(f"{b - a:5d}" for a, b in zip(q, q[1:])) + f" | total {q[6] - q[0]:6d}")
+    nst = int(os.environ.get("MST_ATTN_STAMPS", "7"))
+    for i in range(0, len(e) - nst + 1, nst):
+        q = e[i:i + nst]
+        print(f"   item {i // 7}: top {q[0]:7d} | " + " | ".join(f"{b - a:5d}" for a, b in zip(q, q[1:])) + f" | total {q[-1] - q[0]:6d}")
