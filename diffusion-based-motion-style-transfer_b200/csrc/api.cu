@@ -466,8 +466,7 @@ static int forward_bf16(Engine* e, const mst_forward_args& a, cudaStream_t s) {
   t0.text_emb = a.text_emb; t0.txt_b = e->txt_b; t0.pe = e->pe;
   if (f16) t0.x_f16 = reinterpret_cast<__half*>(w.x); else t0.x_bf16 = w.x;
   t0.B = B; t0.T = T; t0.d = dm; t0.cfg = a.cfg; t0.uncond = a.uncond;
-  if ((rc = token0(t0, NS, s))) return rc;
-  if ((rc = motion_to_tokens_bf16(a.x, w.xa, B, d.n_feats, T, e->f_pad, s))) return rc;
+  if ((rc = motion_to_tokens_bf16(a.x, w.xa, B, d.n_feats, T, e->f_pad, &t0, NS, s))) return rc;
   {
     TcGemmParams p;
     p.a = w.xa; p.w = e->in_w_bf; p.bias = e->in_b; p.out = w.x; p.ldo = dm;

@@ -44,7 +44,10 @@ int tc_gemm(const TcGemmParams& p, cudaStream_t s);
 void set_gemm_debug(long long* dev_buf);  // device buffer of >= 3*2*1024 int64 (or nullptr to switch off)
 
 // x [B,F,T] fp32 -> A operand of the in-projection: bf16 [B*T, f_pad], zero padded
-int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T, int f_pad, cudaStream_t s);
+struct Token0Params;
+// ... and, when t0 is given, token 0 of the n_seqs sequences in the same launch (see simt.cuh)
+int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T, int f_pad, const Token0Params* t0,
+                          int n_seqs, cudaStream_t s);
 
 // fp32 [rows, cols] -> bf16 [rows_pad, cols_pad] zero padded (weight packing)
 int pack_bf16(const float* src, __nv_bfloat16* dst, int rows, int cols, int rows_pad, int cols_pad, cudaStream_t s);

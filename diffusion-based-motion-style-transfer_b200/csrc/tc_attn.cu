@@ -1194,11 +1194,11 @@ int tc_attention(const TcAttnParams& p, cudaStream_t s) {
   g.scale_log2e = 1.4426950408889634f / sqrtf((float)ATT_DH);
   g.dbg = attn_debug_ptr();
   {
-    static const int poll = getenv("MST_ATTN_POLL") ? atoi(getenv("MST_ATTN_POLL")) : 1;
+    static const int poll = getenv("MST_ATTN_POLL") ? atoi(getenv("MST_ATTN_POLL")) : 0;
     g.mma_poll = poll;
   }
   const int grid = g.n_items < sm_count() ? g.n_items : sm_count();
-  static const int attn_v = getenv("MST_ATTN_V") ? atoi(getenv("MST_ATTN_V")) : 4;
+  static const int attn_v = getenv("MST_ATTN_V") ? atoi(getenv("MST_ATTN_V")) : 2;
   if (attn_v == 4) {
     static PerDeviceOnce attr4_set;
     if (attr4_set.first()) {

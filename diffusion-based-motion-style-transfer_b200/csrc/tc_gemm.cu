@@ -26,6 +26,7 @@
 //   linear1 + GELU                                                 TC_EPI_BIAS_GELU_BF16
 //   linear2 + residual + norm2                                     TC_EPI_BIAS_RES_LN
 //   OutputProcess.poseFinal + permute back to [B,F,1,T] (:467-477) TC_EPI_OUTPROJ_F32
+#include "simt.cuh"
 #include "tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -85,7 +86,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : (2 * BN >= 128 ? 128 : 64));
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int OBOX_BYTES = 32 * 64;  // in-projection epilogue: one [32 rows x 32 cols] transpose box per warp
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + NUM_EPI_WARPS * OBOX_BYTES;
 };
 
 // ---- GELU for the FFN epilogue --------------------------------------------------------------------------
@@ -333,7 +335,47 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + col), v);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, row, n_blk * BN + col, v);
+        if constexpr (EPI == TC_EPI_INPROJ) {
+          // acc + bias + positional row -> 16-bit -> the warp's swizzled [32 x 32] box -> read back 8 rows x 64 bytes per
+          // instruction -> coalesced 16-byte stores to the token rows of every CFG pass (a row-per-thread store of the
+          // same data wrote half sectors of 32 different lines per instruction: 29 us for a 4.6 GFLOP GEMM)
+          const int n = n_blk * BN + col;
+          const uint32_t box = ring.bar_base + Cfg::BAR_BYTES + (uint32_t)ew * Cfg::OBOX_BYTES;
+          uint32_t o[16];
+          {
+            const int rb = row < p.M ? row / p.T : 0, rt = row < p.M ? row - rb * p.T : 0;
+            const float* pe = p.pe + (size_t)(rt + 1) * p.N + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              const float4 e4 = __ldg(reinterpret_cast<const float4*>(pe + j));
+              const float x0 = __uint_as_float(v[j]) + b4.x + e4.x, x1 = __uint_as_float(v[j + 1]) + b4.y + e4.y;
+              const float x2 = __uint_as_float(v[j + 2]) + b4.z + e4.z, x3 = __uint_as_float(v[j + 3]) + b4.w + e4.w;
+              o[j >> 1] = p.io_f16 ? pack_f16x2(x0, x1) : pack_bf16x2(x0, x1);
+              o[(j >> 1) + 1] = p.io_f16 ? pack_f16x2(x2, x3) : pack_bf16x2(x2, x3);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(box + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+          __syncwarp();
+          const int piece = lane & 3, S = p.T + 1;
+          uint16_t* const out16 = static_cast<uint16_t*>(p.out);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rr = k * 8 + (lane >> 2);
+            const uint4 val = lds128(box + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
+            const int grow = m_blk * BLOCK_M + quad * 32 + rr;
+            if (grow < p.M) {
+              const int b = grow / p.T, t = grow - b * p.T;
+              for (int pass = 0; pass < p.n_pass; ++pass)
+                *reinterpret_cast<uint4*>(out16 + ((size_t)(pass * p.B + b) * S + t + 1) * p.ldo + n + piece * 8) = val;
+            }
+          }
+          __syncwarp();
+        } else {
+          epilogue_chunk<EPI>(p, row, n_blk * BN + col, v);
+        }
       }
       tc_fence_before();
       mbar_arrive(ring.tempty(acc));
@@ -1559,27 +1601,53 @@ int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
 // layout helpers
 // ---------------------------------------------------------------------------
 // x[b][f][t] fp32 -> a[(b*T + t)][f] bf16, columns [F, f_pad) zero.  32x32 smem transpose.
+// The same launch also writes token 0 of every sequence (blockIdx.y == gridDim.y - 1, one block per (pass, b)):
+// temb[row] + (uncond ? txt_b : text_emb[b]) + pe[0]   (reference mdm_forstyledataset.py:322-327, :344-345) -
+// one launch less per denoise step than a separate token-0 kernel.
 __global__ void __launch_bounds__(256) motion_to_tokens_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a,
-                                                               int F, int T, int f_pad) {
+                                                               int F, int T, int f_pad, const Token0Params t0, int n_seqs) {
   pdl_launch_dependents();
-  pdl_wait();
+  pdl_wait();  // *temb_row_dev is decremented by the previous step's update kernel
+  if (blockIdx.y == gridDim.y - 1) {
+    const int seq = blockIdx.z * gridDim.x + blockIdx.x;
+    if (seq >= n_seqs || (!t0.x_bf16 && !t0.x_f16 && !t0.x_f32)) return;
+    const int b = seq % t0.B;
+    const bool uncond = t0.cfg ? (seq >= t0.B) : (t0.uncond != 0);
+    const int row = t0.temb_row_dev ? (*t0.temb_row_dev + t0.temb_row_offset) : (b + t0.temb_row_offset);
+    const int S = t0.T + 1;
+    for (int n = threadIdx.x; n < t0.d; n += blockDim.x) {
+      float v = t0.temb[(int64_t)row * t0.d + n];
+      if (t0.txt_b) v += (uncond || !t0.text_emb) ? t0.txt_b[n] : t0.text_emb[(int64_t)b * t0.d + n];
+      v += t0.pe[n];
+      const int64_t o = (int64_t)seq * S * t0.d + n;
+      if (t0.x_f32) t0.x_f32[o] = v;
+      if (t0.x_bf16) t0.x_bf16[o] = __float2bfloat16_rn(v);
+      if (t0.x_f16) t0.x_f16[o] = __float2half_rn(v);
+    }
+    return;
+  }
   __shared__ float tile[32][33];
-  const int b = blockIdx.z, f0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int b = blockIdx.z, f0 = blockIdx.y * 32, t0_ = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
-    int f = f0 + i, t = t0 + tx;
+    int f = f0 + i, t = t0_ + tx;
     tile[i][tx] = (f < F && t < T) ? x[((size_t)b * F + f) * T + t] : 0.0f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
-    int t = t0 + i, f = f0 + tx;
+    int t = t0_ + i, f = f0 + tx;
     if (t < T && f < f_pad) a[((size_t)b * T + t) * f_pad + f] = __float2bfloat16_rn(tile[tx][i]);
   }
 }
 
-int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T, int f_pad, cudaStream_t s) {
-  dim3 grid(ceil_div(T, 32), ceil_div(f_pad, 32), B);
-  MST_CUDA_OK(launch_pdl(motion_to_tokens_kernel, grid, dim3(256), 0, s, x, a, F, T, f_pad));
+int motion_to_tokens_bf16(const float* x, __nv_bfloat16* a, int B, int F, int T, int f_pad, const Token0Params* t0,
+                          int n_seqs, cudaStream_t s) {
+  Token0Params tp;
+  if (t0) tp = *t0;
+  int gx = ceil_div(T, 32);
+  if (t0 && gx * B < n_seqs) gx = ceil_div(n_seqs, B);  // enough token-0 blocks (surplus transpose blocks fall outside T)
+  dim3 grid(gx, ceil_div(f_pad, 32) + 1, B);
+  MST_CUDA_OK(launch_pdl(motion_to_tokens_kernel, grid, dim3(256), 0, s, x, a, F, T, f_pad, tp, t0 ? n_seqs : 0));
   MST_LAUNCHED("motion_to_tokens", s);
   return MST_OK;
 }

@@ -127,3 +127,23 @@ def test_oracle_clip_text_matches_independent_golden():
     tok2 = tok.clone()
     tok2[0, 20:30] = 5
     assert torch.equal(OC.encode_text(sd, tok), OC.encode_text(sd, tok2))
+
+
+def test_oracle_matches_headline_shape_golden(state):
+    """B=64, F=181, T=196, CFG scale 2.5 + root_horizontal inpainting: one DDPM step of the REAL reference
+    (tests/golden/make_golden_b64.py); four samples in full and three digests of all 64."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from b64_inputs import KEEP, b64_digests, b64_inputs
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "b64_step.npz")))
+    inp = b64_inputs()
+    sch = OSch.Schedule(OSch.cosine_betas(1000))
+    with torch.no_grad():
+        _, xs = OS.sample_loop(sch, lambda xx, tt: OD.cfg_forward(state, xx, tt, inp["feat"], inp["scale"]), inp["shape"],
+                               NoiseTape(3), mask=inp["mask"], x_inp=inp["x_inp"], stop_timesteps=999)
+    assert relerr(xs[0][KEEP], gold["x0_keep"]) < 5e-5
+    dig = b64_digests(xs[0])
+    for k in ("sum", "l2", "probe"):
+        scale = np.abs(gold["l2"]) if k != "probe" else np.abs(gold["l2"]) * 190.0  # |probe| ~ sqrt(F*T) = 188
+        assert np.max(np.abs(dig[k].numpy() - gold[k]) / scale) < 1e-4, k

@@ -153,7 +153,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t lbo,
   d |= 2ull << 61;
   return d;
 }
-__global__ void k_tmem_mma(long long* out, int nwarps_ld, int n_mma, int mma_n) {
+__global__ void __launch_bounds__(512) k_tmem_mma(long long* out, int nwarps_ld, int n_mma, int mma_n) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t slot;
   __shared__ __align__(8) unsigned long long bar;
