@@ -116,12 +116,31 @@ def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
             "-Xcompiler", "-fPIC", "-shared", "-o", out_path] + [os.path.join(_CSRC, s) for s in SOURCES]
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over the CUDA sources and headers the library is built from (content, not mtimes: the snapshot that
+    carries the built .so to a GPU box does not preserve timestamps)."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted([os.path.join(_CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(_CSRC, x)) for x in HEADERS]):
+        if os.path.exists(d):
+            h.update(os.path.basename(d).encode())
+            with open(d, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
+    """True when the library is missing or was built from other sources than the ones on disk."""
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(_CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(_CSRC, h)) for h in HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(HASH_PATH) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -134,6 +153,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB_PATH
 
 
@@ -195,20 +216,42 @@ def _declare(lib):
         fn.restype = C.c_int
 
 
+def _check_abi(lib):
+    """ctypes mirrors vs the structs the library was compiled with: a stale binary or a header edit without a matching
+    edit here would otherwise corrupt arguments silently."""
+    sz = [C.c_size_t() for _ in range(4)]
+    lib.mst_abi_sizes(*[C.byref(v) for v in sz])
+    got = [v.value for v in sz]
+    want = [C.sizeof(ModelDesc), C.sizeof(Weights), C.sizeof(ForwardArgs), C.sizeof(UpdateArgs)]
+    names = ["mst_model_desc", "mst_weights", "mst_forward_args", "mst_update_args"]
+    a, b = C.c_size_t(), C.c_size_t()
+    lib.mst_abi_sizes_train(C.byref(a), C.byref(b))
+    got += [a.value, b.value]
+    want += [C.sizeof(LayerGrads), C.sizeof(BackwardArgs)]
+    names += ["mst_layer_grads", "mst_backward_args"]
+    bad = [f"{n}: library {g} bytes, ctypes {w}" for n, g, w in zip(names, got, want) if g != w]
+    if bad:
+        raise RuntimeError(f"{LIB_PATH} does not match this Python package (ABI struct sizes differ: " + "; ".join(bad) +
+                           "); rebuild with `python __graft_entry__.py`")
+
+
 def load():
-    """dlopen libmst_b200.so (building it first when the sources are newer)."""
+    """dlopen libmst_b200.so.  The library is (re)built first when it is missing or was built from other sources than
+    the ones on disk (content hash, see source_hash) and a compiler is available; a stale library that cannot be
+    rebuilt raises instead of loading silently.  MST_NO_BUILD=1 never compiles."""
     global _lib
     with _lock:
         if _lib is None:
-            if not os.path.exists(LIB_PATH):
-                # built artefact missing: compile in-tree (nvcc cross-compiles without a GPU)
-                if os.environ.get("MST_NO_BUILD") == "1" or not os.path.exists(nvcc_command()[0]):
-                    raise RuntimeError(
-                        f"{LIB_PATH} is missing and cannot be built here; run `python __graft_entry__.py` "
-                        "(there is no CPU fallback)")
+            if needs_build():
+                can_build = os.environ.get("MST_NO_BUILD") != "1" and os.path.exists(nvcc_command()[0])
+                if not can_build:
+                    what = "is missing" if not os.path.exists(LIB_PATH) else "was built from different sources"
+                    raise RuntimeError(f"{LIB_PATH} {what} and cannot be built here; run `python __graft_entry__.py` "
+                                       "(there is no CPU fallback)")
                 build(force=True)
             lib = C.CDLL(LIB_PATH)
             _declare(lib)
+            _check_abi(lib)
             _lib = lib
     return _lib
 

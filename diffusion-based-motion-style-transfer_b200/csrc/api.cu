@@ -67,16 +67,15 @@ bool pdl_enabled() {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;
+  static int cached[64] = {};  // per device: a process may drive several GPUs (the reference selects one with --device N)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& c = cached[dev & 63];
+  if (c == 0) {
+    int n = 0;
+    c = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
   }
-  return cached;
+  return c;
 }
 
 // ---- workspace carving -----------------------------------------------------

@@ -1373,7 +1373,11 @@ static int run_graphed(bool use_graph, uint64_t key, cudaStream_t user, Body&& b
   }
   static std::mutex mu;
   static std::unordered_map<uint64_t, cudaGraphExec_t> cache;
-  static cudaStream_t cap_stream = nullptr;
+  static cudaStream_t cap_streams[64] = {};  // one capture stream per device (a stream belongs to the device it was made on)
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  cudaStream_t& cap_stream = cap_streams[dev_ & 63];
+  key ^= 0x9e3779b97f4a7c15ull * (uint64_t)(dev_ + 1);
   cudaGraphExec_t exec = nullptr;
   {
     std::lock_guard<std::mutex> lk(mu);
@@ -1396,7 +1400,7 @@ static int run_graphed(bool use_graph, uint64_t key, cudaStream_t user, Body&& b
     if (rc != MST_OK || e1 != cudaSuccess || !graph) {
       if (graph) cudaGraphDestroy(graph);
       cudaGetLastError();
-      return rc != MST_OK ? rc : body(user);
+      return body(user);  // capture failed (or the body reported an error while capturing): run - and report - eagerly
     }
     const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);

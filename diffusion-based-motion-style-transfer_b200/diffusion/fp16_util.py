@@ -95,6 +95,13 @@ class MixedPrecisionTrainer:
         for m in self._denoisers:
             m.mst_tape_pool = True
 
+    def master_params_to_state_dict(self, master_params=None):
+        """reference :225-228: the model's state_dict (the parameters ARE the master params in fp32 mode)"""
+        return self.model.state_dict()
+
+    def state_dict_to_master_params(self, state_dict):
+        return [state_dict[name] for name, _ in self.model.named_parameters()]
+
     def zero_grad(self):
         self.flat.ensure_grad_views()
         self.flat.grads.zero_()

@@ -657,6 +657,8 @@ class GaussianDiffusion:
         assert isinstance(shape, (tuple, list))
         if noise is not None:
             img = noise
+        elif self.noise_fn is not None:
+            img = self.noise_fn(-1, tuple(shape), device)  # test hook: draw -1 is x_T (the reference's th.randn(*shape))
         else:
             img = th.randn(*shape, device=device)
         if skip_timesteps and init_image is None:
@@ -826,7 +828,11 @@ class _TrajectoryPlan:
             self.inp.copy_(inp)
         self.temb.copy_(temb)
         self.seed_off = (int(seed), int(offset))
-        if self.use_graph and (self.graph is None or self.graph_key != self.seed_off):
+        # the captured launches bake in the Philox seed AND the engine's weight pointers (fp32 views of the parameters,
+        # packed copies): a reload of the weights - parameters moved, replaced or re-packed after an optimizer step -
+        # bumps the engine's generation and the step is captured again
+        want_key = (self.seed_off, self.eng.weights_generation)
+        if self.use_graph and (self.graph is None or self.graph_key != want_key):
             self._capture()
         self.t_dev.fill_(int(t_start))
         self.counter.zero_()
@@ -849,7 +855,7 @@ class _TrajectoryPlan:
         with th.cuda.graph(graph):
             self._one_step(*self.seed_off)
         self.launches_per_step = K.launch_count() - n0
-        self.graph, self.graph_key = graph, self.seed_off
+        self.graph, self.graph_key = graph, (self.seed_off, self.eng.weights_generation)
         self.x.copy_(snap)
 
     def step(self):

@@ -8,6 +8,7 @@ no CPU path).
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 from typing import Optional
 
@@ -25,6 +26,38 @@ def default_precision() -> str:
 
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _engine_device(fn):
+    """Run an Engine method with the engine's GPU current: kernels launch on the CUDA runtime's current device and on
+    its current stream, and the reference picks its GPU with ``--device N`` without ever calling ``set_device`` - the
+    model and its tensors may live on cuda:N while the process's current device is still 0."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
+def _tensor_device(fn):
+    """The same for the engine-less kernels: the first CUDA tensor among the arguments names the device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for v in list(args) + list(kwargs.values()):
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                dev = v.device
+                break
+            if isinstance(v, torch.device) and v.type == "cuda":
+                dev = v
+                break
+        if dev is None or dev.index is None or torch.cuda.current_device() == dev.index:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _ptr(t: Optional[torch.Tensor], dtype=torch.float32, name="tensor") -> Optional[int]:
@@ -63,6 +96,7 @@ class Engine:
         self._keep = None  # tensors whose storage the engine aliases
         self._ws = None
         self.n_feats, self.d_model = n_feats, d_model
+        self.weights_generation = 0  # bumped by every load_weights: captured graphs bake weight pointers in
 
     def __del__(self):
         try:
@@ -103,6 +137,7 @@ class Engine:
             L.check(self.lib.mst_engine_load_weights(self._h, C.byref(w), self._packed.data_ptr(), nbytes.value,
                                                      _stream_ptr()), "mst_engine_load_weights")
         self._keep = keep
+        self.weights_generation += 1
 
     # -- scratch -----------------------------------------------------------------
     def workspace_bytes(self, n_seqs: int, n_frames: int) -> int:
@@ -110,6 +145,7 @@ class Engine:
         L.check(self.lib.mst_engine_workspace_bytes(self._h, n_seqs, n_frames, C.byref(nbytes)))
         return int(nbytes.value)
 
+    @_engine_device
     def workspace(self, n_seqs: int, n_frames: int) -> torch.Tensor:
         """Engine-owned scratch for eager calls (grown on demand; captured graphs bring their own)."""
         nbytes = C.c_size_t()
@@ -119,6 +155,7 @@ class Engine:
         return self._ws
 
     # -- small embeddings ----------------------------------------------------------
+    @_engine_device
     def time_embed(self, t: torch.Tensor) -> torch.Tensor:
         """rows of time_embed(pe[t]) (reference TimestepEmbedder.forward, mdm_forstyledataset.py:421)."""
         t = t.to(self.device, torch.int64).contiguous()
@@ -129,6 +166,7 @@ class Engine:
                                         scratch.numel() * 4, _stream_ptr()), "mst_time_embed")
         return out
 
+    @_engine_device
     def text_embed(self, feat: torch.Tensor) -> torch.Tensor:
         """embed_text(feat) (reference mdm_forstyledataset.py:327)."""
         n = feat.shape[0]
@@ -138,6 +176,7 @@ class Engine:
         return out
 
     # -- forward -----------------------------------------------------------------
+    @_engine_device
     def forward(self, x: torch.Tensor, temb: torch.Tensor, text_emb: Optional[torch.Tensor], *, cfg: bool = False,
                 uncond: bool = False, out_cond: Optional[torch.Tensor] = None,
                 out_uncond: Optional[torch.Tensor] = None, temb_row_dev: Optional[torch.Tensor] = None,
@@ -178,6 +217,7 @@ class Engine:
             self._bwd_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self._bwd_scratch
 
+    @_engine_device
     def forward_train(self, x: torch.Tensor, temb: torch.Tensor, text_emb: Optional[torch.Tensor], *,
                       uncond: bool = False, tape: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                       use_graph: bool = False, dropout_p: float = 0.0, dropout_seed: Optional[torch.Tensor] = None,
@@ -211,6 +251,7 @@ class Engine:
                 "mst_denoiser_forward_train")
         return out, tape
 
+    @_engine_device
     def backward(self, d_out: torch.Tensor, tape: torch.Tensor, layer_grads: list, want_dx: bool = False,
                  use_graph: bool = False, dropout_p: float = 0.0, dropout_seed: Optional[torch.Tensor] = None,
                  tape_seqs: int = 0, tape_seq_offset: int = 0):
@@ -240,6 +281,7 @@ class Engine:
         L.check(self.lib.mst_denoiser_backward(self._h, C.byref(a), _stream_ptr()), "mst_denoiser_backward")
         return d_x
 
+    @_engine_device
     def motion_encoder_forward(self, x: torch.Tensor, key_valid: Optional[torch.Tensor], mu_query: torch.Tensor,
                                sigma_query: torch.Tensor, dropout_p: float = 0.0,
                                dropout_seed: Optional[torch.Tensor] = None, tape: Optional[torch.Tensor] = None,
@@ -258,6 +300,7 @@ class Engine:
             _stream_ptr()), "mst_motion_encoder_forward")
         return mu, tape
 
+    @_engine_device
     def motion_encoder_backward(self, d_mu: torch.Tensor, tape: torch.Tensor, shape, dropout_p: float = 0.0,
                                 dropout_seed: Optional[torch.Tensor] = None, d_x: Optional[torch.Tensor] = None,
                                 use_graph: bool = False):
@@ -410,6 +453,7 @@ class TapeSlot:
 # ---------------------------------------------------------------------------------
 # training kernels that need no engine
 # ---------------------------------------------------------------------------------
+@_tensor_device
 def masked_l2_forward(a, b, mask):
     """masked_l2 rows (reference gaussian_diffusion.py:223-235): a [Ra,F,1,T] (rows repeat), b [R,F,1,T], mask [Rm,1,1,T]."""
     R, F, T = b.shape[0], b.shape[1] * b.shape[2], b.shape[3]
@@ -419,6 +463,7 @@ def masked_l2_forward(a, b, mask):
     return loss
 
 
+@_tensor_device
 def masked_l2_backward(a, b, mask, grad_loss):
     R, F, T = b.shape[0], b.shape[1] * b.shape[2], b.shape[3]
     gb = torch.empty_like(b)
@@ -428,6 +473,7 @@ def masked_l2_backward(a, b, mask, grad_loss):
     return gb
 
 
+@_tensor_device
 def update_step_backward(d_x0, d_sample, k_table, t_vec, mask, pred_xstart, clip_denoised, shape):
     B, F, T = shape[0], shape[1] * shape[2], shape[3]
     ref = d_x0 if d_x0 is not None else d_sample
@@ -440,6 +486,7 @@ def update_step_backward(d_x0, d_sample, k_table, t_vec, mask, pred_xstart, clip
     return d_out
 
 
+@_tensor_device
 def recover_from_ric(x, joints_num, mean=None, std=None):
     """x [B,F,1,T] (sampler layout) -> joints [B,1,T,J,3]: inv_transform + recover_from_ric fused (scope row N2)."""
     B, F, T = x.shape[0], x.shape[1] * x.shape[2], x.shape[3]
@@ -449,6 +496,7 @@ def recover_from_ric(x, joints_num, mean=None, std=None):
     return out
 
 
+@_tensor_device
 def dropout_scale(n, p, seed, site):
     """Test hook: the 0 / 1/(1-p) multipliers of dropout site ``site`` for the key in ``seed`` (int64 [1] device)."""
     out = torch.empty(n, dtype=torch.float32, device=seed.device)
@@ -457,6 +505,7 @@ def dropout_scale(n, p, seed, site):
     return out
 
 
+@_tensor_device
 def adamw_step(params, grads, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,
                grad_scale=1.0):
     """torch.optim.AdamW step over flat fp32 arenas, one launch."""
@@ -468,6 +517,7 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999
                                     grad_scale, _stream_ptr()), "mst_adamw_step")
 
 
+@_tensor_device
 def sumsq2(x, y=None):
     """device float64 [2] = (sum x^2, sum y^2)."""
     out = torch.empty(2, dtype=torch.float64, device=x.device)
@@ -492,6 +542,7 @@ def mask_kind_of(mask: Optional[torch.Tensor], shape) -> int:
     raise ValueError(f"inpainting mask with {n} elements does not match state shape {tuple(shape)}")
 
 
+@_tensor_device
 def update_step(*, sampler: int, out_cond, x_t, x_prev, coef1, coef2, sigma=None, recip=None, recipm1=None,
                 out_uncond=None, cfg_scale=None, pred_xstart=None, mask=None, x_inpaint=None, mask_noise=True,
                 clip_denoised=False, t_vec=None, t_scalar_dev=None, t_imm=0, advance_t=False, block_counter=None,
@@ -525,6 +576,7 @@ def update_step(*, sampler: int, out_cond, x_t, x_prev, coef1, coef2, sigma=None
     return x_prev
 
 
+@_tensor_device
 def q_sample(x_start, noise, mask, t_vec, t_imm, sqrt_ab, sqrt_1m_ab, out=None):
     lib = L.load()
     B, F, T = x_start.shape[0], x_start.shape[1] * x_start.shape[2], x_start.shape[3]
@@ -537,6 +589,7 @@ def q_sample(x_start, noise, mask, t_vec, t_imm, sqrt_ab, sqrt_1m_ab, out=None):
     return out
 
 
+@_tensor_device
 def cfg_combine(out_cond, out_uncond, scale, out=None):
     lib = L.load()
     if out is None:
@@ -548,6 +601,7 @@ def cfg_combine(out_cond, out_uncond, scale, out=None):
     return out
 
 
+@_tensor_device
 def philox_normal(shape, seed: int, sample_offset: int, t: int, device) -> torch.Tensor:
     lib = L.load()
     out = torch.empty(shape, dtype=torch.float32, device=device)

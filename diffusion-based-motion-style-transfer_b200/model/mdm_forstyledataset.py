@@ -497,8 +497,12 @@ class NativeDenoiser(nn.Module):
                                "provide precomputed features as y['text_feat'] with shape [B, clip_dim]")
         tokenize = getattr(f, "mst_tokenize", None)  # hook: any callable with clip.tokenize's signature
         if tokenize is None:
-            import clip  # type: ignore
-            tokenize = clip.tokenize
+            try:
+                import clip  # type: ignore
+                tokenize = clip.tokenize
+            except ImportError:  # the native BPE tokenizer (needs the vocabulary file: MST_CLIP_BPE or attach_tokenizer)
+                from .clip_tokenizer import SimpleTokenizer
+                tokenize = f.mst_tokenize = SimpleTokenizer().tokenize
         device = next(self.parameters()).device
         max_text_len = 20 if self.dataset in ['humanml', 'kit'] else None
         if max_text_len is not None:

@@ -2,7 +2,11 @@
 
 Kept from the reference: the constructor's argument names, ``run_step`` / ``forward_backward`` / ``_anneal_lr`` and
 their order of operations (zero_grad -> few_shot_style_finetune_losses -> backward -> norms -> AdamW -> lr anneal).
-Not kept: logger / checkpoint / dataset plumbing (control plane, out of scope - see DESIGN.md).
+Also kept: the epoch-bounded ``run_loop`` (``num_steps // len(data) + 1`` epochs), ``save()`` every ``save_interval`` steps
+and at the end in the reference's on-disk format (``modelNNNNNNNNN.pt`` = the model ``state_dict`` minus the frozen
+``motion_enc.`` / ``controlmdm.`` / ``clip_model.`` entries, ``optNNNNNNNNN.pt`` = a ``torch.optim.AdamW`` state dict indexed
+like ``list(model.parameters())``) and the resume path (``resume_checkpoint`` file or directory), so that
+``train/finetune_style_diffusion.py`` leaves the same files behind.  Not kept: logger / train-platform reporting.
 
 Data parallelism: when ``torch.distributed`` is initialised with more than one rank, every rank
 takes a contiguous shard of the text-to-motion batch (the only batched term of the loss), keeps the B=1 style term
@@ -12,6 +16,8 @@ AdamW step applies it scaled by 1/world_size.
 from __future__ import annotations
 
 import functools
+import os
+from collections import OrderedDict
 
 import torch
 import torch.distributed as dist
@@ -50,11 +56,43 @@ class FusedAdamW:
     def zero_grad(self, set_to_none=False):
         self.flat.grads.zero_()
 
+    def _index_map(self):
+        """(index in list(model.parameters()), offset, numel) of every trainable tensor, arena order."""
+        order = {id(p): i for i, p in enumerate(self.model.parameters())} if self.model is not None else {}
+        out, off = [], 0
+        for k, p in enumerate(self.flat.trainable):
+            out.append((order.get(id(p), k), off, p.numel(), tuple(p.shape)))
+            off += p.numel()
+        return out
+
     def state_dict(self):
-        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
-                "param_groups": self.param_groups}
+        """``torch.optim.AdamW.state_dict()`` layout over ``list(model.parameters())`` (what the reference writes to
+        ``optNNNNNNNNN.pt``, train/training_loop.py:343-348): per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``."""
+        g = self.param_groups[0]
+        n_all = len(list(self.model.parameters())) if self.model is not None else len(self.flat.trainable)
+        state = {}
+        if self.step_count > 0:
+            for idx, off, n, shape in self._index_map():
+                state[idx] = {"step": self.step_count, "exp_avg": self.exp_avg[off:off + n].view(shape).clone(),
+                              "exp_avg_sq": self.exp_avg_sq[off:off + n].view(shape).clone()}
+        group = {"lr": g["lr"], "betas": tuple(g["betas"]), "eps": g["eps"], "weight_decay": g["weight_decay"],
+                 "amsgrad": False, "params": list(range(n_all))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
+        if "state" in sd:  # torch.optim.AdamW layout (ours or the reference's)
+            steps = []
+            for idx, off, n, shape in self._index_map():
+                ent = sd["state"].get(idx)
+                if ent is None:
+                    continue
+                self.exp_avg[off:off + n].copy_(ent["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(ent["exp_avg_sq"].reshape(-1))
+                steps.append(int(ent["step"]))
+            self.step_count = max(steps) if steps else 0
+            g = sd["param_groups"][0]
+            self.param_groups[0].update(lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"], weight_decay=g["weight_decay"])
+            return
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.step_count = int(sd["step"])
@@ -65,8 +103,13 @@ def shard_batch(batch, cond, rank, world):
     """Contiguous shard of the t2m batch for this rank: tensors with a leading batch dimension and lists of
     per-sample entries are sliced; everything else is shared."""
     B = batch.shape[0]
-    per = (B + world - 1) // world
-    lo, hi = min(B, rank * per), min(B, (rank + 1) * per)
+    if B < world or B % world != 0:
+        # equal shards only: the all-reduce averages the per-rank means with equal weight (a ragged split would bias
+        # the text-to-motion term, an empty shard would hang the collective).  The replicated B=1 style term also
+        # assumes that every rank draws the same noise / timesteps: seed the ranks identically.
+        raise ValueError(f"the text-to-motion batch ({B}) must be a positive multiple of the world size ({world})")
+    per = B // world
+    lo, hi = rank * per, (rank + 1) * per
     y = {}
     for k, v in cond["y"].items():
         if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == B:
@@ -94,9 +137,19 @@ class TrainInpaintingLoop:
         self.style_finetune = getattr(args, "style_finetune", 0)
         self.semantic_guidance = getattr(args, "semantic_guidance", 0) if hasattr(args, "style_finetune") else 0
         self.skip_steps = getattr(args, "skip_steps", 0)
+        self.log_interval = getattr(args, "log_interval", 0)
+        self.save_interval = getattr(args, "save_interval", 0)
+        self.save_dir = getattr(args, "save_dir", None)
+        self.resume_checkpoint = getattr(args, "resume_checkpoint", "") or ""
+        self.overwrite = getattr(args, "overwrite", False)
         self.step = 0
         self.resume_step = 0
         self.num_steps = getattr(args, "num_steps", 0)
+        try:
+            self.num_epochs = self.num_steps // max(1, len(data)) + 1  # reference :76
+        except TypeError:
+            self.num_epochs = 1
+        self._load_and_sync_parameters()
         self.use_ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.world = dist.get_world_size() if self.use_ddp else 1
         self.rank = dist.get_rank() if self.use_ddp else 0
@@ -107,8 +160,53 @@ class TrainInpaintingLoop:
             self.schedule_sampler = create_named_schedule_sampler(self.schedule_sampler_type, diffusion)
         self.opt = FusedAdamW(self.mp_trainer.flat, lr=self.lr, weight_decay=self.weight_decay, model=self.model)
         self.opt.grad_scale = 1.0 / self.world
+        if self.resume_step:
+            self._load_optimizer_state()
         self.device = next(model.parameters()).device
         self.last_losses = None
+
+    # ------------------------------------------------------------------ checkpoints (reference :108-140, :309-348)
+    def _load_and_sync_parameters(self):
+        ckpt = self.resume_checkpoint
+        if ckpt and os.path.isdir(ckpt):
+            ckpt = find_resume_checkpoint(ckpt, "model")
+        if not ckpt:
+            return
+        self.resume_step = parse_resume_step_from_filename(ckpt)
+        dev = next(self.model.parameters()).device
+        missing, unexpected = self.model.load_state_dict(torch.load(ckpt, map_location=dev), strict=False)
+        assert len(unexpected) == 0, unexpected
+        assert all(k.startswith(("motion_enc.", "controlmdm.", "clip_model.")) for k in missing), missing
+        if hasattr(self.model, "mst_weights_changed"):
+            self.model.mst_weights_changed()
+
+    def _load_optimizer_state(self):
+        main = self.resume_checkpoint
+        if os.path.isdir(main):
+            main = find_resume_checkpoint(main, "opt")
+        path = os.path.join(os.path.dirname(main), f"opt{self.resume_step:09}.pt")
+        if os.path.exists(path):
+            try:
+                self.opt.load_state_dict(torch.load(path, map_location=next(self.model.parameters()).device))
+            except Exception:  # the reference swallows a mismatching optimizer file too (:136-139)
+                pass
+
+    def ckpt_file_name(self, step=None):
+        return f"model{((self.step if step is None else step) + self.resume_step):09d}.pt"
+
+    def save(self, step=None):
+        """``modelNNNNNNNNN.pt`` + ``optNNNNNNNNN.pt`` in ``save_dir`` (rank 0 only under data parallelism)."""
+        if self.save_dir is None or self.rank != 0:
+            return None
+        step = self.step if step is None else step
+        os.makedirs(self.save_dir, exist_ok=True)
+        drop = ("controlmdm.", "clip_model.") if self.dataset == "humanml" else ("motion_enc.", "clip_model.")
+        sd = OrderedDict((k, v.detach().clone()) for k, v in self.mp_trainer.master_params_to_state_dict().items()
+                         if not k.startswith(drop))
+        path = os.path.join(self.save_dir, self.ckpt_file_name(step))
+        torch.save(sd, path)
+        torch.save(self.opt.state_dict(), os.path.join(self.save_dir, f"opt{(step + self.resume_step):09d}.pt"))
+        return path
 
     # ------------------------------------------------------------------ one optimisation step
     def run_step(self, batch, cond, style_batch=None, style_cond=None):
@@ -156,22 +254,59 @@ class TrainInpaintingLoop:
         for param_group in self.opt.param_groups:
             param_group["lr"] = lr
 
-    # ------------------------------------------------------------------ a plain loop over the given iterables
+    # ------------------------------------------------------------------ the epoch loop (reference :143-190)
     def run_loop(self, max_steps=None):
-        """Iterate ``self.data`` (t2m batches) against the single style example (training_loop.py:143-190) without the
-        reference's logging / checkpoint side effects."""
-        iter_style = iter(self.style_data)
-        content_motion, cond_style = next(iter_style)
+        """``num_epochs`` passes over ``self.data`` (t2m batches) against the style example; checkpoints every
+        ``save_interval`` steps and at the end.  ``max_steps`` (not in the reference) bounds the number of steps."""
+        iter_style = iter(self.style_data) if self.style_finetune else None
         n = 0
-        while max_steps is None or n < max_steps:
+        for _epoch in range(self.num_epochs):
+            if self.style_finetune:
+                try:
+                    content_motion, cond_style = next(iter_style)
+                except StopIteration:
+                    iter_style = iter(self.style_data)
+                    content_motion, cond_style = next(iter_style)
+                cond_style['y'] = {k: v.to(self.device) if torch.is_tensor(v) else v for k, v in cond_style['y'].items()}
+                if torch.is_tensor(content_motion):
+                    content_motion = content_motion.to(self.device)
+            else:
+                content_motion, cond_style = None, None
             for motion, cond in self.data:
                 if self.lr_anneal_steps and self.step + self.resume_step >= self.lr_anneal_steps:
-                    return
+                    break
                 motion = motion.to(self.device)
                 cond['y'] = {k: v.to(self.device) if torch.is_tensor(v) else v for k, v in cond['y'].items()}
-                self.run_step(motion, cond, content_motion, cond_style)
+                self.run_step(motion, cond, content_motion, cond_style)   # advances self.step
+                done = self.step - 1                                         # the reference saves before its increment
+                if self.save_interval and done % self.save_interval == 0:
+                    self.save(step=done)
+                    if os.environ.get("DIFFUSION_TRAINING_TEST", "") and done > 0:
+                        return
                 n += 1
                 if max_steps is not None and n >= max_steps:
-                    return
-            if max_steps is None and self.num_steps and self.step >= self.num_steps:
-                return
+                    break
+            if max_steps is not None and n >= max_steps:
+                break
+            if self.lr_anneal_steps and self.step + self.resume_step >= self.lr_anneal_steps:
+                break
+        if self.save_interval and self.step > 0 and (self.step - 1) % self.save_interval != 0:
+            self.save()  # the last checkpoint if it was not saved already (reference :188-190)
+
+
+def parse_resume_step_from_filename(filename):
+    """path/to/modelNNNNNNNNN.pt -> NNNNNNNNN (reference :352-365)"""
+    split = filename.split("model")
+    if len(split) < 2:
+        return 0
+    try:
+        return int(split[-1].split(".")[0])
+    except ValueError:
+        return 0
+
+
+def find_resume_checkpoint(save_dir, mode='model'):
+    """latest ``{mode}NNNNNNNNN.pt`` of a directory (reference :375-383)"""
+    files = [f for f in os.listdir(save_dir) if f.endswith('.pt') and f.startswith(mode)]
+    steps = [int(f[len(mode):len(mode) + 9]) for f in files]
+    return os.path.join(save_dir, f"{mode}{sorted(steps)[-1]:09d}.pt")

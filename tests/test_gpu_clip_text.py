@@ -124,3 +124,29 @@ def test_mdm_encode_text_runs_on_the_native_tower(towers, sd):
     feat_h = model.encode_text(long_text)
     tok_h = torch.cat([fake_tokenize(long_text, context_length=22), torch.zeros(1, 55, dtype=torch.int64)], dim=1)
     assert relerr(feat_h, OC.encode_text(sd, tok_h)) <= 1e-4
+
+
+def test_captions_to_features_without_the_clip_package(tmp_path):
+    """Row N1 end to end: captions -> native BPE tokenizer (a vocabulary FILE, synthetic here) -> native text tower ->
+    MDM.encode_text, with no `clip` import anywhere; checked against the oracle tower on the same tokens."""
+    import gzip
+    from helpers import Args
+    from mst_b200.model.clip_text import CLIPTextTower
+    from mst_b200.model.clip_tokenizer import SimpleTokenizer, attach_tokenizer
+    from mst_b200.model.mdm_forstyledataset import MDM
+    from mst_b200.utils import model_util as mu
+    merges = [("t", "h"), ("th", "e</w>"), ("w", "a"), ("wa", "l"), ("wal", "k"), ("walk", "s</w>"), ("p", "e"), ("pe", "r"),
+              ("per", "s"), ("pers", "o"), ("perso", "n</w>"), ("j", "u"), ("ju", "m"), ("jum", "p"), ("jump", "s</w>")]
+    bpe = os.path.join(tmp_path, "bpe_simple_vocab.txt.gz")
+    with gzip.open(bpe, "wb") as f:
+        f.write(("#version: synthetic\n" + "\n".join(" ".join(m) for m in merges) + "\n").encode())
+    tok = SimpleTokenizer(bpe)
+    vocab = len(tok.encoder)
+    small = CI.state_dict(seed=4, width=512, layers=2, embed_dim=512, vocab=vocab, ctx=77)
+    model = MDM(**mu.get_transfer_args(Args())).to(DEV).eval()
+    model.clip_model = CLIPTextTower.from_state_dict(small, precision="fp32").to(DEV)
+    attach_tokenizer(model, bpe)
+    texts = ["a person walks", "the person jumps and walks", "a person walks"]
+    feat = model.encode_text(texts)
+    want = OC.encode_text(small, tok.tokenize(texts, truncate=True))
+    assert feat.shape == (3, 512) and relerr(feat, want) <= 1e-4 and torch.equal(feat[0], feat[2])

@@ -199,6 +199,35 @@ def test_install_overlay_registers_reference_names():
         sys.modules.pop(n, None)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference checkout only exists in the build container")
+def test_install_overlay_next_to_the_real_reference():
+    """install('/root/reference'): the hot-path modules resolve to this package, everything else (here the reference's
+    own data_loaders/tensors.py collate, which the demo script uses) keeps coming from the reference - and the mirror's
+    collate builds the same model_kwargs."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch; np.float = float; np.int = int\n"
+        f"sys.path.insert(0, {REPO!r})\n"
+        "import mst_b200\n"
+        "mst_b200.install('/root/reference')\n"
+        "from data_loaders.tensors import collate as ref_collate\n"
+        "from utils import model_util\n"
+        "from diffusion.respace import SpacedDiffusion\n"
+        "from mst_b200.data_loaders.tensors import collate\n"
+        "assert ref_collate.__module__ == 'data_loaders.tensors' and '/root/reference' in sys.modules['data_loaders.tensors'].__file__\n"
+        "assert model_util.__name__.startswith('mst_b200') and SpacedDiffusion.__module__.startswith('mst_b200')\n"
+        "items = [{'inp': torch.randn(181, 1, 76), 'tokens': None, 'lengths': 76, 'text': 'a'},\n"
+        "         {'inp': torch.randn(181, 1, 60), 'tokens': None, 'lengths': 60, 'text': 'b'}]\n"
+        "m0, k0 = ref_collate(items); m1, k1 = collate(items)\n"
+        "assert torch.equal(m0, m1) and sorted(k0['y']) == sorted(k1['y'])\n"
+        "assert torch.equal(k0['y']['mask'].float(), k1['y']['mask'].float()) and torch.equal(k0['y']['lengths'], k1['y']['lengths'])\n"
+        "assert k0['y']['text'] == k1['y']['text']\n"
+        "print('overlay ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "overlay ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_text_feature_cache_encodes_each_caption_once():
     """Scope row N1 (cached-feature API): CLIP is frozen, so a caption is encoded once per process."""
     import torch

@@ -118,7 +118,11 @@ def test_uniform_sampler_follows_numpy_rng_and_range():
 
 def test_shard_batch_slices_per_sample_entries_only():
     from mst_b200.train.training_loop import shard_batch
-    B = 5
+    with pytest.raises(ValueError):  # ragged split: the equal-weight all-reduce would bias the t2m term
+        shard_batch(torch.zeros(5, 3, 1, 2), {"y": {}}, 0, 2)
+    with pytest.raises(ValueError):  # fewer samples than ranks: an empty shard would hang the collective
+        shard_batch(torch.zeros(1, 3, 1, 2), {"y": {}}, 1, 2)
+    B = 6
     batch = torch.arange(B * 6, dtype=torch.float32).view(B, 3, 1, 2)
     cond = {"y": {"text": [f"t{i}" for i in range(B)], "mask": torch.ones(B, 1, 1, 2), "lengths": torch.arange(B),
                   "scalar": 3, "table": torch.zeros(7)}}
