@@ -295,6 +295,76 @@ def test_training_loop_runs_and_reduces_the_loss(mu, FI, tmp_path_factory):
     assert loop.step == 4 and loop.opt.step_count == 4
 
 
+def test_run_loop_checkpoints_in_the_reference_format_and_resumes(mu, FI, tmp_path_factory):
+    """run_loop (reference train/training_loop.py:143-190, :309-348): num_steps // len(data) + 1 epochs, CPU-side
+    kwargs moved to the device, modelNNNNNNNNN.pt without the frozen motion_enc. / clip_model. entries, optNNNNNNNNN.pt
+    in torch.optim.AdamW's own layout over list(model.parameters()), and a second loop that resumes from them."""
+    import os
+    from mst_b200.data_loaders.stylexia_posrot_utils import get_inpainting_mask
+    from mst_b200.train.training_loop import TrainInpaintingLoop
+    save_dir = str(tmp_path_factory.mktemp("ckpt"))
+    inp = FI.make_inputs()
+    F, T = 181, inp["content"].shape[-1]
+
+    class A(Args):
+        batch_size, lr, weight_decay, lr_anneal_steps, style_finetune, semantic_guidance = 3, 1e-4, 0.0, 0, 1, 0
+        skip_steps, use_ddim, Ls, num_steps = 700, 1, 10, 2
+        log_interval, save_interval, resume_checkpoint, overwrite = 1, 2, "", True
+
+    A.save_dir = save_dir
+
+    def make_loop(args):
+        model, *_ = _style_model(mu, FI, tmp_path_factory)
+        diffusion = mu.create_gaussian_diffusion(args, mu.InpaintingGaussianDiffusion, timestep_respacing="ddim20")
+        # everything on the HOST, as a data loader delivers it: run_loop moves it (reference :155, :166-167)
+        style_cond = {"y": {"text": inp["texts_style"], "text_feat": text_features(inp["texts_style"]),
+                            "mask": torch.ones(1, 1, 1, T, dtype=torch.bool), "lengths": torch.tensor([T]),
+                            "inpainted_motion": inp["style"].clone(),
+                            "inpainting_mask": torch.from_numpy(get_inpainting_mask("root_horizontal", (1, F, 1, T))).float()}}
+        cond = {"y": {"text": inp["texts_t2m"], "text_feat": text_features(inp["texts_t2m"]),
+                      "mask": inp["frame_mask_t2m"][:, None, None, :].clone(), "lengths": torch.tensor(inp["lengths"]),
+                      "inpainting_mask": torch.from_numpy(get_inpainting_mask("root_horizontal", tuple(inp["x_start"].shape))).float()}}
+        data = [(inp["x_start"].clone(), cond)]  # len(data) == 1 -> num_epochs = num_steps + 1 = 3
+        return model, TrainInpaintingLoop(args, None, model, data, diffusion=diffusion, style_data=[(inp["content"].clone(), style_cond)])
+
+    np.random.seed(0)
+    model, loop = make_loop(A())
+    assert loop.num_epochs == 3
+    loop.run_loop()
+    assert loop.step == 3
+    files = sorted(os.listdir(save_dir))
+    # saved after loop indices 0 and 2 (step % save_interval == 0 before the increment); the final save is skipped
+    # because (step - 1) % save_interval == 0 - exactly the reference's bookkeeping (:183-190)
+    assert files == ["model000000000.pt", "model000000002.pt", "opt000000000.pt", "opt000000002.pt"], files
+    sd = torch.load(os.path.join(save_dir, "model000000002.pt"), map_location="cpu")
+    assert not any(k.startswith(("motion_enc.", "clip_model.")) for k in sd)
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    assert trainable <= set(sd) and len(trainable) == 96
+    for n, p in model.named_parameters():
+        if n in sd:
+            assert torch.equal(sd[n], p.detach().cpu()), n
+    # the optimizer file loads into a stock torch.optim.AdamW over list(model.parameters()), as the reference resumes it
+    osd = torch.load(os.path.join(save_dir, "opt000000002.pt"), map_location="cpu")
+    params = list(model.parameters())
+    stock = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.0)
+    stock.load_state_dict(osd)
+    idx = {id(p): i for i, p in enumerate(params)}
+    some = next(p for p in params if p.requires_grad)
+    assert torch.equal(stock.state[some]["exp_avg"].cpu(), osd["state"][idx[id(some)]]["exp_avg"])
+    assert int(stock.state[some]["step"]) == 3 and len(osd["state"]) == 96
+    # resume: a fresh loop pointed at the directory picks up the latest files
+    B = A()
+    B.resume_checkpoint = save_dir
+    model2, loop2 = make_loop(B)
+    assert loop2.resume_step == 2 and loop2.opt.step_count == 3
+    for (n, p), (_, q) in zip(model.named_parameters(), model2.named_parameters()):
+        if p.requires_grad:
+            assert torch.equal(p, q), n
+    assert torch.equal(loop2.opt.exp_avg, loop.opt.exp_avg)
+    loop2.run_loop(max_steps=1)
+    assert loop2.step == 1 and "model000000002.pt" in os.listdir(save_dir) and loop2.ckpt_file_name() == "model000000003.pt"
+
+
 # ------------------------------------------------------------------ bf16 tensor-core training mode
 def rel_l2(a, b):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
