@@ -193,6 +193,9 @@ def main():
     ap.add_argument("--traj-steps", type=int, default=1000, dest="traj_steps")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling and finetune sub-records")
+    ap.add_argument("--strong-batch", type=int, default=4096, dest="strong_batch")
+    ap.add_argument("--strong-steps", type=int, default=50, dest="strong_steps")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference_arm(a)
@@ -206,9 +209,10 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries the ONE JSON line; NCCL's log (communicator / ring / NVLS lines of NCCL_DEBUG=INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if a.gpus != world and rank == 0:
         print(f"bench.py: --gpus {a.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run for N>1", file=sys.stderr)
@@ -318,6 +322,16 @@ def main():
         "frac_of_bf16_sustained_peak": 2 * B * model_flops_per_seq(T) * N / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
         "peaks": pk,
     }
+    # ---- BASELINE configs[2] / configs[3] inside the same line, so the driver's 1/2/4/8 runs carry them
+    if not a.no_extra:
+        try:
+            line["strong"] = strong_scaling_leg(a, dev, rank, world, dist, cfg_model, mu, get_inpainting_mask)
+        except Exception as exc:
+            line["strong"] = {"error": str(exc)[:300]}
+        try:
+            line["finetune"] = finetune_leg(a, dev, rank, world, dist)
+        except Exception as exc:
+            line["finetune"] = {"error": str(exc)[:300]}
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             sec, threads = cpu_port_step_seconds(B, T, 3)
@@ -328,6 +342,96 @@ def main():
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def strong_scaling_leg(a, dev, rank, world, dist, cfg_model, mu, get_inpainting_mask):
+    """BASELINE configs[2]: a FIXED total batch (default 4096 motions x 196 frames, CFG + inpainting) sharded over the
+    ranks (contiguous shards, Philox keyed by the global sample index, no collective in the loop), on a respaced
+    trajectory of --strong-steps steps so that the default run stays short.  value = frames of COMPLETE
+    strong_steps-step trajectories per second over all ranks (max-over-ranks device time)."""
+    import contextlib
+    import io
+    total, n = a.strong_batch, a.strong_steps
+    if total % world:
+        raise ValueError(f"strong batch {total} is not a multiple of {world} ranks")
+    B, T = total // world, a.frames
+    shape = (B, F_FEATS, 1, T)
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = mu.create_gaussian_diffusion(Args(), mu.InpaintingGaussianDiffusion, timestep_respacing=str(n))
+    d.rng, d.philox_seed, d.philox_sample_offset = "philox", 3, rank * B
+    g = torch.Generator().manual_seed(100 + rank)
+    kw = {"y": {"text": [""] * B, "text_feat": torch.randn(B, 512, generator=g).to(dev), "scale": torch.full((B,), 2.5, device=dev),
+                "inpainted_motion": torch.randn(shape, generator=g).to(dev),
+                "inpainting_mask": torch.from_numpy(get_inpainting_mask("root_horizontal", shape)).float().to(dev),
+                "mask": torch.ones(B, 1, 1, T, device=dev), "lengths": torch.full((B,), T, device=dev)}}
+    run = lambda: d.p_sample_loop(cfg_model, shape, clip_denoised=False, model_kwargs=kw)
+    run()
+    reps = 2
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / reps
+    del kw, d
+    torch.cuda.empty_cache()
+    flops = 2 * total * model_flops_per_seq(T) * n
+    return {"metric": METRIC, "scaling": "strong", "total_batch": total, "batch_per_gpu": B, "traj_steps": n, "n_gpus": world,
+            "ms_per_trajectory": ms, "ms_per_denoise_step": ms / n, "value": total * T / (ms * 1e-3), "unit": UNIT,
+            "frames_per_s_1000_step_equiv": total * T / (ms * 1e-3) * n / 1000.0,
+            "model_tflops_per_s_all_gpus": flops / (ms * 1e-3) / 1e12,
+            "frac_of_bf16_sustained_peak": flops / (ms * 1e-3) / 1e12 / (world * peaks()["bf16_tflops_sustained"]),
+            "workload": f"B={total} total ({B}/GPU) x T={T}, {n}-step respaced DDPM, CFG + inpainting (BASELINE configs[2])"}
+
+
+def finetune_leg(a, dev, rank, world, dist, B=64, T=76, steps=8, warmup=3):
+    """BASELINE configs[3]: the few-shot style finetune step (t2m batch B=64 x T=76 sharded over the ranks, style example
+    B=1 x 6 differentiable DDIM steps replicated, semantic guidance on, fused AdamW; NCCL all-reduce of the 67 MB fp32
+    gradient arena when world > 1).  ms per step = max over ranks (CUDA events); the all-reduce is timed on the device."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import bench_finetune as BF
+    import contextlib
+    np.random.seed(0)
+    with contextlib.redirect_stdout(sys.stderr):  # the model factories print; stdout carries the ONE JSON line
+        loop, batch = BF.build(dev, B, T, 1, "bf16")
+    for _ in range(warmup):
+        loop.run_step(*batch)
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar = []
+    e0.record()
+    for _ in range(steps):
+        loop.run_step(*batch)
+        if world > 1:
+            ar.append(loop.last_allreduce_ms())
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    out = {"metric": "finetune_ms_per_step", "value": float(ms.item()), "unit": "ms", "n_gpus": world, "higher_is_better": False,
+           "scaling": "strong (t2m batch sharded, style term replicated)", "loss": float(loop.last_losses["loss"]),
+           "workload": f"t2m B={B} x T={T} + style B=1 x 6 DDIM steps with grad, semantic_guidance=1, AdamW (BASELINE configs[3])"}
+    if world > 1:
+        ar_ms = sum(ar) / len(ar)
+        nbytes = loop.mp_trainer.flat.grads.numel() * 4
+        out.update(allreduce_ms=ar_ms, allreduce_bytes=nbytes,
+                   allreduce_busbw_gbs=2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+                   allreduce_overlap_pct=float(getattr(loop, "last_overlap_pct", 0.0)),
+                   allreduce_share_of_step=ar_ms / float(ms.item()))
+    del loop, batch
+    torch.cuda.empty_cache()
+    return out
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four GEMM launches of one layer (QKV 54.6 MB,

@@ -187,6 +187,12 @@ class GaussianDiffusion:
         self.philox_sample_offset = 0          # global index of this shard's first sample (multi-GPU)
         self.noise_fn = None                   # optional callable(step_number, shape, device) -> eps tensor
         self.use_cuda_graph = os.environ.get("MST_GRAPH", "1") != "0"
+        # How a fused trajectory whose caller only wants the final sample is submitted: "full" = ALL its denoise steps
+        # captured as ONE CUDA graph and launched once (the timestep lives in device memory and the update kernel
+        # decrements it, so the N steps are N copies of the same node sequence); "step" = one captured step replayed N
+        # times from the host; an integer K = graphs of K steps.  Graphs above MST_TRAJ_GRAPH_MAX_NODES kernel nodes fall
+        # back to chunks.
+        self.trajectory_graph = os.environ.get("MST_TRAJ_GRAPH", "full")
         self.steps_per_graph = int(os.environ.get("MST_STEPS_PER_GRAPH", "1"))
         self._dev = {}
         self._graphs = {}
@@ -745,6 +751,12 @@ class GaussianDiffusion:
                       self.philox_seed, self.philox_sample_offset)
             self.last_plan_launches = plan.launches_per_step
 
+            if (own_buffers and not progress and self.noise_fn is None and plan.graph is not None
+                    and self.trajectory_graph != "step"):
+                # nobody looks at the intermediate states: submit the whole trajectory at once
+                plan.run_trajectory(n_steps, self.trajectory_graph)
+                yield {"sample": plan.x, "pred_xstart": plan.x0, "_live": True}
+                return
             it = range(n_steps)
             if progress:
                 from tqdm.auto import tqdm
@@ -796,6 +808,8 @@ class _TrajectoryPlan:
         self.use_graph = use_graph
         self.graph = None
         self.graph_key = None
+        self.traj_graphs = {}  # number of steps -> graph of that many consecutive steps
+        self.last_trajectory_launches = 0
         self.launches_per_step = 0
         self.draw_noise = self.eps is not None and diffusion.noise_fn is None
 
@@ -856,7 +870,38 @@ class _TrajectoryPlan:
             self._one_step(*self.seed_off)
         self.launches_per_step = K.launch_count() - n0
         self.graph, self.graph_key = graph, (self.seed_off, self.eng.weights_generation)
+        self.traj_graphs = {}
         self.x.copy_(snap)
+
+    def run_trajectory(self, n_steps, mode="full"):
+        """Submit n_steps denoise steps: one graph launch when the whole trajectory fits one graph."""
+        max_nodes = int(os.environ.get("MST_TRAJ_GRAPH_MAX_NODES", "65536"))
+        per = max(1, self.launches_per_step)
+        chunk = n_steps if mode == "full" else max(1, int(mode))
+        chunk = max(1, min(chunk, n_steps, max_nodes // per))
+        done = 0
+        while done < n_steps:
+            k = min(chunk, n_steps - done)
+            g = self.traj_graphs.get(k)
+            if g is None:
+                g = self.traj_graphs[k] = self._capture_steps(k)
+            g.replay()
+            done += k
+        K.count_graph_replay(n_steps)
+        self.last_trajectory_launches = -(-n_steps // chunk)
+
+    def _capture_steps(self, k):
+        """k consecutive denoise steps as one CUDA graph (the buffers, the device-side timestep and the Philox key are
+        the plan's; nothing in a step depends on the host)."""
+        snap, t_snap, c_snap = self.x.clone(), self.t_dev.clone(), self.counter.clone()
+        graph = th.cuda.CUDAGraph()
+        with th.cuda.graph(graph):
+            for _ in range(k):
+                self._one_step(*self.seed_off)
+        self.x.copy_(snap)
+        self.t_dev.copy_(t_snap)
+        self.counter.copy_(c_snap)
+        return graph
 
     def step(self):
         if self.graph is not None:

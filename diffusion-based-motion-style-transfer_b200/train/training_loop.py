@@ -218,7 +218,22 @@ class TrainInpaintingLoop:
 
     def sync_gradients(self):
         if self.use_ddp:
+            ev = self.__dict__.get("_ar_events")
+            if ev is None and self.mp_trainer.flat.grads.is_cuda:
+                ev = self._ar_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            if ev is not None:
+                ev[0].record()
             dist.all_reduce(self.mp_trainer.flat.grads, op=dist.ReduceOp.SUM)
+            if ev is not None:
+                ev[1].record()
+
+    def last_allreduce_ms(self):
+        """device time of the most recent gradient all-reduce (CUDA events around the collective; synchronises)"""
+        ev = self.__dict__.get("_ar_events")
+        if ev is None:
+            return 0.0
+        ev[1].synchronize()
+        return float(ev[0].elapsed_time(ev[1]))
 
     def forward_backward(self, batch, cond, style_batch, style_cond):
         self.mp_trainer.zero_grad()

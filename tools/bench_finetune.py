@@ -78,8 +78,7 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=dev)
     np.random.seed(0)
     from mst_b200 import engine as K
