@@ -202,6 +202,11 @@ def main():
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: park the real stdout and send everything else that any library prints to
+    # file descriptor 1 (NCCL's version banner ignores NCCL_DEBUG_FILE, the model factories print) to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
@@ -209,10 +214,10 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # stdout carries the ONE JSON line; NCCL's log (communicator / ring / NVLS lines of NCCL_DEBUG=INFO) goes to stderr
+        # NCCL's log (communicator / ring / NVLS lines of NCCL_DEBUG=INFO) is NOT silenced: it is written to fd 1, which
+        # points at stderr in this process (see above)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if a.gpus != world and rank == 0:
         print(f"bench.py: --gpus {a.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run for N>1", file=sys.stderr)
@@ -339,7 +344,8 @@ def main():
                                     "sample": f"3 denoise steps of the same B={B},T={T} CFG+inpainting workload on the CPU "
                                               f"oracle port ({sec:.2f} s/step), extrapolated x{N}",
                                     "host_cpus": os.cpu_count()}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

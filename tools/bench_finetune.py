@@ -75,10 +75,12 @@ def main():
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    real_stdout = os.dup(1)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
+        sys.stdout.flush()
+        os.dup2(2, 1)  # NCCL's banner / log go to stderr; the JSON line is written to the real stdout below
         dist.init_process_group("nccl", device_id=dev)
     np.random.seed(0)
     from mst_b200 import engine as K
@@ -122,7 +124,8 @@ def main():
         out["stages"] = [{"kernel": k, "launches": v[0], "ms": round(v[1], 4), "share": round(v[1] / tot, 4)}
                          for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]]
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
