@@ -407,33 +407,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // 128B-swizzled [32 x 64] staging box -> one TMA store per box.  Two boxes per warp ping-pong, so the only
 // synchronisation is __syncwarp and the bulk-group wait of lane 0 - no CTA-wide barrier in the loop.
 // ---------------------------------------------------------------------------
-template <int EPI>
+template <int EPI, int BN_ = 256>
 struct PairCfg {
-  static constexpr int BN = 256;
+  // Tile width (columns of the 256-row pair tile).  256 maximises operand re-use; a narrower tile trades it for less
+  // wave quantisation (QKV at B=64 is 594 tiles of 256 columns on 74 clusters = 8.03 waves: two clusters run a ninth
+  // tile while 72 idle, 12 % of the launch, profiles/r02h_ncu_full_step_kernels_summary.txt) - measured slower, see
+  // launch_gemm_pair.
+  static constexpr int BN = BN_;
   // The GELU epilogue is issue/latency-bound with two warps per scheduler (5.6k cycles per tile against 4.1k of MMAs):
-  // it gets 16 epilogue warps (4 per scheduler, 64 columns each) and pays with one ring stage; the plain-bias
-  // epilogue keeps 8 warps and a 6-deep ring (~190 KB in flight: the L2 -> SM latency is ~2k cycles under load).
-  static constexpr int EPI_WARPS = EPI == TC_EPI_BIAS_GELU_BF16 ? 16 : 8;
+  // it gets 16 epilogue warps (4 per scheduler) and pays with one ring stage; the plain-bias epilogue keeps 8 warps.
+  static constexpr int EPI_WARPS = (EPI == TC_EPI_BIAS_GELU_BF16 && BN_ % 128 == 0) ? 16 : 8;
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
   static constexpr int THREADS = 64 + EPI_THREADS;
   static constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
-  static constexpr int STAGES = EPI == TC_EPI_BIAS_GELU_BF16 ? 5 : 6;
+  static_assert(COLS_PER_WARP % 32 == 0, "a warp handles whole 32-column steps");
   static constexpr int A_BYTES = BLOCK_M * 128;       // 128 rows x 64 k
-  static constexpr int B_BYTES = (BN / 2) * 128;      // this CTA's 128 of the 256 weight rows
+  static constexpr int B_BYTES = (BN / 2) * 128;      // this CTA's half of the BN weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OBOX_BYTES = 32 * 64;          // output staging: [32 rows x 32 bf16], 64B swizzle
   static constexpr int OUT_BYTES = EPI_WARPS * 2 * OBOX_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 512;
+  static constexpr int MAX_SMEM = 232448;
+  static constexpr int STAGES_FIT = (MAX_SMEM - 1024 - OUT_BYTES - BAR_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;  // 256: 6 (bias) / 5 (GELU); 192: 6; 128: 8 / 6
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
 };
 
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EPI>::THREADS, 1)
+template <int EPI, int BN_>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EPI, BN_>::THREADS, 1)
 tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_out, const TcGemmParams p) {
-  using Cfg = PairCfg<EPI>;
+  using Cfg = PairCfg<EPI, BN_>;
   constexpr int BN = Cfg::BN;
   pdl_launch_dependents();
   MST_DBG_WALL(0);
@@ -1462,25 +1468,43 @@ static int max_active_clusters(Kernel kernel, int cluster_size, int threads, siz
   return n;
 }
 
-template <int EPI>
-static int launch_gemm_pair(const TcGemmParams& p, cudaStream_t s) {
-  using Cfg = PairCfg<EPI>;
+template <int EPI, int BN_>
+static int max_pair_clusters() {
+  using Cfg = PairCfg<EPI, BN_>;
+  static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
+  if (attr_set.first())
+    cudaFuncSetAttribute(tc_gemm_pair_kernel<EPI, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  static const int n = max_active_clusters(tc_gemm_pair_kernel<EPI, BN_>, 2, Cfg::THREADS, Cfg::SMEM_BYTES);
+  return n;
+}
+
+template <int EPI, int BN_>
+static int launch_gemm_pair_bn(const TcGemmParams& p, cudaStream_t s) {
+  using Cfg = PairCfg<EPI, BN_>;
   CUtensorMap ta, tw, to;
   int rc;
   if ((rc = make_tmap_bf16(&ta, p.a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.K, BLOCK_M, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16(&tw, p.w, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, Cfg::BN / 2, BLOCK_K))) return rc;
   if ((rc = make_tmap_bf16_3d(&to, p.out, 1, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, (uint64_t)p.M * p.ldo, 32, 32, 64)))
     return rc;
-  static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
-  if (attr_set.first()) {
-    MST_CUDA_OK(cudaFuncSetAttribute(tc_gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  }
+  const int max_clusters = max_pair_clusters<EPI, BN_>();
   const int tiles = ceil_div(ceil_div(p.M, BLOCK_M), 2) * (p.N / Cfg::BN);
-  static const int max_clusters = max_active_clusters(tc_gemm_pair_kernel<EPI>, 2, Cfg::THREADS, Cfg::SMEM_BYTES);
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  MST_CUDA_OK(launch_pdl(tc_gemm_pair_kernel<EPI>, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, ta, tw, to, p));
+  MST_CUDA_OK(launch_pdl(tc_gemm_pair_kernel<EPI, BN_>, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, ta, tw, to, p));
   MST_LAUNCHED(EPI == TC_EPI_BIAS_BF16 ? "tc_gemm_qkv" : "tc_gemm_ffn1_gelu", s);
   return MST_OK;
+}
+
+// Tile width: 256 columns unless MST_PAIR_BN=128 asks for the narrow tile.  Measured at B=64 (round 2, graph-replayed,
+// tools/gemm_timeline.py): QKV 33.7 us at 256 (8.03 waves), 35.2 at 192 (10.7 waves), 38.7 at 128 (16.05 waves); FFN1
+// 25.1 at 256 (5.35 waves), 28.5 at 128 (10.7 waves) - the better wave balance of a narrow tile does not pay for its
+// lower operand re-use and the extra per-tile hand-overs, so the wave model that picked 192 for QKV was dropped
+// (as was the 192-column instantiation).
+template <int EPI>
+static int launch_gemm_pair(const TcGemmParams& p, cudaStream_t s) {
+  static const int pin = getenv("MST_PAIR_BN") ? atoi(getenv("MST_PAIR_BN")) : 256;
+  if (pin == 128 && p.N % 128 == 0) return launch_gemm_pair_bn<EPI, 128>(p, s);
+  return launch_gemm_pair_bn<EPI, 256>(p, s);
 }
 
 template <bool F16>
