@@ -176,8 +176,11 @@ def workload_config(a, where):
                         f"CFG (cond+uncond batched, scale 2.5) + root_horizontal inpainting, clip_denoised=False, "
                         f"MDM 8L/d512/4h/ff1024 random-init (BASELINE configs[1])",
             "batch_per_gpu": a.batch, "frames": a.frames, "feats": F_FEATS, "traj_steps": a.traj_steps,
-            "precision": a.precision if where == "gpu" else "fp32", "rng": "philox-in-kernel" if where == "gpu" else "torch-cpu",
-            "l2": "per-denoise-step working set (~250 MB of bf16 activations at B=64 CFG) exceeds the 126 MB L2; "
+            "precision": a.precision if where == "gpu" else "fp32",
+            "residual_stream": ("fp16 (LayerNorm outputs), bf16 elsewhere" if a.precision == "bf16" else "fp32") if where == "gpu" else "fp32",
+            "rng": "philox-in-kernel" if where == "gpu" else "torch-cpu",
+            "trajectory_submission": os.environ.get("MST_TRAJ_GRAPH", "full") + " (whole trajectory = one CUDA-graph launch)" if where == "gpu" else "n/a",
+            "l2": "per-denoise-step working set (~250 MB of 16-bit activations at B=64 CFG) exceeds the 126 MB L2; "
                   "a 256 MB buffer is also rewritten between trajectories" if where == "gpu" else "n/a"}
 
 
@@ -440,10 +443,11 @@ def finetune_leg(a, dev, rank, world, dist, B=64, T=76, steps=8, warmup=3):
     return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four GEMM launches of one layer (QKV 54.6 MB,
-# out-proj+LN 56.5 MB, FFN1+GELU 32.8 MB, FFN2+LN 85.0 MB) from one `ncu --set full` capture of the B=64, T=196 step
-NCU_TRAFFIC_B64 = {(64, 196): 57.2e6}
-NCU_TRAFFIC_SRC = "profiles/r01e_ncu_full_step_kernels_summary.txt (bytes per launch, mean of the 4 GEMM launches of a layer)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four GEMM launches of one layer, from one
+# `ncu --set full` capture of the B=64, T=196 step; re-derived every round (tools/ncu_raw_summary.py on the capture)
+NCU_TRAFFIC_B64 = {(64, 196): 55.7e6}
+NCU_TRAFFIC_SRC = ("profiles/r02h_ncu_full_step_kernels_summary.txt (round-2 capture: dram read + write bytes per launch, mean of the "
+                   "4 GEMM launches of a layer: QKV 53.1 MB, out-proj+LN 55.2 MB, FFN1+GELU 30.1 MB, FFN2+LN 84.5 MB)")
 
 
 def roofline_leg(K, model, dev, B, T, pk, ms_denoise_in_graph, steady=True):
@@ -530,8 +534,8 @@ def roofline_leg(K, model, dev, B, T, pk, ms_denoise_in_graph, steady=True):
     if roof is not None:
         # the secondary bound that explains the tensor fraction: every tile design here stages 128 A rows + 128 W rows
         # per CTA and k-block = 128 flop per byte pulled through L2, and the L2 slices deliver ~6300 B/clk chip-wide
-        roof["l2_bound_note"] = ("GEMM tiles move 1 B through L2 per 128 flop; at the ~6300 B/clk LTS cap that is "
-                                 "0.66 of the tensor pipe's 8192 flop/clk/SM - see DESIGN.md section 4")
+        roof["fabric_note"] = ("ncu (profiles/r02h_*): crossbar->L1 at 28 %, LTS->crossbar at 36 % of their peaks in the QKV GEMM - "
+                               "the L2 fabric is not the bound (round 1's '0.66 L2 cap' is withdrawn); see DESIGN.md section 4")
     upd = [s for s in stages if s["kernel"] == "update"]
     if upd and roof is not None:
         by = 20 * B * F_FEATS * T  # out_c, out_u, x_t, x_inp read + x_{t-1} write, [F] mask, in-kernel Philox

@@ -38,7 +38,6 @@ constexpr int ATT_SLOT_COLS = 256;
 struct AttnGeom {
   int S, s_pad, n_qt, n_heads, n_items, d_model;
   float scale_log2e;
-  int mma_poll;    // 1: the MMA thread issues Q K^T / P V in readiness order and staggers the two softmax groups
   long long* dbg;  // developer hook (mst_test_set_gemm_debug): clock64 timeline of CTA 0
 };
 
@@ -198,48 +197,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         mma_commit(o_full(slot));
         if (is_last_of_unit(it)) mma_commit(v_free);
       };
-      if (!g.mma_poll) {
-        if (i0 < i1) issue_qk(i0);
-        for (int it = i0; it < i1; ++it) {
-          if (it + 1 < i1) issue_qk(it + 1);
-          issue_pv(it);
-        }
-      } else {
-        // Readiness order.  In program order (Q K^T of item i+1, then P V of item i) a Q K^T that waits for its TMEM
-        // slot holds back a P V whose P is ready, and both softmax groups start together and stay in lock-step: their
-        // exp2 passes collide on the SFU pipe (3.9 k cycles each instead of ~2 k) while the pipe idles during their
-        // other phases.  Here the first odd item is held until the first P V has been issued - the groups run half a
-        // period apart - and afterwards whichever of the two MMA batches has its inputs is issued first.
-        auto qk_ready = [&](int it) {
-          const int j = it - i0, slot = j & 1, qb = j & 1;
-          if (is_new_unit(it) && !mbar_try_wait(k_full, k_units & 1)) return false;
-          if (!mbar_try_wait(q_full(qb), (j >> 1) & 1)) return false;
-          return mbar_try_wait(slot_free(slot), ((j >> 1) & 1) ^ 1);
-        };
-        auto pv_ready = [&](int it) {
-          const int j = it - i0, slot = j & 1;
-          if (!mbar_try_wait(p_ready(slot), (j >> 1) & 1)) return false;
-          return !is_new_unit(it) || mbar_try_wait(v_full, v_units & 1);
-        };
-        int next_qk = i0, next_pv = i0;
-        const long long t_start = clock64();
-        while (next_pv < i1) {
-          bool progressed = false;
-          if (next_pv < next_qk && pv_ready(next_pv)) {
-            issue_pv(next_pv++);
-            progressed = true;
-          }
-          // at most two items in flight (two TMEM slots); the second item of the CTA waits for the first P V
-          if (next_qk < i1 && next_qk <= next_pv + 1 && !(next_qk == i0 + 1 && next_pv == i0) && qk_ready(next_qk)) {
-            issue_qk(next_qk++);
-            progressed = true;
-          }
-          if (!progressed && clock64() - t_start > 8000000000LL) {
-            printf("mst: attention MMA issuer made no progress (block %d, qk %d pv %d of [%d, %d))\n", (int)blockIdx.x,
-                   next_qk, next_pv, i0, i1);
-            __trap();
-          }
-        }
+      if (i0 < i1) issue_qk(i0);
+      for (int it = i0; it < i1; ++it) {
+        if (it + 1 < i1) issue_qk(it + 1);
+        issue_pv(it);
       }
     }
   } else if (warp >= 4) {
@@ -1193,10 +1154,6 @@ int tc_attention(const TcAttnParams& p, cudaStream_t s) {
   g.d_model = p.d_model;
   g.scale_log2e = 1.4426950408889634f / sqrtf((float)ATT_DH);
   g.dbg = attn_debug_ptr();
-  {
-    static const int poll = getenv("MST_ATTN_POLL") ? atoi(getenv("MST_ATTN_POLL")) : 0;
-    g.mma_poll = poll;
-  }
   const int grid = g.n_items < sm_count() ? g.n_items : sm_count();
   static const int attn_v = getenv("MST_ATTN_V") ? atoi(getenv("MST_ATTN_V")) : 2;
   if (attn_v == 4) {
