@@ -203,6 +203,22 @@ __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, i
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (n + j < p.n_valid) dst[(size_t)j * p.T] = x[j];
+  } else if constexpr (EPI == TC_EPI_BIAS_BF16 || EPI == TC_EPI_BIAS_GELU_BF16) {
+    // small problems only (see tc_gemm: a handful of row blocks): row-per-thread 16-byte stores are fine there
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        uint64_t v2 = pk2(x[8 * q + 2 * e], x[8 * q + 2 * e + 1]);
+        if constexpr (EPI == TC_EPI_BIAS_GELU_BF16) v2 = gelu2(v2);
+        float y0, y1;
+        upk2(v2, y0, y1);
+        o[e] = pack_bf16x2(y0, y1);
+      }
+      dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   } else if constexpr (EPI == TC_EPI_BIAS_F32) {
     float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)row * p.ldo + n);
 #pragma unroll
@@ -1554,6 +1570,19 @@ static long long* g_gemm_dbg = nullptr;
 void set_gemm_debug(long long* dev_buf) { g_gemm_dbg = dev_buf; }
 long long* attn_debug_ptr() { return g_gemm_dbg; }
 
+// Latency regime (B = 1 ... 8 trajectories: M of a few hundred rows): a 256 x 256 pair tile is one serial chain of
+// K/64 k-blocks x 512 cycles on ONE SM pair while the rest of the chip idles (9 us per launch at B=1,
+// profiles/r02i_*).  128 x 64 tiles on single CTAs cut the chain to K/64 x 128 cycles and spread it over N/64 times
+// more SMs.  Threshold (measured, 50-step sweep at T=196): up to 48 wide tiles (B <= 4): 0.352 -> 0.312 ms per step at B=1,
+// 0.372 -> 0.346 at B=4; from B=8 on the wide tiles win again.  MST_SMALL_GEMM=0 disables.
+static bool small_problem(const TcGemmParams& p) {
+  static const bool on = !(getenv("MST_SMALL_GEMM") && getenv("MST_SMALL_GEMM")[0] == '0');
+  if (!on) return false;
+  static const int max_tiles = getenv("MST_SMALL_GEMM_TILES") ? atoi(getenv("MST_SMALL_GEMM_TILES")) : 48;
+  const int tiles = ceil_div(ceil_div(p.M, BLOCK_M), 2) * (p.N / 256);
+  return tiles <= max_tiles;
+}
+
 int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
   TcGemmParams p = p_in;
   p.dbg = g_gemm_dbg;
@@ -1567,9 +1596,11 @@ int tc_gemm(const TcGemmParams& p_in, cudaStream_t s) {
   switch (p.epi) {
     case TC_EPI_BIAS_BF16:
       MST_CHECK_ARG(p.N % 256 == 0 && p.ldo % 8 == 0, "N must be a multiple of 256");
+      if (small_problem(p)) return launch_gemm<64, TC_EPI_BIAS_BF16>(p, s);
       return launch_gemm_pair<TC_EPI_BIAS_BF16>(p, s);
     case TC_EPI_BIAS_GELU_BF16:
       MST_CHECK_ARG(p.N % 256 == 0 && p.ldo % 8 == 0, "N must be a multiple of 256");
+      if (small_problem(p)) return launch_gemm<64, TC_EPI_BIAS_GELU_BF16>(p, s);
       return launch_gemm_pair<TC_EPI_BIAS_GELU_BF16>(p, s);
     case TC_EPI_BIAS_RES_LN:
       MST_CHECK_ARG(p.N == LN_N && p.residual && p.ln_g && p.ln_b, "LN epilogue needs N == 512 and residual/gamma/beta");
