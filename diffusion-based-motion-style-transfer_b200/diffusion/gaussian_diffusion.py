@@ -546,11 +546,21 @@ class GaussianDiffusion:
         terms = {}
         mu = text_features = None
         noise_t2m = th.rand_like(x_start)  # sic: uniform noise in the reference (:1334); drawn in the same RNG order
+        early_cos = None
         if semantic_guidance:
             # (the reference also runs this forward with semantic_guidance == 0 and discards the result, :1335-1337)
             x_t = self.q_sample(x_start, t, noise=noise_t2m, model_kwargs=model_t2m_kwargs)
             model_output = native(x_t, self._map_model_t(t), **model_t2m_kwargs)
             mu, text_features = motion_enc(model_output, **model_t2m_kwargs)
+            hook = getattr(self, "early_t2m_backward", None)
+            if hook is not None:
+                # data-parallel trainer: this term is the only one that differs between ranks.  Back-propagate it NOW and
+                # let the trainer all-reduce its gradient while the (replicated) style term below is still being computed.
+                features_norm = text_features / text_features.norm(dim=-1, keepdim=True)
+                mu_norm = mu / mu.norm(dim=-1, keepdim=True)
+                early_cos = (1 - th.nn.functional.cosine_similarity(features_norm, mu_norm, dim=1, eps=1e-6)).mean()
+                hook(early_cos * Ls)
+                early_cos = early_cos.detach()
         if not use_ddim:
             sample_fn = self.p_sample_loop
         else:
@@ -570,7 +580,10 @@ class GaussianDiffusion:
         target = target.expand(num_step, -1, -1, -1)
         mask = mask.expand(num_step, -1, -1, -1)
         terms["rot_mse"] = self.masked_l2(target, sample, mask)
-        if semantic_guidance:
+        if semantic_guidance and early_cos is not None:
+            terms["text_cosine"] = early_cos  # already back-propagated (detached): the value is kept for logging
+            terms["loss"] = terms["rot_mse"].mean() + early_cos * Ls
+        elif semantic_guidance:
             features_norm = text_features / text_features.norm(dim=-1, keepdim=True)
             mu_norm = mu / mu.norm(dim=-1, keepdim=True)
             cos = th.nn.functional.cosine_similarity(features_norm, mu_norm, dim=1, eps=1e-6)

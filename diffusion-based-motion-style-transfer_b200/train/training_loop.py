@@ -216,7 +216,38 @@ class TrainInpaintingLoop:
         self._anneal_lr()
         self.step += 1
 
+    # ---- overlapped gradient exchange (data parallel, semantic guidance on) ---------------------------------------
+    # Only the text-to-motion term differs between ranks (the B=1 style term is replicated: same seed, same inputs, same
+    # gradient everywhere).  few_shot_style_finetune_losses hands that term to _early_t2m_backward as soon as it exists:
+    # its gradient is back-propagated into the arena, moved to a side buffer and all-reduced ASYNCHRONOUSLY (NCCL's own
+    # stream) while the six style steps run forward and backward; sync_gradients then only waits and adds mean(t2m grad)
+    # to the style gradient.  MST_OVERLAP_ALLREDUCE=0 restores the single blocking all-reduce of the whole arena.
+    def _early_t2m_backward(self, loss_t2m):
+        flat = self.mp_trainer.flat
+        self.mp_trainer.backward(loss_t2m)
+        if self.__dict__.get("_g_t2m") is None:
+            self._g_t2m = torch.empty_like(flat.grads)
+        self._g_t2m.copy_(flat.grads)
+        flat.grads.zero_()
+        ev = self.__dict__.get("_ov_events")
+        if ev is None:
+            ev = self._ov_events = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()                                   # all-reduce handed to NCCL here
+        self._t2m_work = dist.all_reduce(self._g_t2m, op=dist.ReduceOp.SUM, async_op=True)
+
     def sync_gradients(self):
+        work = self.__dict__.pop("_t2m_work", None)
+        if work is not None:
+            ev = self._ov_events
+            ev[1].record()                               # the style term's gradient is complete
+            work.wait()                                  # the compute stream waits for NCCL's stream (a no-op if it is done)
+            ev[2].record()
+            self.mp_trainer.flat.grads.add_(self._g_t2m, alpha=1.0 / self.world)
+            self.opt.grad_scale = 1.0                    # the arena already holds the mean gradient
+            self._overlapped = True
+            return
+        self.opt.grad_scale = 1.0 / self.world
+        self._overlapped = False
         if self.use_ddp:
             ev = self.__dict__.get("_ar_events")
             if ev is None and self.mp_trainer.flat.grads.is_cuda:
@@ -226,6 +257,15 @@ class TrainInpaintingLoop:
             dist.all_reduce(self.mp_trainer.flat.grads, op=dist.ReduceOp.SUM)
             if ev is not None:
                 ev[1].record()
+
+    def last_overlap(self):
+        """(window ms between handing the all-reduce to NCCL and needing its result, exposed wait ms) of the most recent
+        overlapped step, or None"""
+        if not self.__dict__.get("_overlapped"):
+            return None
+        ev = self._ov_events
+        ev[2].synchronize()
+        return float(ev[0].elapsed_time(ev[1])), float(ev[1].elapsed_time(ev[2]))
 
     def last_allreduce_ms(self):
         """device time of the most recent gradient all-reduce (CUDA events around the collective; synchronises)"""
@@ -243,6 +283,8 @@ class TrainInpaintingLoop:
                                       "the reference's generic training_losses path is outside the scope table")
         if self.use_ddp:
             batch, cond, _ = shard_batch(batch, cond, self.rank, self.world)
+        overlap = self.use_ddp and self.semantic_guidance and os.environ.get("MST_OVERLAP_ALLREDUCE", "1") != "0"
+        self.diffusion.early_t2m_backward = self._early_t2m_backward if overlap else None
         args = self.args
         if getattr(args, "use_ddim", 0):
             rng = range(int((args.diffusion_steps - args.skip_steps) / args.diffusion_steps * 20))
