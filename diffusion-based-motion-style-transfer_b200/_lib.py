@@ -112,8 +112,9 @@ class ClipTextWeights(C.Structure):
 
 def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-            "-Xcompiler", "-fPIC", "-shared", "-o", out_path] + [os.path.join(_CSRC, s) for s in SOURCES]
+    extra = os.environ.get("MST_NVCC_FLAGS", "").split()
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"] + extra + [
+        "-Xcompiler", "-fPIC", "-shared", "-o", out_path] + [os.path.join(_CSRC, s) for s in SOURCES]
 
 
 HASH_PATH = LIB_PATH + ".srchash"

@@ -38,8 +38,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef MST_MBAR_SUSPEND_NS
+#define MST_MBAR_SUSPEND_NS 20000  // measured: -0.24 % on the B=64 step (fewer polling trips of the waiting warps)
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if MST_MBAR_SUSPEND_NS > 0
+  // suspend-time hint: the warp may stay parked up to this long before try_wait returns false, instead of the
+  // (short) system default - fewer trips around the polling loop for warps that wait for microseconds
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"((uint32_t)MST_MBAR_SUSPEND_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -49,6 +65,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU.
@@ -143,6 +160,17 @@ __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk
 
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if MST_MBAR_SUSPEND_NS > 0
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"((uint32_t)MST_MBAR_SUSPEND_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -152,6 +180,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
