@@ -302,50 +302,53 @@ extern "C" int mst_engine_load_weights(mst_engine_t h, const mst_weights* w, voi
     cudaStream_t s = (cudaStream_t)stream;
     Carver c(packed_dev);
     int rc;
-    auto* in_w = c.take<__nv_bfloat16>((size_t)d.d_model * e->f_pad);
-    if ((rc = pack_bf16(w->in_w, in_w, d.d_model, d.n_feats, d.d_model, e->f_pad, s))) return rc;
-    auto* out_w = c.take<__nv_bfloat16>((size_t)e->f_pad * d.d_model);
-    if ((rc = pack_bf16(w->out_w, out_w, d.n_feats, d.d_model, e->f_pad, d.d_model, s))) return rc;
+    // every re-pack below is one job of ONE launch (this runs after every optimizer step of the finetune loop)
+    CvtJobs js;
+    const int dm = d.d_model, ff = d.d_ff;
+    auto* in_w = c.take<__nv_bfloat16>((size_t)dm * e->f_pad);
+    auto* out_w = c.take<__nv_bfloat16>((size_t)e->f_pad * dm);
     auto* out_b = c.take<float>(e->f_pad);
     pad_copy_f32_kernel<<<ceil_div(e->f_pad, 128), 128, 0, s>>>(w->out_b, out_b, d.n_feats, e->f_pad);
     MST_LAUNCHED("pad_copy", s);
     e->in_w_bf = in_w; e->out_w_bf = out_w; e->out_b_pad = out_b;
     for (int l = 0; l < d.n_layers; ++l) {
-      const mst_layer_weights& L = w->layers[l];
-      auto* qkv = c.take<__nv_bfloat16>((size_t)3 * d.d_model * d.d_model);
-      auto* o = c.take<__nv_bfloat16>((size_t)d.d_model * d.d_model);
-      auto* w1 = c.take<__nv_bfloat16>((size_t)d.d_ff * d.d_model);
-      auto* w2 = c.take<__nv_bfloat16>((size_t)d.d_model * d.d_ff);
-      if ((rc = pack_bf16(L.qkv_w, qkv, 3 * d.d_model, d.d_model, 3 * d.d_model, d.d_model, s))) return rc;
-      if ((rc = pack_bf16(L.o_w, o, d.d_model, d.d_model, d.d_model, d.d_model, s))) return rc;
-      if ((rc = pack_bf16(L.w1, w1, d.d_ff, d.d_model, d.d_ff, d.d_model, s))) return rc;
-      if ((rc = pack_bf16(L.w2, w2, d.d_model, d.d_ff, d.d_model, d.d_ff, s))) return rc;
+      auto* qkv = c.take<__nv_bfloat16>((size_t)3 * dm * dm);
+      auto* o = c.take<__nv_bfloat16>((size_t)dm * dm);
+      auto* w1 = c.take<__nv_bfloat16>((size_t)ff * dm);
+      auto* w2 = c.take<__nv_bfloat16>((size_t)dm * ff);
       e->lb[l] = LayerBF16{qkv, o, w1, w2};
     }
     for (int l = 0; l < d.n_layers; ++l) {
-      const mst_layer_weights& L = w->layers[l];
-      auto* qkv = c.take<__nv_bfloat16>((size_t)3 * d.d_model * d.d_model);  // [d, 3d]
-      auto* o = c.take<__nv_bfloat16>((size_t)d.d_model * d.d_model);         // [d, d]
-      auto* w1 = c.take<__nv_bfloat16>((size_t)d.d_ff * d.d_model);           // [d, ff]
-      auto* w2 = c.take<__nv_bfloat16>((size_t)d.d_model * d.d_ff);           // [ff, d]
-      if ((rc = cvt_bf16(L.qkv_w, 3 * d.d_model, d.d_model, d.d_model, nullptr, qkv, 3 * d.d_model, s))) return rc;
-      if ((rc = cvt_bf16(L.o_w, d.d_model, d.d_model, d.d_model, nullptr, o, d.d_model, s))) return rc;
-      if ((rc = cvt_bf16(L.w1, d.d_ff, d.d_model, d.d_model, nullptr, w1, d.d_ff, s))) return rc;
-      if ((rc = cvt_bf16(L.w2, d.d_model, d.d_ff, d.d_ff, nullptr, w2, d.d_model, s))) return rc;
+      auto* qkv = c.take<__nv_bfloat16>((size_t)3 * dm * dm);  // [d, 3d]
+      auto* o = c.take<__nv_bfloat16>((size_t)dm * dm);         // [d, d]
+      auto* w1 = c.take<__nv_bfloat16>((size_t)ff * dm);        // [d, ff]
+      auto* w2 = c.take<__nv_bfloat16>((size_t)dm * ff);        // [ff, d]
       e->lbt[l] = LayerBF16T{qkv, o, w1, w2};
     }
-    {
-      auto* out_h = c.take<__half>((size_t)e->f_pad * d.d_model);
-      if ((rc = pack_f16(w->out_w, out_h, d.n_feats, d.d_model, e->f_pad, d.d_model, s))) return rc;
-      e->out_w_h = out_h;
-      for (int l = 0; l < d.n_layers; ++l) {
-        const mst_layer_weights& L = w->layers[l];
-        auto* qkv = c.take<__half>((size_t)3 * d.d_model * d.d_model);
-        auto* w1 = c.take<__half>((size_t)d.d_ff * d.d_model);
-        if ((rc = pack_f16(L.qkv_w, qkv, 3 * d.d_model, d.d_model, 3 * d.d_model, d.d_model, s))) return rc;
-        if ((rc = pack_f16(L.w1, w1, d.d_ff, d.d_model, d.d_ff, d.d_model, s))) return rc;
-        e->lh[l] = LayerF16{qkv, w1};
+    auto* out_h = c.take<__half>((size_t)e->f_pad * dm);
+    e->out_w_h = out_h;
+    for (int l = 0; l < d.n_layers; ++l) {
+      auto* qkv = c.take<__half>((size_t)3 * dm * dm);
+      auto* w1 = c.take<__half>((size_t)ff * dm);
+      e->lh[l] = LayerF16{qkv, w1};
+    }
+    auto bf = [](const __nv_bfloat16* p) { return const_cast<__nv_bfloat16*>(p); };
+    auto hf = [](const __half* p) { return const_cast<__half*>(p); };
+    cvt_jobs_add(js, w->in_w, dm, d.n_feats, d.n_feats, in_w, nullptr, dm, e->f_pad, nullptr, 0, nullptr);
+    cvt_jobs_add(js, w->out_w, d.n_feats, dm, dm, out_w, out_h, e->f_pad, dm, nullptr, 0, nullptr);
+    for (int l = 0; l < d.n_layers; ++l) {
+      const mst_layer_weights& L = w->layers[l];
+      if (js.n + 4 > CVT_MAX_JOBS) {
+        if ((rc = cvt_multi(js, s, "pack_weights"))) return rc;
+        js = CvtJobs();
       }
+      cvt_jobs_add(js, L.qkv_w, 3 * dm, dm, dm, bf(e->lb[l].qkv_w), hf(e->lh[l].qkv_w), 3 * dm, dm, bf(e->lbt[l].qkv_w), 3 * dm, nullptr);
+      cvt_jobs_add(js, L.o_w, dm, dm, dm, bf(e->lb[l].o_w), nullptr, dm, dm, bf(e->lbt[l].o_w), dm, nullptr);
+      cvt_jobs_add(js, L.w1, ff, dm, dm, bf(e->lb[l].w1), hf(e->lh[l].w1), ff, dm, bf(e->lbt[l].w1), ff, nullptr);
+      cvt_jobs_add(js, L.w2, dm, ff, ff, bf(e->lb[l].w2), nullptr, dm, ff, bf(e->lbt[l].w2), dm, nullptr);
+    }
+    if ((rc = cvt_multi(js, s, "pack_weights"))) return rc;
+    {
       const char* env = getenv("MST_STREAM_F16");
       e->stream_f16 = !(env && env[0] == '0');
     }

@@ -141,4 +141,101 @@ __device__ __forceinline__ void smem_gemm_n128(const float* a, int lda, const fl
     }
 }
 
+// ---- tensor-core variants (mma.sync m16n8k8, tf32 operands, fp32 accumulation) -----------------------------------------
+// The packed SIMT products above are bound by the shared-memory pipe (every thread re-reads whole operand rows: ~40 k
+// wavefront cycles per CTA in the training attention).  Warp-level MMA fragments read each operand element once per 16 x 8
+// output tile: ~4 k cycles.  Used by the 16-bit training mode only (the fp32 parity mode keeps the exact fp32 products); tf32
+// keeps 10 mantissa bits, more than the bf16 operands of the linear layers around it.  256 threads = 8 warps.
+// Fragment layout (g = lane / 4, t = lane % 4):  A: (g, t) (g+8, t) (g, t+4) (g+8, t+4);  B: (k = t, n = g) (k = t+4, n = g);
+// C: (g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1); results are handed out as pairs of adjacent columns: out(m, n, v_n, v_n1).
+// operands go in as raw fp32 bits: the tensor core reads the upper 19 (sign, exponent, 10 mantissa bits), i.e. truncates;
+// cvt.rna.tf32 would round, but it expands to three instructions per element here and tripled the kernels' instruction count
+__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// C(m, n) = sum_k a[m*lda + k] * b[n*ldb + k] for m < 16 MT, n < 80 (operands zero padded); K % 8 == 0.
+// Work unit = one 16-row tile x two 8-column tiles; the 5 MT units go round the 8 warps.
+template <int MT, typename Out>
+__device__ __forceinline__ void mma_gemm_nt80(const float* a, int lda, const float* b, int ldb, int K, Out out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int u = warp; u < MT * 5; u += 8) {
+    const int mt = u / 5, n0 = (u - mt * 5) * 16;
+    float c[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[j][e] = 0.0f;
+    const float* ar = a + (16 * mt + g) * lda + t;
+    const float* br = b + (n0 + g) * ldb + t;
+#pragma unroll 4
+    for (int k = 0; k < K; k += 8) {
+      const uint32_t af[4] = {to_tf32(ar[k]), to_tf32(ar[8 * lda + k]), to_tf32(ar[k + 4]), to_tf32(ar[8 * lda + k + 4])};
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        mma_tf32(c[j], af, to_tf32(br[j * 8 * ldb + k]), to_tf32(br[j * 8 * ldb + k + 4]));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = 16 * mt + g, n = n0 + 8 * j + 2 * t;
+      out(m, n, c[j][0], c[j][1]);  // columns n, n + 1
+      out(m + 8, n, c[j][2], c[j][3]);
+    }
+  }
+}
+
+// C(m, n) = sum_k A(m, k) * b[k*ldb + n] for 128 columns, m < 16 MT; A(m, k) = TA ? a[k*lda + m] : a[m*lda + k]; K % 8 == 0.
+// Warp w owns columns [16 w, 16 w + 16) of all row tiles.
+template <bool TA, int MT, typename Out>
+__device__ __forceinline__ void mma_gemm_n128(const float* a, int lda, const float* b, int ldb, int K, Out out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float c[MT][2][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[i][j][e] = 0.0f;
+  const float* bc = b + 16 * warp + g;
+#pragma unroll 2
+  for (int k = 0; k < K; k += 8) {
+    uint32_t bf[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      bf[j][0] = to_tf32(bc[(k + t) * ldb + 8 * j]);
+      bf[j][1] = to_tf32(bc[(k + t + 4) * ldb + 8 * j]);
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      uint32_t af[4];
+      const int m = 16 * i + g;
+      if (TA) {
+        af[0] = to_tf32(a[(k + t) * lda + m]);
+        af[1] = to_tf32(a[(k + t) * lda + m + 8]);
+        af[2] = to_tf32(a[(k + t + 4) * lda + m]);
+        af[3] = to_tf32(a[(k + t + 4) * lda + m + 8]);
+      } else {
+        af[0] = to_tf32(a[m * lda + k + t]);
+        af[1] = to_tf32(a[(m + 8) * lda + k + t]);
+        af[2] = to_tf32(a[m * lda + k + t + 4]);
+        af[3] = to_tf32(a[(m + 8) * lda + k + t + 4]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) mma_tf32(c[i][j], af, bf[j][0], bf[j][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = 16 * i + g, n = 16 * warp + 8 * j + 2 * t;
+      out(m, n, c[i][j][0], c[i][j][1]);  // columns n, n + 1
+      out(m + 8, n, c[i][j][2], c[i][j][3]);
+    }
+}
+
 }  // namespace mst

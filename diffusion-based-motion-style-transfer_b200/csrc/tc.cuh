@@ -60,6 +60,27 @@ int pack_f16(const float* src, __half* dst, int rows, int cols, int rows_pad, in
 int cvt_bf16(const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, __nv_bfloat16* dst_t, int rows_pad,
              cudaStream_t s);
 
+// Several conversions in one launch: each job turns fp32 src [rows, cols] (leading dimension ld) into any of
+//   dst   bf16 [rows_pad, cols_pad] zero padded,      dst_h  fp16 [rows_pad, cols_pad] zero padded,
+//   dst_t bf16 [cols, t_ld] transposed, columns [rows, t_ld) zero,      colsum[c] += sum_r src[r, c].
+struct CvtJob {
+  const float* src;
+  __nv_bfloat16* dst;
+  __nv_bfloat16* dst_t;
+  __half* dst_h;
+  float* colsum;
+  int rows, cols, ld, rows_pad, cols_pad, t_ld, tile0, tiles_x;
+};
+constexpr int CVT_MAX_JOBS = 40;
+struct CvtJobs {
+  CvtJob j[CVT_MAX_JOBS];
+  int n = 0;
+  int tiles_of_last = 0;
+};
+void cvt_jobs_add(CvtJobs& js, const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, __half* dst_h, int rows_pad,
+                  int cols_pad, __nv_bfloat16* dst_t, int t_ld, float* colsum);
+int cvt_multi(const CvtJobs& js, cudaStream_t s, const char* name);
+
 struct TcAttnParams {
   const __nv_bfloat16* qkv = nullptr;  // [n_seqs*S, 3d]  (Q | K | V column blocks)
   __nv_bfloat16* out = nullptr;        // [n_seqs*S, d]

@@ -1747,6 +1747,74 @@ int cvt_bf16(const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, _
   return MST_OK;
 }
 
+// Several conversions in ONE launch (the per-weight / per-operand launches were pure latency on the finetune step: 83
+// launches to re-pack the weights after every optimizer step, 3 per backward linear): every job turns an fp32 matrix into any
+// of a zero-padded bf16 copy, a transposed bf16 copy, a zero-padded fp16 copy, and column sums; one CTA per 32 x 32 tile.
+__global__ void __launch_bounds__(256) cvt_multi_kernel(const __grid_constant__ CvtJobs jobs) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
+  __shared__ float tile[32][33];
+  __shared__ float red[8][32];
+  int k = 0;
+  while (k + 1 < jobs.n && (int)blockIdx.x >= jobs.j[k + 1].tile0) ++k;
+  const CvtJob& J = jobs.j[k];
+  const int t = (int)blockIdx.x - J.tile0;
+  const int r0 = (t / J.tiles_x) * 32, c0 = (t % J.tiles_x) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int rows = J.rows, cols = J.cols;
+  float part = 0.0f;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    const float v = (r < rows && c < cols) ? J.src[(size_t)r * J.ld + c] : 0.0f;
+    tile[i][tx] = v;
+    part += v;
+    if (r < J.rows_pad && c < J.cols_pad) {
+      if (J.dst) J.dst[(size_t)r * J.cols_pad + c] = __float2bfloat16_rn(v);
+      if (J.dst_h) J.dst_h[(size_t)r * J.cols_pad + c] = __float2half_rn(v);
+    }
+  }
+  if (J.colsum) red[ty][tx] = part;
+  if (!J.dst_t && !J.colsum) return;
+  __syncthreads();
+  if (J.colsum && ty == 0 && c0 + tx < cols && r0 < rows) {
+    float a = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][tx];
+    atomicAdd(J.colsum + c0 + tx, a);
+  }
+  if (J.dst_t)
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (c < cols && r < J.t_ld) J.dst_t[(size_t)c * J.t_ld + r] = __float2bfloat16_rn(tile[tx][i]);
+    }
+}
+
+void cvt_jobs_add(CvtJobs& js, const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, __half* dst_h, int rows_pad,
+                  int cols_pad, __nv_bfloat16* dst_t, int t_ld, float* colsum) {
+  CvtJob& J = js.j[js.n];
+  J.src = src; J.dst = dst; J.dst_t = dst_t; J.dst_h = dst_h; J.colsum = colsum;
+  J.rows = rows; J.cols = cols; J.ld = ld;
+  J.rows_pad = (dst || dst_h) ? rows_pad : 0;
+  J.cols_pad = (dst || dst_h) ? cols_pad : 0;
+  J.t_ld = dst_t ? t_ld : 0;
+  int r_ext = J.rows_pad > J.t_ld ? J.rows_pad : J.t_ld, c_ext = J.cols_pad > cols ? J.cols_pad : cols;
+  if (colsum && r_ext < rows) r_ext = rows;
+  if (!dst_t && !colsum) c_ext = J.cols_pad;
+  J.tiles_x = ceil_div(c_ext, 32);
+  J.tile0 = js.n ? js.j[js.n - 1].tile0 + js.tiles_of_last : 0;
+  js.tiles_of_last = J.tiles_x * ceil_div(r_ext, 32);
+  ++js.n;
+}
+
+int cvt_multi(const CvtJobs& js, cudaStream_t s, const char* name) {
+  if (js.n <= 0) return MST_OK;
+  const int tiles = js.j[js.n - 1].tile0 + js.tiles_of_last;
+  if (tiles <= 0) return MST_OK;
+  MST_CUDA_OK(launch_pdl(cvt_multi_kernel, dim3(tiles), dim3(256), 0, s, js));
+  MST_LAUNCHED(name, s);
+  return MST_OK;
+}
+
 __global__ void __launch_bounds__(256) pack_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows,
                                                        int cols, int rows_pad, int cols_pad) {
   const size_t total = (size_t)rows_pad * cols_pad;

@@ -309,11 +309,16 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__
     h[i] = gelu_f(u[i]);
 }
 // du = dh * gelu'(u), in place in dh
-__global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ u, float* __restrict__ dh, long long n) {
+// (+ a bf16 copy: the A operand of the dX GEMM that follows, when dh_bf is given)
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ u, float* __restrict__ dh,
+                                                       __nv_bfloat16* __restrict__ dh_bf, long long n) {
   pdl_launch_dependents();
   pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dh[i] *= gelu_grad_f(u[i]);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = dh[i] * gelu_grad_f(u[i]);
+    dh[i] = g;
+    if (dh_bf) dh_bf[i] = __float2bfloat16_rn(g);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -375,7 +380,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* in, const flo
 }
 
 // du = dh * mask * gelu'(u), in place in dh
-__global__ void __launch_bounds__(256) gelu_bwd_drop_kernel(const float* __restrict__ u, float* __restrict__ dh, long long n4,
+__global__ void __launch_bounds__(256) gelu_bwd_drop_kernel(const float* __restrict__ u, float* __restrict__ dh,
+                                                            __nv_bfloat16* __restrict__ dh_bf, long long n4,
                                                             long long per_seq4, Drop d, uint32_t site) {
   pdl_launch_dependents();
   pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
@@ -387,6 +393,10 @@ __global__ void __launch_bounds__(256) gelu_bwd_drop_kernel(const float* __restr
     g.x *= m.x * gelu_grad_f(uu.x); g.y *= m.y * gelu_grad_f(uu.y);
     g.z *= m.z * gelu_grad_f(uu.z); g.w *= m.w * gelu_grad_f(uu.w);
     reinterpret_cast<float4*>(dh)[v] = g;
+    if (dh_bf) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(g.x, g.y), hi = __floats2bfloat162_rn(g.z, g.w);
+      reinterpret_cast<uint2*>(dh_bf)[v] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
   }
 }
 
@@ -548,6 +558,151 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
+// The same for d = 128 * NC with 128-bit accesses: a lane owns the float4 chunks lane + 32 c of the row, so the dropout mask of
+// the residual branch (drawn per float4, drop_scale4) can be applied here and the separate dropout launch of the backward goes
+// away (dzm = dz * mask of `site`; null = not wanted).  The column partials of the 8 warps meet ONCE in shared memory (the
+// loop above pays 2 * NC * 4 barriers and as many rounds of atomics), and every warp fetches its next row before it reduces the
+// current one.
+template <int NC>
+__global__ void __launch_bounds__(256) layernorm_bwd4_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                             const float* __restrict__ gamma, float* __restrict__ dz,
+                                                             float* __restrict__ dzm, __nv_bfloat16* __restrict__ dz_bf,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int S,
+                                                             Drop drop, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
+  constexpr int d = 128 * NC;
+  __shared__ float4 red[8][2 * NC * 32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float4 dg[NC], db[NC], gm[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    dg[c] = db[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[c] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * c);
+  }
+  const float inv_d = 1.0f / (float)d;
+  const int stride = gridDim.x * 8;
+  int row = blockIdx.x * 8 + wib;
+  float4 v[NC], go[NC];
+  if (row < M) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      v[c] = __ldg(reinterpret_cast<const float4*>(z + (long long)row * d) + lane + 32 * c);
+      go[c] = __ldg(reinterpret_cast<const float4*>(dy + (long long)row * d) + lane + 32 * c);
+    }
+  }
+  for (; row < M; row += stride) {
+    float4 vn[NC], gn[NC];
+    const int next = row + stride;
+    if (next < M) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        vn[c] = __ldg(reinterpret_cast<const float4*>(z + (long long)next * d) + lane + 32 * c);
+        gn[c] = __ldg(reinterpret_cast<const float4*>(dy + (long long)next * d) + lane + 32 * c);
+      }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sum += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_d;
+    float q = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
+      q += v[c].x * v[c].x + v[c].y * v[c].y + v[c].z * v[c].z + v[c].w * v[c].w;
+    }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_d + 1e-5f);
+    float sg = 0.0f, sgx = 0.0f;
+    float4 g[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      v[c].x *= rstd; v[c].y *= rstd; v[c].z *= rstd; v[c].w *= rstd;  // xhat
+      g[c] = make_float4(go[c].x * gm[c].x, go[c].y * gm[c].y, go[c].z * gm[c].z, go[c].w * gm[c].w);
+      sg += (g[c].x + g[c].y) + (g[c].z + g[c].w);
+      sgx += g[c].x * v[c].x + g[c].y * v[c].y + g[c].z * v[c].z + g[c].w * v[c].w;
+      dg[c].x += go[c].x * v[c].x; dg[c].y += go[c].y * v[c].y; dg[c].z += go[c].z * v[c].z; dg[c].w += go[c].w * v[c].w;
+      db[c].x += go[c].x; db[c].y += go[c].y; db[c].z += go[c].z; db[c].w += go[c].w;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    const float mg = sg * inv_d, mgx = sgx * inv_d;
+    const int seq = row / S;
+    const long long local4 = (long long)(row - seq * S) * (d / 4);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float4 o4 = make_float4(rstd * (g[c].x - mg - v[c].x * mgx), rstd * (g[c].y - mg - v[c].y * mgx),
+                              rstd * (g[c].z - mg - v[c].z * mgx), rstd * (g[c].w - mg - v[c].w * mgx));
+      reinterpret_cast<float4*>(dz + (long long)row * d)[lane + 32 * c] = o4;
+      if (dzm) {
+        const float4 m = drop_scale4(drop, site, seq, local4 + lane + 32 * c);
+        o4.x *= m.x; o4.y *= m.y; o4.z *= m.z; o4.w *= m.w;
+        reinterpret_cast<float4*>(dzm + (long long)row * d)[lane + 32 * c] = o4;
+      }
+      if (dz_bf) {  // bf16 copy of what the GEMM branch sees (masked when dropout is on): A operand of the dX GEMM
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(o4.x, o4.y), hi = __floats2bfloat162_rn(o4.z, o4.w);
+        reinterpret_cast<uint2*>(dz_bf + (long long)row * d)[lane + 32 * c] =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { v[c] = vn[c]; go[c] = gn[c]; }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    red[wib][c * 32 + lane] = dg[c];
+    red[wib][(NC + c) * 32 + lane] = db[c];
+  }
+  __syncthreads();
+  // 2 * d column sums, 4 per float4 slot: thread t owns slots t, t + 256, ...
+  for (int slot = threadIdx.x; slot < 2 * NC * 32; slot += 256) {
+    float4 a = red[0][slot];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 b = red[w][slot];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const bool is_b = slot >= NC * 32;
+    float* out = is_b ? dbeta : dgamma;
+    if (out) {
+      const int col = 4 * (slot - (is_b ? NC * 32 : 0));  // chunk (c * 32 + lane) covers columns 4 * (lane + 32 c) ..
+      atomicAdd(out + col, a.x); atomicAdd(out + col + 1, a.y); atomicAdd(out + col + 2, a.z); atomicAdd(out + col + 3, a.w);
+    }
+  }
+}
+
+// LayerNorm backward (+ the dropout-masked copy of dz for the GEMM branch when dzm is given): picks the 128-bit kernel when
+// d is a multiple of 128.  Returns whether dzm was written (otherwise the caller runs the separate dropout kernel).
+static int layernorm_bwd(const float* dy, const float* z, const float* gamma, float* dz, float* dzm, __nv_bfloat16* dz_bf,
+                         float* dgamma, float* dbeta, int M, int d, int S, const Drop& drop, uint32_t site, bool* masked,
+                         bool* staged, cudaStream_t s) {
+  *masked = false;
+  *staged = false;
+  const int nc = d % 128 == 0 ? d / 128 : 0;
+  if (nc == 1 || nc == 2 || nc == 4) {  // 8 would need 64 KB of static shared memory for the partials
+    // rows per warp: 1 while that still fills the machine, at most ~4 (the column partials cost 2 d atomics per CTA)
+    int blocks = ceil_div(M, 8);
+    const int cap = 2 * sm_count();
+    if (blocks > cap) blocks = ceil_div(M, 8 * ceil_div(blocks, cap));
+    float* m = drop.on() ? dzm : nullptr;
+    cudaError_t err;
+    if (nc == 1) err = launch_pdl(layernorm_bwd4_kernel<1>, dim3(blocks), dim3(256), 0, s, dy, z, gamma, dz, m, dz_bf, dgamma, dbeta, M, S, drop, site);
+    else if (nc == 2) err = launch_pdl(layernorm_bwd4_kernel<2>, dim3(blocks), dim3(256), 0, s, dy, z, gamma, dz, m, dz_bf, dgamma, dbeta, M, S, drop, site);
+    else err = launch_pdl(layernorm_bwd4_kernel<4>, dim3(blocks), dim3(256), 0, s, dy, z, gamma, dz, m, dz_bf, dgamma, dbeta, M, S, drop, site);
+    MST_CUDA_OK(err);
+    *masked = m != nullptr;
+    *staged = dz_bf != nullptr;
+  } else {
+    const int blocks = ceil_div(M, 8) < sm_count() ? ceil_div(M, 8) : sm_count();  // few blocks: 2 d atomics each at the end
+    MST_CUDA_OK(launch_pdl(layernorm_bwd_kernel, dim3(blocks), dim3(256), 0, s, dy, z, gamma, dz, dgamma, dbeta, M, d));
+  }
+  MST_LAUNCHED("bwd_ln", s);
+  return MST_OK;
+}
+
 // out[n] += sum_m x[m*ld + n]
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int ld,
                                                      int rows_per_block) {
@@ -666,10 +821,13 @@ static int linear_fwd(bool tc, const Stage& st, const float* x, const Lin& L, co
 }
 
 // dx [M, n_in] = dy W (+ add); dW [n_out, n_in] += dy^T x; db [n_out] += column sums of dy (null pointers skip)
+// dy_staged: the producer of dy already left its bf16 copy in st.a (then frozen layers - no dW, no db - need no conversion
+// launch at all)
 static int linear_bwd(bool tc, const Stage& st, const float* dy, const float* x, const Lin& L, const float* add, float* dx,
-                      float* dw, float* db, int M, cudaStream_t s, const char* name_dx, const char* name_dw) {
+                      float* dw, float* db, int M, cudaStream_t s, const char* name_dx, const char* name_dw,
+                      bool dy_staged = false) {
   int rc;
-  if (db && (rc = colsum(dy, db, M, L.n_out, L.n_out, s))) return rc;
+  if (db && !tc && (rc = colsum(dy, db, M, L.n_out, L.n_out, s))) return rc;
   if (!tc) {
     if (dw) {
       GemmEx g;  // dW += dy^T x
@@ -685,9 +843,15 @@ static int linear_bwd(bool tc, const Stage& st, const float* dy, const float* x,
     }
     return MST_OK;
   }
-  if ((rc = cvt_bf16(dy, M, L.n_out, L.n_out, dx ? st.a : nullptr, dw ? st.at : nullptr, st.m_pad, s))) return rc;
+  {  // one launch: dy -> bf16 (operand of dX), dy^T (operand of dW), db += column sums;  x^T (operand of dW)
+    CvtJobs js;
+    __nv_bfloat16* a_dst = dx && !dy_staged ? st.a : nullptr;
+    if (a_dst || dw || db)
+      cvt_jobs_add(js, dy, M, L.n_out, L.n_out, a_dst, nullptr, M, L.n_out, dw ? st.at : nullptr, st.m_pad, db);
+    if (dw) cvt_jobs_add(js, x, M, L.n_in, L.n_in, nullptr, nullptr, 0, 0, st.bt, st.m_pad, nullptr);
+    if ((rc = cvt_multi(js, s, "bwd_operands"))) return rc;
+  }
   if (dw) {
-    if ((rc = cvt_bf16(x, M, L.n_in, L.n_in, nullptr, st.bt, st.m_pad, s))) return rc;
     TcGemmParams p;
     p.a = st.at; p.w = st.bt; p.out = dw; p.ldo = L.n_in; p.M = L.n_out; p.N = L.n_in; p.K = st.m_pad;
     p.accumulate = 1; p.epi = TC_EPI_TRAIN_F32;
@@ -775,7 +939,7 @@ __device__ __forceinline__ float drop_scale1(const Drop& d, uint32_t site, int s
 // kernel of their forward.
 // Shared memory: Q and V share one buffer (V is fetched once the scores are done), so two CTAs fit on an SM - the kernel is
 // latency-bound with 8 warps per SM (2 per scheduler), and at B=64 all 256 CTAs are then co-resident instead of 2 waves.
-template <int TM>
+template <int TM, bool MMA>
 __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ key_valid,
                                                              float* __restrict__ p_out, float* __restrict__ pd_out,
                                                              float* __restrict__ ao, __nv_bfloat16* __restrict__ ao_bf, int S,
@@ -811,7 +975,12 @@ __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __r
     }
   }
   __syncthreads();
-  smem_gemm_nt2<TM, 5>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v) { Ps[i * SA_LDP + j] = v * scale; });
+  if constexpr (MMA)
+    mma_gemm_nt80<TM>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v0, float v1) {
+      *reinterpret_cast<float2*>(Ps + i * SA_LDP + j) = make_float2(v0 * scale, v1 * scale);
+    });
+  else
+    smem_gemm_nt2<TM, 5>(Qs, SA_LDX, Ks, SA_LDX, SA_DH, [&](int i, int j, float v) { Ps[i * SA_LDP + j] = v * scale; });
   __syncthreads();
   {
     float* const dst[1] = {Vs};
@@ -842,33 +1011,60 @@ __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __r
     }
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.0f / sum;
-    for (int j = lane; j < S; j += 32) {
-      float pv = r[j] * inv;
-      pg[i * S + j] = pv;
-      if (drop.on()) {
-        pv *= drop_scale1(drop, site, seq, ((long long)head * S + i) * S + j);
-        pdg[i * S + j] = pv;
+    if (!drop.on()) {
+      for (int j = lane; j < S; j += 32) {
+        const float pv = r[j] * inv;
+        pg[i * S + j] = pv;
+        r[j] = pv;
       }
-      r[j] = pv;
+    } else {
+      // the mask is drawn per group of 4 consecutive elements of the flattened [H, S, S] probabilities: a lane takes one
+      // group (one Philox call instead of one per element) and the up to 4 elements of this row that fall into it
+      const long long base = ((long long)head * S + i) * S, g0 = base >> 2;
+      const int ng = (int)(((base + S - 1) >> 2) - g0) + 1;  // <= 21 for S <= 80
+      for (int gi = lane; gi < ng; gi += 32) {
+        const float4 m = drop_scale4(drop, site, seq, g0 + gi);
+        const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = (int)(4 * (g0 + gi) + e - base);
+          if (j >= 0 && j < S) {
+            const float pv = r[j] * inv;
+            pg[i * S + j] = pv;
+            pdg[i * S + j] = pv * mm[e];
+            r[j] = pv * mm[e];
+          }
+        }
+      }
     }
   }
   __syncthreads();
   float* og = ao + (long long)seq * S * d_model + head * SA_DH;
   __nv_bfloat16* ob = ao_bf ? ao_bf + (long long)seq * S * d_model + head * SA_DH : nullptr;  // operand of the out-projection
-  smem_gemm_n128<false, TM>(Ps, SA_LDP, Vs, SA_LDX, SA_MAXS, [&](int li, int c, float v) {
-    const int i = r0 + li;
-    if (i < S) {
-      og[(long long)i * d_model + c] = v;
-      if (ob) ob[(long long)i * d_model + c] = __float2bfloat16_rn(v);
-    }
-  });
+  if constexpr (MMA)
+    mma_gemm_n128<false, TM>(Ps, SA_LDP, Vs, SA_LDX, SA_MAXS, [&](int li, int c, float v0, float v1) {
+      const int i = r0 + li;
+      if (i < S) {
+        *reinterpret_cast<float2*>(og + (long long)i * d_model + c) = make_float2(v0, v1);
+        if (ob) *reinterpret_cast<__nv_bfloat162*>(ob + (long long)i * d_model + c) = __floats2bfloat162_rn(v0, v1);
+      }
+    });
+  else
+    smem_gemm_n128<false, TM>(Ps, SA_LDP, Vs, SA_LDX, SA_MAXS, [&](int li, int c, float v) {
+      const int i = r0 + li;
+      if (i < S) {
+        og[(long long)i * d_model + c] = v;
+        if (ob) ob[(long long)i * d_model + c] = __float2bfloat16_rn(v);
+      }
+    });
 }
 
 // grid (heads, n_seqs).  dao [n_seqs*S, d] -> dqkv [n_seqs*S, 3d] (Q | K | V column blocks)
+template <bool MMA>
 __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ p_in,
                                                              const float* __restrict__ pd_in, const float* __restrict__ dao,
-                                                             float* __restrict__ dqkv, int S, int d_model, int H, float scale,
-                                                             Drop drop, uint32_t site) {
+                                                             float* __restrict__ dqkv, __nv_bfloat16* __restrict__ dqkv_bf, int S,
+                                                             int d_model, int H, float scale, Drop drop, uint32_t site) {
   pdl_launch_dependents();
   pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
   extern __shared__ float sm[];
@@ -881,6 +1077,7 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   const int head = blockIdx.x, seq = blockIdx.y;
   const float* base = qkv + (long long)seq * S * 3 * d_model + head * SA_DH;
   float* dbase = dqkv + (long long)seq * S * 3 * d_model + head * SA_DH;
+  __nv_bfloat16* dbf = dqkv_bf ? dqkv_bf + (long long)seq * S * 3 * d_model + head * SA_DH : nullptr;  // operand of the dX GEMM
   const long long pp = ((long long)seq * H + head) * S * S;
   {
     float* const dst[3] = {Qs, Ks, Vs};
@@ -893,14 +1090,33 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   sa_load_p(Ps, (drop.on() ? pd_in : p_in) + pp, S);
   __syncthreads();
   // dV = Pd^T dO
-  smem_gemm_n128<true, 5>(Ps, SA_LDP, Os, SA_LDX, SA_MAXS, [&](int j, int c, float v) {
-    if (j < S) dbase[(long long)j * 3 * d_model + 2 * d_model + c] = v;
-  });
-  // dP = dO V^T (masked like the forward's dropout)
-  smem_gemm_nt2<5, 5>(Os, SA_LDX, Vs, SA_LDX, SA_DH, [&](int i, int j, float v) {
-    if (drop.on() && i < S && j < S) v *= drop_scale1(drop, site, seq, ((long long)head * S + i) * S + j);
-    Ds[i * SA_LDP + j] = v;
-  });
+  // results of the 128-column products: column block `blk` (0 Q, 1 K, 2 V) of dqkv, scaled
+  auto store1 = [&](int blk, float sc) {
+    return [=](int r, int c, float v) {
+      if (r < S) {
+        dbase[(long long)r * 3 * d_model + blk * d_model + c] = v * sc;
+        if (dbf) dbf[(long long)r * 3 * d_model + blk * d_model + c] = __float2bfloat16_rn(v * sc);
+      }
+    };
+  };
+  auto store2 = [&](int blk, float sc) {
+    return [=](int r, int c, float v0, float v1) {
+      if (r < S) {
+        *reinterpret_cast<float2*>(dbase + (long long)r * 3 * d_model + blk * d_model + c) = make_float2(v0 * sc, v1 * sc);
+        if (dbf)
+          *reinterpret_cast<__nv_bfloat162*>(dbf + (long long)r * 3 * d_model + blk * d_model + c) = __floats2bfloat162_rn(v0 * sc, v1 * sc);
+      }
+    };
+  };
+  if constexpr (MMA) mma_gemm_n128<true, 5>(Ps, SA_LDP, Os, SA_LDX, SA_MAXS, store2(2, 1.0f));
+  else smem_gemm_n128<true, 5>(Ps, SA_LDP, Os, SA_LDX, SA_MAXS, store1(2, 1.0f));
+  // dP = dO V^T (the forward's dropout mask is applied row by row below)
+  if constexpr (MMA)
+    mma_gemm_nt80<5>(Os, SA_LDX, Vs, SA_LDX, SA_DH, [&](int i, int j, float v0, float v1) {
+      *reinterpret_cast<float2*>(Ds + i * SA_LDP + j) = make_float2(v0, v1);
+    });
+  else
+    smem_gemm_nt2<5, 5>(Os, SA_LDX, Vs, SA_LDX, SA_DH, [&](int i, int j, float v) { Ds[i * SA_LDP + j] = v; });
   __syncthreads();
   if (drop.on()) {  // the softmax backward needs the probabilities BEFORE dropout
     sa_load_p(Ps, p_in + pp, S);
@@ -911,6 +1127,20 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   for (int i = warp; i < SA_MAXS; i += 8) {
     const float* pr = Ps + i * SA_LDP;
     float* dr = Ds + i * SA_LDP;
+    if (drop.on() && i < S) {  // dP *= mask: one Philox call per group of 4 consecutive elements (see the forward)
+      const long long base = ((long long)head * S + i) * S, g0 = base >> 2;
+      const int ng = (int)(((base + S - 1) >> 2) - g0) + 1;
+      for (int gi = lane; gi < ng; gi += 32) {
+        const float4 m = drop_scale4(drop, site, seq, g0 + gi);
+        const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = (int)(4 * (g0 + gi) + e - base);
+          if (j >= 0 && j < S) dr[j] *= mm[e];
+        }
+      }
+      __syncwarp();
+    }
     float dot = 0.0f;
     for (int j = lane; j < SA_MAXS; j += 32) dot = fmaf(pr[j], dr[j], dot);
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -918,17 +1148,27 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   }
   __syncthreads();
   // dQ = scale dS K ;  dK = scale dS^T Q
-  smem_gemm_n128<false, 5>(Ds, SA_LDP, Ks, SA_LDX, SA_MAXS, [&](int i, int c, float v) {
-    if (i < S) dbase[(long long)i * 3 * d_model + c] = v * scale;
-  });
-  smem_gemm_n128<true, 5>(Ds, SA_LDP, Qs, SA_LDX, SA_MAXS, [&](int j, int c, float v) {
-    if (j < S) dbase[(long long)j * 3 * d_model + d_model + c] = v * scale;
-  });
+  if constexpr (MMA) {
+    mma_gemm_n128<false, 5>(Ds, SA_LDP, Ks, SA_LDX, SA_MAXS, store2(0, scale));
+    mma_gemm_n128<true, 5>(Ds, SA_LDP, Qs, SA_LDX, SA_MAXS, store2(1, scale));
+  } else {
+    smem_gemm_n128<false, 5>(Ds, SA_LDP, Ks, SA_LDX, SA_MAXS, store1(0, scale));
+    smem_gemm_n128<true, 5>(Ds, SA_LDP, Qs, SA_LDX, SA_MAXS, store1(1, scale));
+  }
 }
 
 constexpr size_t SA_FWD_SMEM = (size_t)(2 * SA_MAXS * SA_LDX + SA_MAXS * SA_LDP) * sizeof(float);  // 111 KB: 2 CTAs per SM
 constexpr size_t SA_BWD_SMEM = (size_t)(4 * SA_MAXS * SA_LDX + 2 * SA_MAXS * SA_LDP) * sizeof(float);
 static_assert(SA_BWD_SMEM <= 227 * 1024, "small-attention backward shared memory");
+
+// the 16-bit training mode runs the attention products on mma.sync (tf32); MST_TRAIN_ATTN_MMA=0 keeps the fp32 FMAs
+static bool attn_mma(bool tc) {
+  static const bool on = [] {
+    const char* e = getenv("MST_TRAIN_ATTN_MMA");
+    return !(e && e[0] == '0');
+  }();
+  return tc && on;
+}
 
 static bool attn_small_ok(const mst_model_desc& d, int S) {
   return S <= SA_MAXS && d.d_model / d.n_heads == SA_DH;
@@ -1019,16 +1259,17 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
     if (attn_small_ok(d, S)) {
       static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
       if (attr_set.first()) {
-        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
-        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_FWD_SMEM));
       }
-      if (NS * H <= 32) {  // a handful of (sequence, head) pairs: five CTAs each
-        MST_CUDA_OK(launch_pdl(attn_small_fwd_kernel<1>, dim3(H, NS, 5), dim3(256), SA_FWD_SMEM, s, (const float*)t.qkv, key_valid,
-                               t.p, t.pd, t.ao, bf, S, dm, H, scale, drop, drop_site(l, 1)));
-      } else {
-        MST_CUDA_OK(launch_pdl(attn_small_fwd_kernel<5>, dim3(H, NS, 1), dim3(256), SA_FWD_SMEM, s, (const float*)t.qkv, key_valid,
-                               t.p, t.pd, t.ao, bf, S, dm, H, scale, drop, drop_site(l, 1)));
-      }
+      // 16-bit mode: the two products on mma.sync (tf32); fp32 parity mode: exact fp32 FMAs
+      const bool few = NS * H <= 32;  // a handful of (sequence, head) pairs: five CTAs each
+      auto kern = attn_mma(tc) ? (few ? attn_small_fwd_kernel<1, true> : attn_small_fwd_kernel<5, true>)
+                     : (few ? attn_small_fwd_kernel<1, false> : attn_small_fwd_kernel<5, false>);
+      MST_CUDA_OK(launch_pdl(kern, dim3(H, NS, few ? 5 : 1), dim3(256), SA_FWD_SMEM, s, (const float*)t.qkv, key_valid,
+                             t.p, t.pd, t.ao, bf, S, dm, H, scale, drop, drop_site(l, 1)));
       MST_LAUNCHED("train_attn_small", s);
     } else {
       GemmEx sc;  // scores = scale * Q K^T per (seq, head)
@@ -1146,46 +1387,48 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
     const mst_layer_grads& G = grads[l];
     Lin lqkv, lo, lf1, lf2;
     layer_lins(e, l, &lqkv, &lo, &lf1, &lf2);
-    const int ln_blocks = ceil_div(M, 8) < sm_count() ? ceil_div(M, 8) : sm_count();  // few blocks: 1024 atomics each at the end
-    // LN2
+    // LN2 (+ the dropout2 mask for the GEMM branch in the same kernel when the row width allows)
     float* dz2 = spare;
-    MST_CUDA_OK(launch_pdl(layernorm_bwd_kernel, dim3(ln_blocks), dim3(256), 0, s, (const float*)gx, (const float*)t.z2, L.ln2_g, dz2, G.ln2_g, G.ln2_b, M, dm));
-    MST_LAUNCHED("bwd_ln2", s);
+    bool masked, staged;
+    __nv_bfloat16* bf = tc ? w.stage.a : nullptr;  // producers leave the bf16 operand of the next dX GEMM here
+    if ((rc = layernorm_bwd(gx, t.z2, L.ln2_g, dz2, w.gm, bf, G.ln2_g, G.ln2_b, M, dm, S, drop, drop_site(l, 4), &masked, &staged, s))) return rc;
     // FFN2: dh = dz2 W2, dW2 += dz2^T h, db2 += sum dz2   (dropout2: the GEMM path sees the masked gradient)
     const float* dz2g = dz2;
     if (drop.on()) {
-      if ((rc = dropout(dz2, nullptr, w.gm, (long long)M * dm, drop, drop_site(l, 4), s))) return rc;
+      if (!masked && (rc = dropout(dz2, nullptr, w.gm, (long long)M * dm, drop, drop_site(l, 4), s))) return rc;
       dz2g = w.gm;
     }
-    if ((rc = linear_bwd(tc, w.stage, dz2g, t.h, lf2, nullptr, w.dh, G.w2, G.b2, M, s, "bwd_dh", "bwd_dw2"))) return rc;
+    if ((rc = linear_bwd(tc, w.stage, dz2g, t.h, lf2, nullptr, w.dh, G.w2, G.b2, M, s, "bwd_dh", "bwd_dw2", staged && (masked || !drop.on())))) return rc;
     if (drop.on())
-      MST_CUDA_OK(launch_pdl(gelu_bwd_drop_kernel, dim3(ew_blocks((long long)M * ff / 4)), dim3(256), 0, s, (const float*)t.u, w.dh,
+      MST_CUDA_OK(launch_pdl(gelu_bwd_drop_kernel, dim3(ew_blocks((long long)M * ff / 4)), dim3(256), 0, s, (const float*)t.u, w.dh, bf,
                              (long long)M * ff / 4, (long long)S * ff / 4, drop, drop_site(l, 3)));
     else
-      MST_CUDA_OK(launch_pdl(gelu_bwd_kernel, dim3(ew_blocks((long long)M * ff)), dim3(256), 0, s, (const float*)t.u, w.dh, (long long)M * ff));
+      MST_CUDA_OK(launch_pdl(gelu_bwd_kernel, dim3(ew_blocks((long long)M * ff)), dim3(256), 0, s, (const float*)t.u, w.dh, bf, (long long)M * ff));
     MST_LAUNCHED("bwd_gelu", s);
     // FFN1: dy = dz2 + du W1 (into gx: the incoming gradient is no longer needed), dW1 += du^T y, db1 += sum du
-    if ((rc = linear_bwd(tc, w.stage, w.dh, t.y, lf1, dz2, gx, G.w1, G.b1, M, s, "bwd_dy", "bwd_dw1"))) return rc;
+    if ((rc = linear_bwd(tc, w.stage, w.dh, t.y, lf1, dz2, gx, G.w1, G.b1, M, s, "bwd_dy", "bwd_dw1", bf != nullptr))) return rc;
     // LN1
     float* dz1 = spare;  // dz2 is dead
-    MST_CUDA_OK(launch_pdl(layernorm_bwd_kernel, dim3(ln_blocks), dim3(256), 0, s, (const float*)gx, (const float*)t.z1, L.ln1_g, dz1, G.ln1_g, G.ln1_b, M, dm));
-    MST_LAUNCHED("bwd_ln1", s);
+    if ((rc = layernorm_bwd(gx, t.z1, L.ln1_g, dz1, w.gm, bf, G.ln1_g, G.ln1_b, M, dm, S, drop, drop_site(l, 2), &masked, &staged, s))) return rc;
     float* dao = spare2;  // out-proj: dao = dz1 Wo, dWo += dz1^T ao, dbo += sum dz1   (dropout1: masked gradient)
     const float* dz1g = dz1;
     if (drop.on()) {
-      if ((rc = dropout(dz1, nullptr, w.gm, (long long)M * dm, drop, drop_site(l, 2), s))) return rc;
+      if (!masked && (rc = dropout(dz1, nullptr, w.gm, (long long)M * dm, drop, drop_site(l, 2), s))) return rc;
       dz1g = w.gm;
     }
-    if ((rc = linear_bwd(tc, w.stage, dz1g, t.ao, lo, nullptr, dao, G.o_w, G.o_b, M, s, "bwd_dao", "bwd_dwo"))) return rc;
+    if ((rc = linear_bwd(tc, w.stage, dz1g, t.ao, lo, nullptr, dao, G.o_w, G.o_b, M, s, "bwd_dao", "bwd_dwo", staged && (masked || !drop.on())))) return rc;
+    bool dqkv_staged = false;
     // attention
     if (attn_small_ok(d, S)) {
       static PerDeviceOnce attr_set;  // cudaFuncSetAttribute is per device
       if (attr_set.first()) {
-        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_BWD_SMEM));
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_BWD_SMEM));
+        MST_CUDA_OK(cudaFuncSetAttribute(attn_small_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_BWD_SMEM));
       }
-      MST_CUDA_OK(launch_pdl(attn_small_bwd_kernel, dim3(H, NS), dim3(256), SA_BWD_SMEM, s, (const float*)t.qkv, (const float*)t.p,
-                             (const float*)t.pd, (const float*)dao, w.dqkv, S, dm, H, scale, drop, drop_site(l, 1)));
+      MST_CUDA_OK(launch_pdl(attn_mma(tc) ? attn_small_bwd_kernel<true> : attn_small_bwd_kernel<false>, dim3(H, NS), dim3(256), SA_BWD_SMEM, s, (const float*)t.qkv, (const float*)t.p,
+                             (const float*)t.pd, (const float*)dao, w.dqkv, bf, S, dm, H, scale, drop, drop_site(l, 1)));
       MST_LAUNCHED("bwd_attn_small", s);
+      dqkv_staged = bf != nullptr;
     } else {
       const long long qkv_bs = (long long)S * 3 * dm, pp_bs = (long long)H * S * S, pp_hs = (long long)S * S;
       GemmEx dp;  // dP = dao V^T
@@ -1212,7 +1455,7 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
       if ((rc = gemm_ex(dk, s, "bwd_dk"))) return rc;
     }
     // QKV: gradient w.r.t. the layer input = dz1 + dqkv Wqkv, dWqkv += dqkv^T x, dbqkv += sum dqkv
-    if ((rc = linear_bwd(tc, w.stage, w.dqkv, t.x, lqkv, dz1, gx, G.qkv_w, G.qkv_b, M, s, "bwd_dx", "bwd_dwqkv"))) return rc;
+    if ((rc = linear_bwd(tc, w.stage, w.dqkv, t.x, lqkv, dz1, gx, G.qkv_w, G.qkv_b, M, s, "bwd_dx", "bwd_dwqkv", dqkv_staged))) return rc;
   }
   *g_x = gx;
   return MST_OK;

@@ -87,7 +87,7 @@ class MixedPrecisionTrainer:
         self.model_params = self.flat.trainable + self.flat.frozen
         self.master_params = self.model_params
         self.lg_loss_scale = initial_lg_loss_scale
-        self.last_norms = (0.0, 0.0)
+        self._norms_dev = None
         # gradients live in the arena from now on: the model may run its forward / backward on pooled tapes and
         # accumulate straight into them (CUDA-graph replay, model/mdm_forstyledataset.py::_DenoiserGradFn)
         # the native denoisers of the model (walked once: model.modules() costs ~0.1 ms per call and a step asks 5 times)
@@ -121,10 +121,23 @@ class MixedPrecisionTrainer:
         # after a SUM all-reduce the arena holds world_size x the mean gradient; the optimiser applies it scaled by
         # opt.grad_scale = 1 / world_size, and the logged norm is that of the applied (mean) gradient
         scale = getattr(opt, "grad_scale", 1.0)
-        grad_norm, param_norm = self._compute_norms(grad_scale=1.0 / scale if scale else 1.0)
-        self.last_norms = (grad_norm, param_norm)
+        # the two sums of squares stay on the device: reading them here would drain the GPU once per step (the host then
+        # cannot issue step i+1 while step i still runs); `last_norms` fetches them when somebody looks
+        self._flush()
+        self._norms_dev = (K.sumsq2(self.flat.grads, None), K.sumsq2(self.flat.params, None),
+                           1.0 / scale if scale else 1.0)
         opt.step()
         return True
+
+    @property
+    def last_norms(self):
+        """(||grad||_2 of the applied gradient, ||param||_2 before the step) of the most recent optimize() (reference
+        :215-223); synchronises with the device."""
+        dev = self.__dict__.get("_norms_dev")
+        if dev is None:
+            return (0.0, 0.0)
+        both = th.stack([dev[0], dev[1]]).cpu()  # ONE host read
+        return float(np.sqrt(both[0, 0].item())) / dev[2], float(np.sqrt(both[1, 0].item()))
 
     def _compute_norms(self, grad_scale=1.0):
         """(||grad||_2 / grad_scale, ||param||_2) over all master params (reference :215-223)."""

@@ -34,9 +34,30 @@ class ScheduleSampler(ABC):
             restricted = weights_all[data_range]
             prob = restricted / restricted.sum()
         drawn = np.random.choice(support, size=(batch_size,), p=prob)
-        timesteps = th.from_numpy(drawn).long().to(device)
-        importance = th.from_numpy(1 / (len(prob) * prob[drawn])).float().to(device)
-        return timesteps, importance
+        importance = 1 / (len(prob) * prob[drawn])
+        if th.device(device).type != "cuda":
+            return th.from_numpy(drawn).long().to(device), th.from_numpy(importance).float().to(device)
+        # a blocking host-to-device copy drains the stream once per training step; stage the few bytes in pinned memory
+        # and copy asynchronously instead (ring of staging buffers: a slot is reused only after its copy has completed)
+        ring = self.__dict__.setdefault("_h2d_ring", {})
+        key = (batch_size, str(device))
+        if key not in ring:
+            ring[key] = [0, [(th.empty(batch_size, dtype=th.int64).pin_memory(), th.empty(batch_size, dtype=th.float32).pin_memory(),
+                              th.cuda.Event()) for _ in range(4)], [False] * 4]
+        state = ring[key]
+        k = state[0] % 4
+        state[0] += 1
+        t_host, w_host, ev = state[1][k]
+        if state[2][k]:
+            ev.synchronize()
+        t_host.copy_(th.from_numpy(np.asarray(drawn, dtype=np.int64)))
+        w_host.copy_(th.from_numpy(np.asarray(importance, dtype=np.float32)))
+        with th.cuda.device(device):
+            timesteps = t_host.to(device, non_blocking=True)
+            weights = w_host.to(device, non_blocking=True)
+            ev.record()
+        state[2][k] = True
+        return timesteps, weights
 
 
 class UniformSampler(ScheduleSampler):

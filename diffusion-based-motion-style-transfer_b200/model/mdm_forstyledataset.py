@@ -183,7 +183,7 @@ class _DenoiserGradFn(torch.autograd.Function):
                               tape_seqs=slot.tape_seqs, tape_seq_offset=k * B)
             ctx.tape, ctx.epoch = slot.tape, slot.epoch
             return slot.out[r].clone()
-        ctx.drop_seed = torch.arange(key, key + B, dtype=torch.int64).to(x.device) if p > 0 else None
+        ctx.drop_seed = torch.arange(key, key + B, dtype=torch.int64, device=x.device) if p > 0 else None
         out, tape = eng.forward_train(x, temb, text_emb, uncond=uncond, dropout_p=p, dropout_seed=ctx.drop_seed)
         ctx.tape = tape
         return out
@@ -194,22 +194,35 @@ class _DenoiserGradFn(torch.autograd.Function):
             raise RuntimeError("the mst activation tape of this forward was already consumed by a backward pass "
                                "(retain_graph is not supported: run the forward again)")
         layers = ctx.native._mst_cached_tensors()[1]
-        flat = [p for lp in layers for p in lp.values()]
-        needs = {id(p): bool(ctx.needs_input_grad[5 + i]) for i, p in enumerate(flat)}
         slot = ctx.slot
         if slot is not None:
             if slot.epoch != ctx.epoch:
                 raise RuntimeError("this forward's pooled activation tape was recycled by a later training step "
                                    "(call backward() before the next zero_grad(), or disable the pool)")
-            direct = all((not needs[id(p)]) or (p.grad is not None and p.grad.is_contiguous() and
-                                                 p.grad.dtype == torch.float32) for p in flat)
+            # the six single-sequence forwards of a finetune step share one slot and ask the same question about the
+            # same ~100 parameters: walk them once per step (p.grad is a slow property), not once per backward call
+            want = ctx.needs_input_grad[5:]
+            cache = slot.__dict__.get("_bw_cache")
+            if cache is not None and cache[0] == slot.epoch and cache[1] is layers and cache[2] == want:
+                direct, grads, n_flat = cache[3], cache[4], cache[5]
+            else:
+                flat = [p for lp in layers for p in lp.values()]
+                needs = {id(p): bool(want[i]) for i, p in enumerate(flat)}
+                direct = all((not needs[id(p)]) or (p.grad is not None and p.grad.is_contiguous() and
+                                                     p.grad.dtype == torch.float32) for p in flat)
+                grads = ([{k_: (p.grad if needs[id(p)] else None) for k_, p in lp.items()} for lp in layers]
+                         if direct else None)
+                n_flat = len(flat)
+                slot._bw_cache = (slot.epoch, layers, want, direct, grads, n_flat)
             if direct and not ctx.needs_input_grad[1]:
                 # accumulate straight into .grad (what autograd's AccumulateGrad would do with a returned tensor); the
                 # kernels run once every forward recorded on this tape has reported its output gradient
-                grads = [{k_: (p.grad if needs[id(p)] else None) for k_, p in lp.items()} for lp in layers]
                 slot.stage_backward(ctx.k, d_out, ctx.drop_p, grads)
                 ctx.tape = None
-                return (None,) * (5 + len(flat))
+                return (None,) * (5 + n_flat)
+        flat = [p for lp in layers for p in lp.values()]
+        needs = {id(p): bool(ctx.needs_input_grad[5 + i]) for i, p in enumerate(flat)}
+        if slot is not None:
             # a gradient w.r.t. x (or parameters without .grad buffers) was requested: plain backward on the pooled tape
             B = d_out.shape[0]
             grads = _flat_layer_grads(layers, needs)
@@ -265,7 +278,7 @@ class _MotionEncoderGradFn(torch.autograd.Function):
                                        tape=slot.tape, mu=slot.mu, use_graph=True)
             ctx.tape, ctx.drop_seed = slot.tape, slot.seed
             return slot.mu.clone()
-        ctx.drop_seed = torch.arange(key, key + x.shape[0], dtype=torch.int64).to(x.device) if p > 0 else None
+        ctx.drop_seed = torch.arange(key, key + x.shape[0], dtype=torch.int64, device=x.device) if p > 0 else None
         mu, tape = eng.motion_encoder_forward(x, key_valid, mq, sq, dropout_p=p, dropout_seed=ctx.drop_seed)
         ctx.tape = tape
         return mu
