@@ -117,6 +117,24 @@ class MixedPrecisionTrainer:
         self._flush()   # batched backward passes still waiting for a forward whose output never reached the loss
         self.flat.ensure_grad_views()
 
+    def backward_into(self, loss: th.Tensor, grad_views):
+        """Back-propagate ``loss`` with every trainable parameter's ``.grad`` pointing at ``grad_views`` (a second
+        arena, same layout as ``flat.grads``) and put the arena views back afterwards: lets one loss term accumulate its
+        gradient apart from the others (on another stream, to be all-reduced on its own)."""
+        own = self.flat.__dict__.get("_grad_views")
+        if own is None:
+            self.flat.ensure_grad_views()
+            own = self.flat._grad_views
+        params = self.flat.trainable
+        for p, v in zip(params, grad_views):
+            p.grad = v
+        try:
+            loss.backward()
+            self._flush()
+        finally:
+            for p, v in zip(params, own):
+                p.grad = v
+
     def optimize(self, opt):
         # after a SUM all-reduce the arena holds world_size x the mean gradient; the optimiser applies it scaled by
         # opt.grad_scale = 1 / world_size, and the logged norm is that of the applied (mean) gradient

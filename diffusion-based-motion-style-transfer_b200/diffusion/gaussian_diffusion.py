@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import enum
 import math
+import contextlib
 import os
 from copy import deepcopy
 
@@ -547,20 +548,32 @@ class GaussianDiffusion:
         mu = text_features = None
         noise_t2m = th.rand_like(x_start)  # sic: uniform noise in the reference (:1334); drawn in the same RNG order
         early_cos = None
+        hook = getattr(self, "early_t2m_backward", None) if semantic_guidance else None
+        side = getattr(self, "t2m_stream", None) if hook is not None else None
         if semantic_guidance:
-            # (the reference also runs this forward with semantic_guidance == 0 and discards the result, :1335-1337)
-            x_t = self.q_sample(x_start, t, noise=noise_t2m, model_kwargs=model_t2m_kwargs)
-            model_output = native(x_t, self._map_model_t(t), **model_t2m_kwargs)
-            mu, text_features = motion_enc(model_output, **model_t2m_kwargs)
-            hook = getattr(self, "early_t2m_backward", None)
-            if hook is not None:
-                # data-parallel trainer: this term is the only one that differs between ranks.  Back-propagate it NOW and
-                # let the trainer all-reduce its gradient while the (replicated) style term below is still being computed.
-                features_norm = text_features / text_features.norm(dim=-1, keepdim=True)
-                mu_norm = mu / mu.norm(dim=-1, keepdim=True)
-                early_cos = (1 - th.nn.functional.cosine_similarity(features_norm, mu_norm, dim=1, eps=1e-6)).mean()
-                hook(early_cos * Ls)
-                early_cos = early_cos.detach()
+            if side is not None:
+                # the trainer's hook: this branch (the only one that differs between data-parallel ranks) runs on its own
+                # stream, next to the style steps below.  Weight re-packs happen on the main stream first, both streams
+                # read them; tensors of the main stream's allocator that the side stream reads are marked for it.
+                native.mst_engine(x_start.device, precision=native.mst_train_prec())
+                motion_enc.mst_engine(x_start.device, precision=motion_enc.mst_train_prec())
+                side.wait_stream(th.cuda.current_stream())
+                for tensor in (noise_t2m, t, x_start):
+                    tensor.record_stream(side)
+            with (th.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                # (the reference also runs this forward with semantic_guidance == 0 and discards the result, :1335-1337)
+                x_t = self.q_sample(x_start, t, noise=noise_t2m, model_kwargs=model_t2m_kwargs)
+                model_output = native(x_t, self._map_model_t(t), **model_t2m_kwargs)
+                mu, text_features = motion_enc(model_output, **model_t2m_kwargs)
+                if hook is not None:
+                    # back-propagate the term NOW: the trainer accumulates (and, data parallel, all-reduces) its gradient
+                    # apart from the style term's, which is still to be computed
+                    features_norm = text_features / text_features.norm(dim=-1, keepdim=True)
+                    mu_norm = mu / mu.norm(dim=-1, keepdim=True)
+                    early_cos = (1 - th.nn.functional.cosine_similarity(features_norm, mu_norm, dim=1, eps=1e-6)).mean()
+                    hook(early_cos * Ls)
+                    early_cos = early_cos.detach()
+                    mu = text_features = model_output = x_t = None
         if not use_ddim:
             sample_fn = self.p_sample_loop
         else:
@@ -581,8 +594,14 @@ class GaussianDiffusion:
         mask = mask.expand(num_step, -1, -1, -1)
         terms["rot_mse"] = self.masked_l2(target, sample, mask)
         if semantic_guidance and early_cos is not None:
-            terms["text_cosine"] = early_cos  # already back-propagated (detached): the value is kept for logging
-            terms["loss"] = terms["rot_mse"].mean() + early_cos * Ls
+            # already back-propagated (detached): the values are kept for logging.  They live on the side stream, so the
+            # sum with the style term is left to the trainer (after it has joined the streams): 'loss' is the part that
+            # still needs a backward pass, 'loss_t2m' the part that had its own
+            terms["text_cosine"] = early_cos
+            terms["loss_t2m"] = early_cos * Ls
+            terms["loss"] = terms["rot_mse"].mean()
+            if side is None:
+                terms["loss"] = terms["loss"] + terms.pop("loss_t2m")
         elif semantic_guidance:
             features_norm = text_features / text_features.norm(dim=-1, keepdim=True)
             mu_norm = mu / mu.norm(dim=-1, keepdim=True)

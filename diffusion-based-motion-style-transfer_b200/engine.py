@@ -213,9 +213,14 @@ class Engine:
         return int(tb.value), int(sb.value)
 
     def _scratch(self, nbytes: int) -> torch.Tensor:
-        if getattr(self, "_bwd_scratch", None) is None or self._bwd_scratch.numel() < nbytes:
-            self._bwd_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        return self._bwd_scratch
+        """backward scratch, one buffer PER STREAM: the trainer back-propagates the text-to-motion batch on a side stream
+        while the style steps run on the main one, through the same engine"""
+        pool = self.__dict__.setdefault("_bwd_scratch", {})
+        key = _stream_ptr()
+        buf = pool.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = pool[key] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return buf
 
     @_engine_device
     def forward_train(self, x: torch.Tensor, temb: torch.Tensor, text_emb: Optional[torch.Tensor], *,

@@ -203,7 +203,10 @@ class _DenoiserGradFn(torch.autograd.Function):
             # same ~100 parameters: walk them once per step (p.grad is a slow property), not once per backward call
             want = ctx.needs_input_grad[5:]
             cache = slot.__dict__.get("_bw_cache")
-            if cache is not None and cache[0] == slot.epoch and cache[1] is layers and cache[2] == want:
+            probe = layers[0]["qkv_w"].grad  # the trainer may point .grad at a second arena for this backward
+            arena = None if probe is None else probe.data_ptr()
+            if (cache is not None and cache[0] == slot.epoch and cache[1] is layers and cache[2] == want
+                    and cache[6] == arena):
                 direct, grads, n_flat = cache[3], cache[4], cache[5]
             else:
                 flat = [p for lp in layers for p in lp.values()]
@@ -213,7 +216,7 @@ class _DenoiserGradFn(torch.autograd.Function):
                 grads = ([{k_: (p.grad if needs[id(p)] else None) for k_, p in lp.items()} for lp in layers]
                          if direct else None)
                 n_flat = len(flat)
-                slot._bw_cache = (slot.epoch, layers, want, direct, grads, n_flat)
+                slot._bw_cache = (slot.epoch, layers, want, direct, grads, n_flat, arena)
             if direct and not ctx.needs_input_grad[1]:
                 # accumulate straight into .grad (what autograd's AccumulateGrad would do with a returned tensor); the
                 # kernels run once every forward recorded on this tape has reported its output gradient

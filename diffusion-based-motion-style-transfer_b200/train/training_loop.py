@@ -216,34 +216,49 @@ class TrainInpaintingLoop:
         self._anneal_lr()
         self.step += 1
 
-    # ---- overlapped gradient exchange (data parallel, semantic guidance on) ---------------------------------------
-    # Only the text-to-motion term differs between ranks (the B=1 style term is replicated: same seed, same inputs, same
-    # gradient everywhere).  few_shot_style_finetune_losses hands that term to _early_t2m_backward as soon as it exists:
-    # its gradient is back-propagated into the arena, moved to a side buffer and all-reduced ASYNCHRONOUSLY (NCCL's own
-    # stream) while the six style steps run forward and backward; sync_gradients then only waits and adds mean(t2m grad)
-    # to the style gradient.  MST_OVERLAP_ALLREDUCE=0 restores the single blocking all-reduce of the whole arena.
+    # ---- the text-to-motion term on its own stream (semantic guidance on) ------------------------------------------
+    # The step has two independent branches until the optimizer: the text-to-motion batch (denoiser + MotionEncoder forward
+    # and backward: throughput work) and the six sequential B=1 style steps (a latency chain that occupies a handful of
+    # SMs).  few_shot_style_finetune_losses runs the first branch on `diffusion.t2m_stream` and hands its loss term to
+    # _early_t2m_backward as soon as it exists: the term is back-propagated THERE, into a second gradient arena, and -
+    # data parallel - all-reduced asynchronously (only this term differs between ranks: the style term is replicated, same
+    # seed, same inputs), all while the main stream works through the style steps.  sync_gradients joins the streams and
+    # forms  style gradient + mean(t2m gradients)  for the fused AdamW.
+    # MST_OVERLAP_ALLREDUCE=0 restores the serial step with one blocking all-reduce of the whole arena.
     def _early_t2m_backward(self, loss_t2m):
         flat = self.mp_trainer.flat
-        self.mp_trainer.backward(loss_t2m)
         if self.__dict__.get("_g_t2m") is None:
-            self._g_t2m = torch.empty_like(flat.grads)
-        self._g_t2m.copy_(flat.grads)
-        flat.grads.zero_()
+            self._g_t2m = torch.zeros_like(flat.grads)
+            views, off = [], 0
+            for p in flat.trainable:
+                n = p.numel()
+                views.append(self._g_t2m[off:off + n].view(p.shape))
+                off += n
+            self._g_t2m_views = views
+        self._g_t2m.zero_()
+        self.mp_trainer.backward_into(loss_t2m, self._g_t2m_views)
         ev = self.__dict__.get("_ov_events")
         if ev is None:
             ev = self._ov_events = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record()                                   # all-reduce handed to NCCL here
-        self._t2m_work = dist.all_reduce(self._g_t2m, op=dist.ReduceOp.SUM, async_op=True)
+        ev[0].record()                                   # (this stream) gradient complete, all-reduce handed to NCCL here
+        self._t2m_work = (dist.all_reduce(self._g_t2m, op=dist.ReduceOp.SUM, async_op=True) if self.use_ddp else None)
+        self._t2m_pending = True
 
     def sync_gradients(self):
-        work = self.__dict__.pop("_t2m_work", None)
-        if work is not None:
+        if self.__dict__.pop("_t2m_pending", False):
+            work = self.__dict__.pop("_t2m_work", None)
             ev = self._ov_events
+            main = torch.cuda.current_stream()
             ev[1].record()                               # the style term's gradient is complete
-            work.wait()                                  # the compute stream waits for NCCL's stream (a no-op if it is done)
+            if work is not None:
+                work.wait()                              # this stream waits for NCCL's stream (a no-op if it is done)
+            main.wait_stream(self.diffusion.t2m_stream)
             ev[2].record()
             self.mp_trainer.flat.grads.add_(self._g_t2m, alpha=1.0 / self.world)
             self.opt.grad_scale = 1.0                    # the arena already holds the mean gradient
+            extra = self.last_losses.pop("loss_t2m", None)
+            if extra is not None:                        # the logged loss is the whole objective again
+                self.last_losses["loss"] = self.last_losses["loss"] + extra
             self._overlapped = True
             return
         self.opt.grad_scale = 1.0 / self.world
@@ -283,8 +298,10 @@ class TrainInpaintingLoop:
                                       "the reference's generic training_losses path is outside the scope table")
         if self.use_ddp:
             batch, cond, _ = shard_batch(batch, cond, self.rank, self.world)
-        overlap = self.use_ddp and self.semantic_guidance and os.environ.get("MST_OVERLAP_ALLREDUCE", "1") != "0"
+        overlap = bool(self.semantic_guidance) and os.environ.get("MST_OVERLAP_ALLREDUCE", "1") != "0"
         self.diffusion.early_t2m_backward = self._early_t2m_backward if overlap else None
+        if overlap and getattr(self.diffusion, "t2m_stream", None) is None:
+            self.diffusion.t2m_stream = torch.cuda.Stream(device=self.device)
         args = self.args
         if getattr(args, "use_ddim", 0):
             rng = range(int((args.diffusion_steps - args.skip_steps) / args.diffusion_steps * 20))
