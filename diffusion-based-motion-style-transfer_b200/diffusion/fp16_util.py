@@ -94,6 +94,7 @@ class MixedPrecisionTrainer:
         self._denoisers = [m for m in model.modules() if hasattr(m, "mst_tape_pool")]
         for m in self._denoisers:
             m.mst_tape_pool = True
+            m.__dict__["mst_direct_grads"] = True  # every trainable parameter keeps an arena view as .grad (ensure_grad_views)
 
     def master_params_to_state_dict(self, master_params=None):
         """reference :225-228: the model's state_dict (the parameters ARE the master params in fp32 mode)"""

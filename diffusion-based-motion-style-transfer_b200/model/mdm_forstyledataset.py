@@ -166,7 +166,7 @@ class _DenoiserGradFn(torch.autograd.Function):
     def forward(ctx, native, x, temb, text_emb, uncond, *params):
         eng = native.__dict__.pop("_mst_eng_hint", None) or native.mst_engine(x.device, precision=native.mst_train_prec())
         B = x.shape[0]
-        slot, k = native._mst_tape_acquire(eng, B, x.shape[-1], text_emb is not None)
+        slot, k = native.__dict__.pop("_mst_slot_hint", None) or native._mst_tape_acquire(eng, B, x.shape[-1], text_emb is not None)
         ctx.native, ctx.eng, ctx.slot, ctx.k = native, eng, slot, k
         p = ctx.drop_p = native.mst_dropout_p()
         key = native.mst_draw_dropout_key() if p > 0 else 0
@@ -242,6 +242,60 @@ class _DenoiserGradFn(torch.autograd.Function):
                                dropout_p=ctx.drop_p, dropout_seed=ctx.drop_seed)
         ctx.tape = None
         return (None, d_x, None, None, None) + tuple(g for lg in grads for g in lg.values())
+
+
+class _DenoiserPooledFn(torch.autograd.Function):
+    """The trainer's fast lane of ``_DenoiserGradFn``: pooled tape, gradients accumulated straight into the parameters'
+    arena ``.grad`` buffers, no gradient w.r.t. x.  The ~100 encoder parameters are NOT autograd inputs here (one anchor
+    parameter keeps the node alive): with them, every apply() and every backward spends ~0.1 ms of host time wrapping,
+    unwrapping and validating tensors whose gradients are written by the kernels anyway."""
+
+    @staticmethod
+    def forward(ctx, native, x, temb, text_emb, uncond, anchor, where):
+        eng, slot, k = where
+        B = x.shape[0]
+        ctx.native, ctx.slot, ctx.k = native, slot, k
+        p = ctx.drop_p = native.mst_dropout_p()
+        key = native.mst_draw_dropout_key() if p > 0 else 0
+        r = slot.rows(k)
+        slot.x[r].copy_(x)
+        slot.temb[r].copy_(temb)
+        if text_emb is not None:
+            slot.text[r].copy_(text_emb)
+        if p > 0:
+            slot.seed[r].copy_(torch.arange(key, key + B, dtype=torch.int64), non_blocking=True)
+        eng.forward_train(slot.x[r], slot.temb[r], slot.text[r] if text_emb is not None else None, uncond=uncond,
+                          tape=slot.tape, out=slot.out[r], use_graph=True, dropout_p=p, dropout_seed=slot.seed[r],
+                          tape_seqs=slot.tape_seqs, tape_seq_offset=k * B)
+        ctx.epoch, ctx.live = slot.epoch, True
+        return slot.out[r].clone()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        if not ctx.live:
+            raise RuntimeError("the mst activation tape of this forward was already consumed by a backward pass "
+                               "(retain_graph is not supported: run the forward again)")
+        slot = ctx.slot
+        if slot.epoch != ctx.epoch:
+            raise RuntimeError("this forward's pooled activation tape was recycled by a later training step "
+                               "(call backward() before the next zero_grad(), or disable the pool)")
+        layers = ctx.native._mst_cached_tensors()[1]
+        cache = slot.__dict__.get("_bw_cache")
+        probe = layers[0]["qkv_w"].grad  # the trainer may point .grad at a second arena for this backward
+        arena = None if probe is None else probe.data_ptr()
+        if cache is not None and cache[0] == slot.epoch and cache[1] is layers and cache[2] == "pooled" and cache[6] == arena:
+            grads = cache[4]
+        else:
+            for lp in layers:
+                for p in lp.values():
+                    if p.requires_grad and (p.grad is None or not p.grad.is_contiguous() or p.grad.dtype != torch.float32):
+                        raise RuntimeError("mst_direct_grads promises an fp32 .grad buffer on every trainable encoder "
+                                           "parameter (MixedPrecisionTrainer keeps them in its arena)")
+            grads = [{k_: (p.grad if p.requires_grad else None) for k_, p in lp.items()} for lp in layers]
+            slot._bw_cache = (slot.epoch, layers, "pooled", True, grads, 0, arena)
+        slot.stage_backward(ctx.k, d_out, ctx.drop_p, grads)
+        ctx.live = False
+        return (None,) * 7
 
 
 class _MencSlot:
@@ -607,8 +661,15 @@ class NativeDenoiser(nn.Module):
                 text_emb = None if force_mask else self.text_embedding(y, x.device, eng=eng)
             if 'text' in self.cond_mode and text_emb is None and not force_mask:
                 raise RuntimeError("text-conditioned model called without text")
+            uncond = force_mask or text_emb is None
+            if self.mst_tape_pool and self.__dict__.get("mst_direct_grads") and not xc.requires_grad:
+                where = self._mst_tape_acquire(eng, xc.shape[0], xc.shape[-1], text_emb is not None)
+                anchor = next((p for p in enc_params if p.requires_grad), None)
+                if where[0] is not None and anchor is not None:
+                    return _DenoiserPooledFn.apply(self, xc, temb, text_emb, uncond, anchor, (eng,) + tuple(where))
+                self.__dict__["_mst_slot_hint"] = where
             self.__dict__["_mst_eng_hint"] = eng  # the bridge below would otherwise fingerprint the weights a third time
-            return _DenoiserGradFn.apply(self, xc, temb, text_emb, force_mask or text_emb is None, *enc_params)
+            return _DenoiserGradFn.apply(self, xc, temb, text_emb, uncond, *enc_params)
         eng = self.mst_engine(x.device)
         temb = eng.time_embed(timesteps)
         text_emb = None if force_mask else self.text_embedding(y, x.device)
