@@ -232,7 +232,8 @@ static int gemm_ex(GemmEx p, cudaStream_t s, const char* name) {
       return fail(MST_ERR_INVALID, "gemm_ex: split-k overwrite needs a dense single output");
     MST_CUDA_OK(cudaMemsetAsync(p.c, 0, (size_t)p.M * p.N * sizeof(float), s));
   }
-  if (tiles128 >= 120) {
+  static const long long t128 = getenv("MST_GEMM_EX_T128") ? atoll(getenv("MST_GEMM_EX_T128")) : 400;
+  if (tiles128 >= t128) {
     dim3 grid(ceil_div(p.N, 128), ceil_div(p.M, 128), (unsigned)(z * p.split_k));
     MST_CUDA_OK(launch_pdl(gemm_ex_kernel<8>, grid, dim3(256), 0, s, p));
   } else {
