@@ -1,6 +1,7 @@
 // Declarations of the tcgen05 / TMEM / TMA kernels (tc_gemm.cu, tc_attn.cu).
 #pragma once
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace mst {
 
@@ -35,6 +36,13 @@ struct TcGemmParams {
   float* out2 = nullptr;  // OUTPROJ: rows of sequences >= B go here (uncond pass)
   const float* add = nullptr;  // TRAIN_F32: fp32 tensor with out's layout added to the result (residual paths)
   int accumulate = 0;          // TRAIN_F32: out += result (gradient accumulation)
+  // TRAIN_F32, linear1 of the taped forward: besides out = u, also h = dropout(gelu(u)) as fp32 (tape) and bf16 (operand
+  // of linear2) - the separate GELU launch of every layer goes away.  Rows are grouped rows_per_seq per sequence.
+  float* gelu_out = nullptr;
+  __nv_bfloat16* gelu_bf = nullptr;
+  Drop drop;
+  uint32_t drop_site = 0;
+  int rows_per_seq = 1;
   // 16-bit format switches of the sampler's residual stream (see tc_gemm_ln5_kernel): IEEE fp16 instead of bf16
   int ab_f16 = 0;  // A and W hold fp16 (QKV, FFN1 and the final projection read the fp16 stream)
   int io_f16 = 0;  // RES_LN: residual and output are fp16;  INPROJ: output is fp16

@@ -140,6 +140,8 @@ __device__ __forceinline__ uint64_t gelu2(uint64_t x) {
   return mul2(x, fma2(z, q, pk2(0.5f, 0.5f)));
 }
 
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
 // ---- direct (row-per-thread) epilogue of one 32-column chunk: the small fp32 / row-remapping cases ----
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, int n, const uint32_t (&v)[32]) {
@@ -164,6 +166,21 @@ __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, i
         r.x += o4.x; r.y += o4.y; r.z += o4.z; r.w += o4.w;
       }
       *reinterpret_cast<float4*>(dst + j) = r;
+      if (p.gelu_out) {  // h = dropout(gelu(u)): the same erf GELU and the same mask counters as gelu_drop_fwd_kernel
+        float4 h = make_float4(gelu_erf_f(r.x), gelu_erf_f(r.y), gelu_erf_f(r.z), gelu_erf_f(r.w));
+        if (p.drop.on()) {
+          const int seq = row / p.rows_per_seq;
+          const long long local4 = (long long)(row - seq * p.rows_per_seq) * (p.ldo >> 2) + ((n + j) >> 2);
+          const float4 m = drop_scale4(p.drop, p.drop_site, seq, local4);
+          h.x *= m.x; h.y *= m.y; h.z *= m.z; h.w *= m.w;
+        }
+        *reinterpret_cast<float4*>(p.gelu_out + (size_t)row * p.ldo + n + j) = h;
+        if (p.gelu_bf) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
+          *reinterpret_cast<uint2*>(p.gelu_bf + (size_t)row * p.ldo + n + j) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+      }
     }
     return;
   }

@@ -17,6 +17,7 @@
 #include "simt.cuh"
 #include "tc.cuh"
 #include "smem_gemm.cuh"
+#include "dropout.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -320,46 +321,6 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__
     dh[i] = g;
     if (dh_bf) dh_bf[i] = __float2bfloat16_rn(g);
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Dropout of the training forward (nn.TransformerEncoderLayer(dropout=0.1) and PositionalEncoding(dropout=0.1) are
-// active once the reference calls model.train(), train/finetune_style_diffusion.py:256).  Counter-based: the keep /
-// drop decision of element i at site s is Philox4x32-10(key = *seed_dev, counter = (i / 4, site, 0, 0)) lane i % 4
-// < p, so the backward recomputes the mask instead of storing it, and a CUDA-graph replay picks up a new seed from
-// device memory.  Sites: 0 = token sequence after the positional encoding; 8 * (layer + 1) + {1: attention
-// probabilities, 2: out-proj output, 3: GELU output, 4: linear2 output}.
-// ---------------------------------------------------------------------------------------------------------
-struct Drop {
-  float p = 0.0f;                      // 0 = off
-  const unsigned long long* seed = nullptr;  // device: one key per sequence of the call (the masks of a sequence do not
-                                             // depend on which other sequences share the launch, so forwards recorded one
-                                             // by one can be back-propagated as one batch)
-  int n_seqs = 1;
-  __host__ __device__ bool on() const { return p > 0.0f; }
-};
-
-__device__ __forceinline__ void philox4(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t (&o)[4]) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-  uint32_t x = c0, y = c1, z = 0u, w = 0u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, x), lo0 = M0 * x, hi1 = __umulhi(M1, z), lo1 = M1 * z;
-    const uint32_t nx = hi1 ^ y ^ k0, nz = hi0 ^ w ^ k1;
-    x = nx; y = lo1; z = nz; w = lo0;
-    k0 += W0; k1 += W1;
-  }
-  o[0] = x; o[1] = y; o[2] = z; o[3] = w;
-}
-
-// scale factors (0 or 1/(1-p)) of elements [4v, 4v+3] of `site` of sequence `seq` (v counts inside the sequence)
-__device__ __forceinline__ float4 drop_scale4(const Drop& d, uint32_t site, int seq, long long v) {
-  const unsigned long long seed = d.seed[seq];
-  uint32_t r[4];
-  philox4((uint32_t)v, site ^ ((uint32_t)(v >> 32) << 16), (uint32_t)seed, (uint32_t)(seed >> 32), r);
-  const float keep = 1.0f / (1.0f - d.p);
-  const uint32_t thr = (uint32_t)(d.p * 4294967296.0);  // drop when r < thr
-  return make_float4(r[0] < thr ? 0.0f : keep, r[1] < thr ? 0.0f : keep, r[2] < thr ? 0.0f : keep, r[3] < thr ? 0.0f : keep);
 }
 
 // out[i] = in[i] * mask[i] (+ add[i]); n % 4 == 0, all pointers 16-byte aligned; in may alias out
@@ -805,8 +766,19 @@ static void carve_stage(const mst_model_desc& d, int M, void* base, Stage* st) {
 }
 
 // a_staged: the producer of x already left its bf16 copy in st.a (fused conversions of the forward chain)
+// Fused GELU of linear1 (tensor-core mode): h = dropout(gelu(out)) as fp32 (tape) and bf16 (operand of linear2)
+struct GeluOut {
+  float* h = nullptr;
+  __nv_bfloat16* h_bf = nullptr;
+  Drop drop;
+  uint32_t site = 0;
+  int rows_per_seq = 1;
+};
+
+// a_bf: the bf16 A operand when it is staged somewhere else than st.a
 static int linear_fwd(bool tc, const Stage& st, const float* x, const Lin& L, const float* bias, const float* add, float* out,
-                      int M, cudaStream_t s, const char* name, bool a_staged = false) {
+                      int M, cudaStream_t s, const char* name, bool a_staged = false, const GeluOut* gelu = nullptr,
+                      const __nv_bfloat16* a_bf = nullptr) {
   if (!tc) {
     GemmEx g;
     g.a = x; g.lda = L.n_in; g.b = L.w; g.ldb = L.n_in; g.trans_b = 1; g.bias = bias; g.add = add; g.c = out; g.ldc = L.n_out;
@@ -816,8 +788,11 @@ static int linear_fwd(bool tc, const Stage& st, const float* x, const Lin& L, co
   int rc;
   if (!a_staged && (rc = cvt_bf16(x, M, L.n_in, L.n_in, st.a, nullptr, 0, s))) return rc;
   TcGemmParams p;
-  p.a = st.a; p.w = L.w_bf; p.bias = bias; p.add = add; p.out = out; p.ldo = L.n_out; p.M = M; p.N = L.n_out; p.K = L.n_in;
+  p.a = a_bf ? a_bf : st.a; p.w = L.w_bf; p.bias = bias; p.add = add; p.out = out; p.ldo = L.n_out; p.M = M; p.N = L.n_out; p.K = L.n_in;
   p.epi = TC_EPI_TRAIN_F32;
+  if (gelu) {
+    p.gelu_out = gelu->h; p.gelu_bf = gelu->h_bf; p.drop = gelu->drop; p.drop_site = gelu->site; p.rows_per_seq = gelu->rows_per_seq;
+  }
   return tc_gemm(p, s);
 }
 
@@ -1171,6 +1146,18 @@ static bool attn_mma(bool tc) {
   return tc && on;
 }
 
+// MST_TRAIN_GELU_EPI=1: the GELU (+ dropout) of the taped forward inside linear1's epilogue instead of its own kernel.
+// One node less per layer, but measured SLOWER (10.14 vs 9.82 ms and 4.22 vs 4.13 ms per finetune step with / without
+// semantic guidance on the same box): the row-per-thread fp32 epilogue then runs 64 erff + a Philox call per thread and
+// tile on the critical chain of every layer.  Off by default, kept for the record.
+static bool gelu_in_epilogue() {
+  static const bool on = [] {
+    const char* e = getenv("MST_TRAIN_GELU_EPI");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
 static bool attn_small_ok(const mst_model_desc& d, int S) {
   return S <= SA_MAXS && d.d_model / d.n_heads == SA_DH;
 }
@@ -1303,13 +1290,23 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
                              drop.on() ? (const float*)t.x : (const float*)nullptr, drop.on() ? t.z1 : (float*)nullptr, L.ln1_g,
                              L.ln1_b, t.y, bf, M, dm, S, drop, drop_site(l, 2)));
       MST_LAUNCHED("train_add_drop_ln", s);
-      if ((rc = linear_fwd(tc, tp.stage, t.y, lf1, L.b1, nullptr, t.u, M, s, "train_ffn1", tc))) return rc;
       // h = dropout(gelu(u)); z2 = y + dropout2(h W2^T + b2); x' = LN2(z2)
-      const long long n4 = (long long)M * ff / 4;
-      MST_CUDA_OK(launch_pdl(gelu_drop_fwd_kernel, dim3(ew_blocks(n4)), dim3(256), 0, s, (const float*)t.u, t.h, bf, n4,
-                             (long long)S * ff / 4, drop, drop_site(l, 3)));
-      MST_LAUNCHED("train_gelu_drop", s);
-      if ((rc = linear_fwd(tc, tp.stage, t.h, lf2, L.b2, drop.on() ? nullptr : t.y, t.z2, M, s, "train_ffn2", tc))) return rc;
+      const __nv_bfloat16* h_bf = nullptr;
+      if (tc && gelu_in_epilogue()) {
+        // the GELU rides in linear1's epilogue; its bf16 copy goes to the (forward-idle) transpose staging, because the
+        // GEMM is still reading its own A operand from stage.a
+        GeluOut go;
+        go.h = t.h; go.h_bf = tp.stage.at; go.drop = drop; go.site = drop_site(l, 3); go.rows_per_seq = S;
+        if ((rc = linear_fwd(tc, tp.stage, t.y, lf1, L.b1, nullptr, t.u, M, s, "train_ffn1", tc, &go))) return rc;
+        h_bf = tp.stage.at;
+      } else {
+        if ((rc = linear_fwd(tc, tp.stage, t.y, lf1, L.b1, nullptr, t.u, M, s, "train_ffn1", tc))) return rc;
+        const long long n4 = (long long)M * ff / 4;
+        MST_CUDA_OK(launch_pdl(gelu_drop_fwd_kernel, dim3(ew_blocks(n4)), dim3(256), 0, s, (const float*)t.u, t.h, bf, n4,
+                               (long long)S * ff / 4, drop, drop_site(l, 3)));
+        MST_LAUNCHED("train_gelu_drop", s);
+      }
+      if ((rc = linear_fwd(tc, tp.stage, t.h, lf2, L.b2, drop.on() ? nullptr : t.y, t.z2, M, s, "train_ffn2", tc, nullptr, h_bf))) return rc;
       MST_CUDA_OK(launch_pdl(add_drop_ln_kernel, dim3(ln_grid), dim3(256), 0, s, (const float*)t.z2,
                              drop.on() ? (const float*)t.y : (const float*)nullptr, drop.on() ? t.z2 : (float*)nullptr, L.ln2_g,
                              L.ln2_b, x_next, l + 1 < d.n_layers ? bf : (__nv_bfloat16*)nullptr, M, dm, S, drop,

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Opcode histogram per kernel of the built library (cuobjdump -sass): the Blackwell-native instructions
 (UTC*MMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA, UTCBAR = tcgen05.commit,
-SYNCS = mbarrier) next to the legacy ones that must stay at zero (HMMA = mma.sync / wmma).
+SYNCS = mbarrier) next to the legacy ones (HMMA = mma.sync / wmma): zero in every sampler kernel; the only HMMA in the
+library are the tf32 m16n8k8 products of the short-sequence TRAINING attention (attn_small_*<..., true>: 80 x 80 x 128
+products held in shared memory by one CTA per (sequence, head); DESIGN.md section 4, round-2 finetune table).
     python tools/sass_histogram.py > profiles/rNN_sass_opcode_histogram.txt"""
 import collections
 import os
@@ -40,3 +42,5 @@ for k, c in hist.items():
 print(f"{'ALL listed kernels':58s} {tot['_total']:6d} " + " ".join(f"{tot[w]:9d}" for w in WATCH))
 print(f"legacy tensor-core opcodes in the whole library: HMMA {sum(c['HMMA'] for c in hist.values())}, "
       f"HGMMA {sum(c['HGMMA'] for c in hist.values())}")
+print("kernels with HMMA (mma.sync): " + (", ".join(k for k, c in hist.items() if c["HMMA"]) or "none") +
+      "  [training attention of the finetune step only; no sampler kernel]")
