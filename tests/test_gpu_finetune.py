@@ -295,6 +295,59 @@ def test_training_loop_runs_and_reduces_the_loss(mu, FI, tmp_path_factory):
     assert loop.step == 4 and loop.opt.step_count == 4
 
 
+def test_side_stream_step_equals_the_serial_step(mu, FI, tmp_path_factory, monkeypatch):
+    """The trainer runs the text-to-motion branch on its own stream and back-propagates it into a second gradient arena
+    (training_loop.py::_early_t2m_backward); MST_OVERLAP_ALLREDUCE=0 is the serial step.  Same seeds, dropout off:
+    the parameters after three steps and the logged losses agree to fp32 rounding, and the concurrent mode really used
+    the side arena."""
+    from mst_b200.data_loaders.stylexia_posrot_utils import get_inpainting_mask
+    from mst_b200.train.training_loop import TrainInpaintingLoop
+    inp = FI.make_inputs()
+    F, T = 181, inp["content"].shape[-1]
+
+    class A(Args):
+        batch_size, lr, weight_decay, lr_anneal_steps, style_finetune, semantic_guidance = 3, 1e-4, 0.0, 0, 1, 1
+        skip_steps, use_ddim, Ls, num_steps = 700, 1, 10, 4
+
+    mask_style = torch.from_numpy(get_inpainting_mask("root_horizontal", (1, F, 1, T))).float().to(DEV)
+    mask_t2m = torch.from_numpy(get_inpainting_mask("root_horizontal", tuple(inp["x_start"].shape))).float().to(DEV)
+    style_cond = {"y": {"text": inp["texts_style"], "text_feat": text_features(inp["texts_style"]).to(DEV),
+                        "mask": torch.ones(1, 1, 1, T, dtype=torch.bool, device=DEV), "lengths": torch.tensor([T]),
+                        "inpainted_motion": inp["style"].to(DEV), "inpainting_mask": mask_style}}
+    cond = {"y": {"text": inp["texts_t2m"], "text_feat": text_features(inp["texts_t2m"]).to(DEV),
+                  "mask": inp["frame_mask_t2m"][:, None, None, :].to(DEV), "lengths": torch.tensor(inp["lengths"]),
+                  "inpainting_mask": mask_t2m}}
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MST_OVERLAP_ALLREDUCE", mode)
+        model, *_ = _style_model(mu, FI, tmp_path_factory)
+        for m in model.modules():
+            if hasattr(m, "mst_train_dropout"):
+                m.mst_train_dropout = 0.0
+        diffusion = mu.create_gaussian_diffusion(A(), mu.InpaintingGaussianDiffusion, timestep_respacing="ddim20")
+        loop = TrainInpaintingLoop(A(), None, model, [(inp["x_start"], cond)], diffusion=diffusion,
+                                   style_data=((inp["content"].to(DEV), style_cond),))
+        np.random.seed(0)
+        torch.manual_seed(0)
+        torch.cuda.manual_seed(0)
+        losses = []
+        for _ in range(3):
+            loop.run_step(inp["x_start"].to(DEV), cond, inp["content"].to(DEV), style_cond)
+            losses.append(float(loop.last_losses["loss"]))
+        torch.cuda.synchronize()
+        res[mode] = (loop.mp_trainer.flat.train_params.clone(), losses, loop.__dict__.get("_g_t2m"),
+                     loop.mp_trainer.last_norms)
+    a, b = res["1"][0], res["0"][0]
+    # Adam moves an element by ~lr * g / |g|: where the gradient is rounding noise (|g| ~ 1e-9) the two summation orders
+    # may step in different directions; everywhere else the parameters agree to fp32 rounding
+    diff = (a - b).abs()
+    print("side-stream vs serial: max |dp| %.3e, fraction above 2e-6: %.3e" % (float(diff.max()), float((diff > 2e-6).float().mean())))
+    assert float(diff.max()) < 1e-4 and float((diff > 2e-6).float().mean()) < 1e-4
+    assert np.allclose(res["1"][1], res["0"][1], rtol=1e-5)
+    assert np.allclose(res["1"][3], res["0"][3], rtol=1e-4)
+    assert res["0"][2] is None and res["1"][2] is not None and float(res["1"][2].abs().sum()) > 0
+
+
 def test_run_loop_checkpoints_in_the_reference_format_and_resumes(mu, FI, tmp_path_factory):
     """run_loop (reference train/training_loop.py:143-190, :309-348): num_steps // len(data) + 1 epochs, CPU-side
     kwargs moved to the device, modelNNNNNNNNN.pt without the frozen motion_enc. / clip_model. entries, optNNNNNNNNN.pt
