@@ -36,6 +36,9 @@ struct TcGemmParams {
   float* out2 = nullptr;  // OUTPROJ: rows of sequences >= B go here (uncond pass)
   const float* add = nullptr;  // TRAIN_F32: fp32 tensor with out's layout added to the result (residual paths)
   int accumulate = 0;          // TRAIN_F32: out += result (gradient accumulation)
+  // TRAIN_F32 as the in-projection of the taped forward: GEMM row (b, t), t < tok_T, lands in output row
+  // b * (tok_T + tok_off) + t + tok_off (+ pe[t + tok_off] when pe is given); tok_T == 0: rows map one to one
+  int tok_T = 0, tok_off = 0;
   // TRAIN_F32, linear1 of the taped forward: besides out = u, also h = dropout(gelu(u)) as fp32 (tape) and bf16 (operand
   // of linear2) - the separate GELU launch of every layer goes away.  Rows are grouped rows_per_seq per sequence.
   float* gelu_out = nullptr;

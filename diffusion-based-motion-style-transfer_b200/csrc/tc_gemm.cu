@@ -148,14 +148,25 @@ __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, i
   if (row >= p.M) return;
   float x[32];
   if constexpr (EPI == TC_EPI_TRAIN_F32) {
-    float* dst = static_cast<float*>(p.out) + (size_t)row * p.ldo + n;
-    const float* addp = p.add ? p.add + (size_t)row * p.ldo + n : nullptr;
+    int orow = row;
+    const float* pe_row = nullptr;
+    if (p.tok_T > 0) {  // in-projection of the taped forward: (b, t) -> token row (b, t + tok_off)
+      const int b = row / p.tok_T, t = row - b * p.tok_T;
+      orow = b * (p.tok_T + p.tok_off) + t + p.tok_off;
+      if (p.pe) pe_row = p.pe + (size_t)(t + p.tok_off) * p.N + n;
+    }
+    float* dst = static_cast<float*>(p.out) + (size_t)orow * p.ldo + n;
+    const float* addp = p.add ? p.add + (size_t)orow * p.ldo + n : nullptr;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
       if (p.bias) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
         r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
+      }
+      if (pe_row) {
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(pe_row + j));
+        r.x += e4.x; r.y += e4.y; r.z += e4.z; r.w += e4.w;
       }
       if (addp) {
         const float4 a4 = __ldg(reinterpret_cast<const float4*>(addp + j));

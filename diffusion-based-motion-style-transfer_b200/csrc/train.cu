@@ -1162,6 +1162,30 @@ static bool attn_small_ok(const mst_model_desc& d, int S) {
   return S <= SA_MAXS && d.d_model / d.n_heads == SA_DH;
 }
 
+// The in-/out-projections of the B=64 batch on the fp32 SIMT GEMM cost 110-250 us each (K or N = 181 keeps them off the TMA
+// path): in the 16-bit mode the motion goes through motion_to_tokens_bf16 (the sampler's [B*T, f_pad] operand) and the
+// tcgen05 training GEMM instead.  MST_TRAIN_PROJ_TC=0 keeps the fp32 kernels.
+static bool proj_on_tc(const Engine* e, int B, int T) {
+  static const bool on = [] {
+    const char* v = getenv("MST_TRAIN_PROJ_TC");
+    return !(v && v[0] == '0');
+  }();
+  return on && e->desc.precision == MST_PREC_BF16 && e->in_w_bf && e->out_w_bf && (long long)B * T >= 512;
+}
+
+// tokens[(b, t + tok_off)] = x[b,:,t] in_w^T + in_b (+ pe[t + tok_off]) into out [B * (T + tok_off), d]; scratch_bf: B*T*f_pad bf16
+static int inproj_tc(Engine* e, const float* x, int B, int T, int tok_off, const float* pe, float* out,
+                     __nv_bfloat16* scratch_bf, cudaStream_t s) {
+  const mst_model_desc& d = e->desc;
+  int rc;
+  if ((rc = motion_to_tokens_bf16(x, scratch_bf, B, d.n_feats, T, e->f_pad, nullptr, 0, s))) return rc;
+  TcGemmParams p;
+  p.a = scratch_bf; p.w = e->in_w_bf; p.bias = e->in_b; p.out = out; p.ldo = d.d_model;
+  p.M = B * T; p.N = d.d_model; p.K = e->f_pad; p.epi = TC_EPI_TRAIN_F32;
+  p.tok_T = T; p.tok_off = tok_off; p.pe = pe;
+  return tc_gemm(p, s);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // tape: everything the backward needs, per layer
 // ---------------------------------------------------------------------------------------------------------
@@ -1225,8 +1249,9 @@ static Tape tape_view(const Tape& full, const mst_model_desc& d, int S, int k) {
   return v;
 }
 
+// stage_last: leave the bf16 copy of the stack's output in stage.a as well (operand of the tensor-core out-projection)
 static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const uint8_t* key_valid, const Drop& drop,
-                                cudaStream_t s) {
+                                cudaStream_t s, bool stage_last = false) {
   const mst_model_desc& d = e->desc;
   const int M = NS * S, dm = d.d_model, H = d.n_heads, dh = dm / H, ff = d.d_ff;
   const float scale = 1.0f / sqrtf((float)dh);
@@ -1309,7 +1334,7 @@ static int encoder_forward_tape(Engine* e, const Tape& tp, int NS, int S, const 
       if ((rc = linear_fwd(tc, tp.stage, t.h, lf2, L.b2, drop.on() ? nullptr : t.y, t.z2, M, s, "train_ffn2", tc, nullptr, h_bf))) return rc;
       MST_CUDA_OK(launch_pdl(add_drop_ln_kernel, dim3(ln_grid), dim3(256), 0, s, (const float*)t.z2,
                              drop.on() ? (const float*)t.y : (const float*)nullptr, drop.on() ? t.z2 : (float*)nullptr, L.ln2_g,
-                             L.ln2_b, x_next, l + 1 < d.n_layers ? bf : (__nv_bfloat16*)nullptr, M, dm, S, drop,
+                             L.ln2_b, x_next, (l + 1 < d.n_layers || stage_last) ? bf : (__nv_bfloat16*)nullptr, M, dm, S, drop,
                              drop_site(l, 4)));
       MST_LAUNCHED("train_add_drop_ln", s);
       continue;
@@ -1721,7 +1746,10 @@ extern "C" int mst_denoiser_forward_train(mst_engine_t h, const mst_forward_args
     t0.text_emb = a.text_emb; t0.txt_b = e->txt_b; t0.pe = e->pe; t0.x_f32 = tp.l[0].x;
     t0.B = B; t0.T = T; t0.d = dm; t0.cfg = 0; t0.uncond = a.uncond;
     if ((rc = token0(t0, B, s))) return rc;
-    {
+    const bool ptc = proj_on_tc(e, B, T);
+    if (ptc) {
+      if ((rc = inproj_tc(e, a.x, B, T, 1, e->pe, tp.l[0].x, tp.stage.at, s))) return rc;
+    } else {
       GemmF32Params p;
       p.a = a.x; p.a_mode = A_MOTION; p.w = e->in_w; p.ldw = d.n_feats; p.bias = e->in_b;
       p.c = tp.l[0].x; p.ldc = dm; p.M = B * T; p.N = dm; p.K = d.n_feats; p.epi = EPI_INPROJ;
@@ -1729,8 +1757,13 @@ extern "C" int mst_denoiser_forward_train(mst_engine_t h, const mst_forward_args
       if ((rc = gemm_f32(p, s))) return rc;
     }
     if (drop.on() && (rc = dropout(tp.l[0].x, nullptr, tp.l[0].x, (long long)B * S * dm, drop, 0, s))) return rc;
-    if ((rc = encoder_forward_tape(e, tp, B, S, nullptr, drop, s))) return rc;
-    {
+    if ((rc = encoder_forward_tape(e, tp, B, S, nullptr, drop, s, ptc))) return rc;
+    if (ptc) {  // the sampler's out-projection: bf16 tokens (staged by the last LayerNorm kernel) -> fp32 [B, F, T]
+      TcGemmParams p;
+      p.a = tp.stage.a; p.w = e->out_w_bf; p.bias = e->out_b_pad; p.out = a.out_cond;
+      p.M = B * S; p.N = e->f_pad; p.K = dm; p.epi = TC_EPI_OUTPROJ_F32; p.B = B; p.T = T; p.n_valid = d.n_feats;
+      if ((rc = tc_gemm(p, s))) return rc;
+    } else {
       GemmF32Params p;
       p.a = tp.x_out; p.lda = dm; p.w = e->out_w; p.ldw = dm; p.bias = e->out_b;
       p.c = a.out_cond; p.M = B * S; p.N = d.n_feats; p.K = dm; p.epi = EPI_OUTPROJ; p.T = T; p.B = B;
@@ -1824,10 +1857,14 @@ extern "C" int mst_motion_encoder_forward(mst_engine_t h, const float* x, const 
   key = fnv1a(e, sizeof(Engine), key) ^ 0x3eull;
   return run_graphed(use_graph != 0, key, (cudaStream_t)stream, [&](cudaStream_t s) -> int {
     int rc;
-    GemmEx g;  // tokens[(b, t+2)] = x[b,:,t] in_w^T + in_b
-    g.a = x; g.a_mode = AX_MOTION_TOK; g.T = T; g.tok_off = 2; g.b = e->in_w; g.ldb = d.n_feats; g.trans_b = 1;
-    g.bias = e->in_b; g.c = tp.l[0].x; g.ldc = dm; g.M = B * S; g.N = dm; g.K = d.n_feats;
-    if ((rc = gemm_ex(g, s, "menc_inproj"))) return rc;
+    if (proj_on_tc(e, B, T)) {
+      if ((rc = inproj_tc(e, x, B, T, 2, nullptr, tp.l[0].x, tp.stage.at, s))) return rc;
+    } else {
+      GemmEx g;  // tokens[(b, t+2)] = x[b,:,t] in_w^T + in_b
+      g.a = x; g.a_mode = AX_MOTION_TOK; g.T = T; g.tok_off = 2; g.b = e->in_w; g.ldb = d.n_feats; g.trans_b = 1;
+      g.bias = e->in_b; g.c = tp.l[0].x; g.ldc = dm; g.M = B * S; g.N = dm; g.K = d.n_feats;
+      if ((rc = gemm_ex(g, s, "menc_inproj"))) return rc;
+    }
     MST_CUDA_OK(launch_pdl(menc_tokens_kernel, dim3(B * S), dim3(128), 0, s, mu_query, sigma_query, e->pe, tp.l[0].x, S, dm));
     MST_LAUNCHED("menc_tokens", s);
     if (drop.on() && (rc = dropout(tp.l[0].x, nullptr, tp.l[0].x, (long long)B * S * dm, drop, 0, s))) return rc;
