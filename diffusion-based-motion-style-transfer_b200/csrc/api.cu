@@ -153,6 +153,9 @@ static size_t packed_bytes(const mst_model_desc& d, int f_pad) {
     c.take<__half>((size_t)3 * d.d_model * d.d_model);
     c.take<__half>((size_t)d.d_ff * d.d_model);
   }
+  c.take<__nv_bfloat16>((size_t)f_pad * d.d_model);  // in_w^T, out_w^T: backward of the in-/out-projection (training)
+  c.take<__nv_bfloat16>((size_t)d.d_model * f_pad);
+  c.take<float>(f_pad);                               // zeros
   return align_up(c.off, 1024);
 }
 
@@ -339,7 +342,22 @@ extern "C" int mst_engine_load_weights(mst_engine_t h, const mst_weights* w, voi
     for (int l = 0; l < d.n_layers; ++l) {
       const mst_layer_weights& L = w->layers[l];
       if (js.n + 4 > CVT_MAX_JOBS) {
+        {
+      // transposed projections for the training backward; rows [n_feats, f_pad) of in_w^T and the zero vector are cleared
+      auto* in_wt = c.take<__nv_bfloat16>((size_t)e->f_pad * dm);
+      auto* out_wt = c.take<__nv_bfloat16>((size_t)dm * e->f_pad);
+      auto* zeros = c.take<float>(e->f_pad);
+      MST_CUDA_OK(cudaMemsetAsync(in_wt, 0, (size_t)e->f_pad * dm * sizeof(__nv_bfloat16), s));
+      MST_CUDA_OK(cudaMemsetAsync(zeros, 0, (size_t)e->f_pad * sizeof(float), s));
+      if (js.n + 2 > CVT_MAX_JOBS) {
         if ((rc = cvt_multi(js, s, "pack_weights"))) return rc;
+        js = CvtJobs();
+      }
+      cvt_jobs_add(js, w->in_w, dm, d.n_feats, d.n_feats, nullptr, nullptr, 0, 0, in_wt, dm, nullptr);     // [F, d]
+      cvt_jobs_add(js, w->out_w, d.n_feats, dm, dm, nullptr, nullptr, 0, 0, out_wt, e->f_pad, nullptr);    // [d, Fpad]
+      e->in_wt_bf = in_wt; e->out_wt_bf = out_wt; e->zero_pad = zeros;
+    }
+    if ((rc = cvt_multi(js, s, "pack_weights"))) return rc;
         js = CvtJobs();
       }
       cvt_jobs_add(js, L.qkv_w, 3 * dm, dm, dm, bf(e->lb[l].qkv_w), hf(e->lh[l].qkv_w), 3 * dm, dm, bf(e->lbt[l].qkv_w), 3 * dm, nullptr);

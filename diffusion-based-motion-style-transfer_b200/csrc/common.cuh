@@ -112,6 +112,9 @@ struct Engine {
   // bf16 packed copies (MST_PREC_BF16)
   const __nv_bfloat16* in_w_bf = nullptr;   // [d, Fpad]
   const __nv_bfloat16* out_w_bf = nullptr;  // [Fpad, d]
+  const __nv_bfloat16* in_wt_bf = nullptr;   // [Fpad, d]  in_w^T  (training backward of the in-projection on tensor cores)
+  const __nv_bfloat16* out_wt_bf = nullptr;  // [d, Fpad]  out_w^T (... of the out-projection)
+  const float* zero_pad = nullptr;           // [Fpad] zeros (bias-free out-projection-style epilogue)
   const float* out_b_pad = nullptr;         // [Fpad]
   LayerBF16 lb[MST_MAX_LAYERS];
   LayerBF16T lbt[MST_MAX_LAYERS];

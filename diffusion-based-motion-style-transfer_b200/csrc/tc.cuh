@@ -39,6 +39,8 @@ struct TcGemmParams {
   // TRAIN_F32 as the in-projection of the taped forward: GEMM row (b, t), t < tok_T, lands in output row
   // b * (tok_T + tok_off) + t + tok_off (+ pe[t + tok_off] when pe is given); tok_T == 0: rows map one to one
   int tok_T = 0, tok_off = 0;
+  // OUTPROJ_F32: leading token rows of every sequence that carry no output (0 = the default, one)
+  int drop_tokens = 0;
   // TRAIN_F32, linear1 of the taped forward: besides out = u, also h = dropout(gelu(u)) as fp32 (tape) and bf16 (operand
   // of linear2) - the separate GELU launch of every layer goes away.  Rows are grouped rows_per_seq per sequence.
   float* gelu_out = nullptr;

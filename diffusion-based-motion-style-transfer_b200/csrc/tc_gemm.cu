@@ -222,12 +222,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcGemmParams& p, int row, i
                                        pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
     }
   } else if constexpr (EPI == TC_EPI_OUTPROJ_F32) {
-    const int S = p.T + 1;
+    const int tok = p.drop_tokens > 0 ? p.drop_tokens : 1;
+    const int S = p.T + tok;
     const int seq = row / S, s = row - seq * S;
-    if (s == 0) return;
+    if (s < tok) return;
     float* base = (seq < p.B) ? static_cast<float*>(p.out) : p.out2;
     const int sb = (seq < p.B) ? seq : seq - p.B;
-    float* dst = base + ((size_t)sb * p.n_valid + n) * p.T + (s - 1);
+    float* dst = base + ((size_t)sb * p.n_valid + n) * p.T + (s - tok);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (n + j < p.n_valid) dst[(size_t)j * p.T] = x[j];

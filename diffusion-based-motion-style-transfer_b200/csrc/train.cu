@@ -1186,6 +1186,28 @@ static int inproj_tc(Engine* e, const float* x, int B, int T, int tok_off, const
   return tc_gemm(p, s);
 }
 
+// g[(b, s)] = s < tok_off ? (untouched) : sum_f d_out[b][f][s - tok_off] out_w[f][:]  - backward of the out-projection
+static int outproj_bwd_tc(Engine* e, const float* d_out, int B, int T, float* g, __nv_bfloat16* scratch_bf, cudaStream_t s) {
+  const mst_model_desc& d = e->desc;
+  int rc;
+  if ((rc = motion_to_tokens_bf16(d_out, scratch_bf, B, d.n_feats, T, e->f_pad, nullptr, 0, s))) return rc;
+  TcGemmParams p;
+  p.a = scratch_bf; p.w = e->out_wt_bf; p.out = g; p.ldo = d.d_model;
+  p.M = B * T; p.N = d.d_model; p.K = e->f_pad; p.epi = TC_EPI_TRAIN_F32;
+  p.tok_T = T; p.tok_off = 1;
+  return tc_gemm(p, s);
+}
+
+// d_x[b][f][t] = sum_n gx[(b, t + tok_off)][n] in_w[n][f]  - backward of the in-projection; gx_bf: bf16 copy of gx [M, d]
+static int inproj_bwd_tc(Engine* e, const __nv_bfloat16* gx_bf, int B, int T, int tok_off, float* d_x, cudaStream_t s) {
+  const mst_model_desc& d = e->desc;
+  TcGemmParams p;
+  p.a = gx_bf; p.w = e->in_wt_bf; p.bias = e->zero_pad; p.out = d_x;
+  p.M = B * (T + tok_off); p.N = e->f_pad; p.K = d.d_model; p.epi = TC_EPI_OUTPROJ_F32;
+  p.B = B; p.T = T; p.n_valid = d.n_feats; p.drop_tokens = tok_off;
+  return tc_gemm(p, s);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // tape: everything the backward needs, per layer
 // ---------------------------------------------------------------------------------------------------------
@@ -1810,10 +1832,16 @@ extern "C" int mst_denoiser_backward(mst_engine_t h, const mst_backward_args* ap
     // OutputProcess backward: g[(b,s)][k] = s == 0 ? 0 : sum_f d_out[b][f][s-1] out_w[f][k]   (the tape's x_out slot is
     // dead after the forward: reuse it)
     float* g = tp.x_out;
-    GemmEx go;
-    go.a = a.d_out; go.a_mode = AX_MOTION_TOK; go.T = T; go.tok_off = 1; go.b = e->out_w; go.ldb = dm; go.c = g; go.ldc = dm;
-    go.M = M; go.N = dm; go.K = d.n_feats;
-    if ((rc = gemm_ex(go, s, "bwd_outproj"))) return rc;
+    if (proj_on_tc(e, B, T) && e->out_wt_bf) {
+      // token 0 of every sequence gets no gradient from the output projection
+      MST_CUDA_OK(cudaMemset2DAsync(g, (size_t)S * dm * 4, 0, (size_t)dm * 4, B, s));
+      if ((rc = outproj_bwd_tc(e, a.d_out, B, T, g, w.stage.at, s))) return rc;
+    } else {
+      GemmEx go;
+      go.a = a.d_out; go.a_mode = AX_MOTION_TOK; go.T = T; go.tok_off = 1; go.b = e->out_w; go.ldb = dm; go.c = g; go.ldc = dm;
+      go.M = M; go.N = dm; go.K = d.n_feats;
+      if ((rc = gemm_ex(go, s, "bwd_outproj"))) return rc;
+    }
     float* gx = nullptr;
     if ((rc = encoder_backward(e, tp, a.layer_grads, B, S, g, w, &gx, drop, s))) return rc;
     if (a.d_x) {  // InputProcess backward: d_x[b][f][t] = sum_n gx[(b,t+1)][n] in_w[n][f]
@@ -1911,6 +1939,12 @@ extern "C" int mst_motion_encoder_backward(mst_engine_t h, const float* d_mu, in
     float* gx = nullptr;
     if ((rc = encoder_backward(e, tp, kNoGrads, B, S, g, w, &gx, drop, s))) return rc;
     if (drop.on() && (rc = dropout(gx, nullptr, gx, (long long)B * S * dm, drop, 0, s))) return rc;
+    if (proj_on_tc(e, B, T) && e->in_wt_bf) {
+      CvtJobs js;  // bf16 operand of the tensor-core product
+      cvt_jobs_add(js, gx, B * S, dm, dm, w.stage.a, nullptr, B * S, dm, nullptr, 0, nullptr);
+      if ((rc = cvt_multi(js, s, "bwd_operands"))) return rc;
+      return inproj_bwd_tc(e, w.stage.a, B, T, 2, d_x, s);
+    }
     GemmEx gi;
     gi.a = gx; gi.lda = dm; gi.a_mode = AX_TOKROWS; gi.T = T; gi.tok_off = 2; gi.b = e->in_w; gi.ldb = d.n_feats;
     gi.c = d_x; gi.c_mode = CX_MOTION; gi.M = B * T; gi.N = d.n_feats; gi.K = dm;
