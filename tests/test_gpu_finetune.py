@@ -137,6 +137,29 @@ def test_motion_encoder_matches_reference_golden(style, gold, FI):
     assert relerr(x.grad, gold["menc/dx"]) < TOL
 
 
+def test_motion_encoder_tensor_core_projections_close_to_fp32(mu, FI, tmp_path_factory):
+    """B * T >= 512 routes the MotionEncoder's in-projection (forward) and its backward through the tcgen05 training GEMM in
+    the 16-bit mode (csrc/train.cu::inproj_tc / inproj_bwd_tc); mu and d mu / d x stay within the 16-bit tolerance of the fp32
+    mode, ragged lengths included."""
+    B, T = 8, 76
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(B, 181, 1, T, generator=g)
+    lengths = torch.randint(T // 2, T + 1, (B,), generator=g)
+    mask = (torch.arange(T)[None, :] < lengths[:, None])[:, None, None, :].to(DEV)
+    wgt = torch.randn(B, 512, generator=g).to(DEV)
+    y = {"mask": mask, "text_feat": text_features(["a"] * B).to(DEV)}
+    out = {}
+    for prec in ("fp32", "bf16"):
+        model, *_ = _style_model(mu, FI, tmp_path_factory, precision=prec)
+        model.motion_enc.mst_train_precision = prec
+        x = x0.clone().to(DEV).requires_grad_(True)
+        mu_, _ = model.motion_enc(x, y)
+        (mu_ * wgt).sum().backward()
+        out[prec] = (mu_.detach().clone(), x.grad.clone())
+    assert relerr(out["bf16"][0], out["fp32"][0]) < 2e-2
+    assert rel_l2(out["bf16"][1], out["fp32"][1]) < 3e-2
+
+
 def test_masked_l2_kernel_forward_backward():
     from mst_b200.diffusion.gaussian_diffusion import GaussianDiffusion  # noqa: F401
     from mst_b200 import engine as K
