@@ -1779,43 +1779,99 @@ int cvt_bf16(const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, _
 // Several conversions in ONE launch (the per-weight / per-operand launches were pure latency on the finetune step: 83
 // launches to re-pack the weights after every optimizer step, 3 per backward linear): every job turns an fp32 matrix into any
 // of a zero-padded bf16 copy, a transposed bf16 copy, a zero-padded fp16 copy, and column sums; one CTA per 32 x 32 tile.
+constexpr int CVT_TILE = 64;  // rows and columns of one CTA's tile
+
 __global__ void __launch_bounds__(256) cvt_multi_kernel(const __grid_constant__ CvtJobs jobs) {
   pdl_launch_dependents();
   pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
-  __shared__ float tile[32][33];
-  __shared__ float red[8][32];
+  // 64 x 64 tile: 16 values per thread in flight (128-bit loads when the rows allow), transposed rows leave as 128-byte runs
+  __shared__ float tile[CVT_TILE][CVT_TILE + 1];
+  __shared__ float red[8][CVT_TILE];
   int k = 0;
   while (k + 1 < jobs.n && (int)blockIdx.x >= jobs.j[k + 1].tile0) ++k;
   const CvtJob& J = jobs.j[k];
   const int t = (int)blockIdx.x - J.tile0;
-  const int r0 = (t / J.tiles_x) * 32, c0 = (t % J.tiles_x) * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int r0 = (t / J.tiles_x) * CVT_TILE, c0 = (t % J.tiles_x) * CVT_TILE;
   const int rows = J.rows, cols = J.cols;
-  float part = 0.0f;
-  for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + tx;
-    const float v = (r < rows && c < cols) ? J.src[(size_t)r * J.ld + c] : 0.0f;
-    tile[i][tx] = v;
-    part += v;
-    if (r < J.rows_pad && c < J.cols_pad) {
-      if (J.dst) J.dst[(size_t)r * J.cols_pad + c] = __float2bfloat16_rn(v);
-      if (J.dst_h) J.dst_h[(size_t)r * J.cols_pad + c] = __float2half_rn(v);
+  const int q = threadIdx.x & 15, rr = threadIdx.x >> 4;  // float4 column of the tile, row phase (16 rows per pass)
+  const bool vec = (J.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(J.src) & 15) == 0;
+  float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + rr + 16 * i, c = c0 + 4 * q;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) {
+      const float* sp = J.src + (size_t)r * J.ld + c;
+      if (vec && c + 3 < cols) {
+        v = __ldg(reinterpret_cast<const float4*>(sp));
+      } else {
+        if (c < cols) v.x = __ldg(sp);
+        if (c + 1 < cols) v.y = __ldg(sp + 1);
+        if (c + 2 < cols) v.z = __ldg(sp + 2);
+        if (c + 3 < cols) v.w = __ldg(sp + 3);
+      }
+    }
+    float* tr = &tile[rr + 16 * i][4 * q];
+    tr[0] = v.x; tr[1] = v.y; tr[2] = v.z; tr[3] = v.w;
+    part[0] += v.x; part[1] += v.y; part[2] += v.z; part[3] += v.w;
+    if (r < J.rows_pad) {
+      const float e[4] = {v.x, v.y, v.z, v.w};
+      if ((J.cols_pad & 3) == 0 && c + 3 < J.cols_pad) {  // whole group inside the padded row: 8-byte stores
+        if (J.dst) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+          *reinterpret_cast<uint2*>(J.dst + (size_t)r * J.cols_pad + c) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+        if (J.dst_h) {
+          const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+          *reinterpret_cast<uint2*>(J.dst_h + (size_t)r * J.cols_pad + c) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c + u < J.cols_pad) {
+            if (J.dst) J.dst[(size_t)r * J.cols_pad + c + u] = __float2bfloat16_rn(e[u]);
+            if (J.dst_h) J.dst_h[(size_t)r * J.cols_pad + c + u] = __float2half_rn(e[u]);
+          }
+      }
     }
   }
-  if (J.colsum) red[ty][tx] = part;
   if (!J.dst_t && !J.colsum) return;
+  if (J.colsum) {  // the 16 row phases of a column group meet through the quarter-warp shuffles, then shared memory
+#pragma unroll
+    for (int u = 0; u < 4; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], 16);
+    if ((threadIdx.x & 16) == 0) {
+      float* rd = &red[0][0] + (threadIdx.x >> 5) * CVT_TILE + 4 * q;  // 8 warps x 64 columns
+      rd[0] = part[0]; rd[1] = part[1]; rd[2] = part[2]; rd[3] = part[3];
+    }
+  }
   __syncthreads();
-  if (J.colsum && ty == 0 && c0 + tx < cols && r0 < rows) {
+  if (J.colsum && threadIdx.x < CVT_TILE && c0 + (int)threadIdx.x < cols && r0 < rows) {
+    const float* rd = &red[0][0];
     float a = 0.0f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) a += red[w][tx];
-    atomicAdd(J.colsum + c0 + tx, a);
+    for (int w = 0; w < 8; ++w) a += rd[w * CVT_TILE + threadIdx.x];
+    atomicAdd(J.colsum + c0 + threadIdx.x, a);
   }
-  if (J.dst_t)
-    for (int i = ty; i < 32; i += 8) {
-      const int c = c0 + i, r = r0 + tx;
-      if (c < cols && r < J.t_ld) J.dst_t[(size_t)c * J.t_ld + r] = __float2bfloat16_rn(tile[tx][i]);
+  if (J.dst_t) {
+    // warp w writes transposed rows c0 + w, c0 + w + 8, ...: lane l the source rows r0 + 2 l, r0 + 2 l + 1 (4 bytes)
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int r = r0 + 2 * l;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int cc = w + 8 * i, c = c0 + cc;
+      if (c >= cols) continue;
+      const float x0 = tile[2 * l][cc], x1 = tile[2 * l + 1][cc];
+      __nv_bfloat16* dp = J.dst_t + (size_t)c * J.t_ld + r;
+      if ((J.t_ld & 1) == 0 && r + 1 < J.t_ld) {
+        *reinterpret_cast<__nv_bfloat162*>(dp) = __floats2bfloat162_rn(x0, x1);
+      } else {
+        if (r < J.t_ld) dp[0] = __float2bfloat16_rn(x0);
+        if (r + 1 < J.t_ld) dp[1] = __float2bfloat16_rn(x1);
+      }
     }
+  }
 }
 
 void cvt_jobs_add(CvtJobs& js, const float* src, int rows, int cols, int ld, __nv_bfloat16* dst, __half* dst_h, int rows_pad,
@@ -1829,9 +1885,9 @@ void cvt_jobs_add(CvtJobs& js, const float* src, int rows, int cols, int ld, __n
   int r_ext = J.rows_pad > J.t_ld ? J.rows_pad : J.t_ld, c_ext = J.cols_pad > cols ? J.cols_pad : cols;
   if (colsum && r_ext < rows) r_ext = rows;
   if (!dst_t && !colsum) c_ext = J.cols_pad;
-  J.tiles_x = ceil_div(c_ext, 32);
+  J.tiles_x = ceil_div(c_ext, CVT_TILE);
   J.tile0 = js.n ? js.j[js.n - 1].tile0 + js.tiles_of_last : 0;
-  js.tiles_of_last = J.tiles_x * ceil_div(r_ext, 32);
+  js.tiles_of_last = J.tiles_x * ceil_div(r_ext, CVT_TILE);
   ++js.n;
 }
 
