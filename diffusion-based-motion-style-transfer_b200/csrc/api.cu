@@ -342,7 +342,15 @@ extern "C" int mst_engine_load_weights(mst_engine_t h, const mst_weights* w, voi
     for (int l = 0; l < d.n_layers; ++l) {
       const mst_layer_weights& L = w->layers[l];
       if (js.n + 4 > CVT_MAX_JOBS) {
-        {
+        if ((rc = cvt_multi(js, s, "pack_weights"))) return rc;
+        js = CvtJobs();
+      }
+      cvt_jobs_add(js, L.qkv_w, 3 * dm, dm, dm, bf(e->lb[l].qkv_w), hf(e->lh[l].qkv_w), 3 * dm, dm, bf(e->lbt[l].qkv_w), 3 * dm, nullptr);
+      cvt_jobs_add(js, L.o_w, dm, dm, dm, bf(e->lb[l].o_w), nullptr, dm, dm, bf(e->lbt[l].o_w), dm, nullptr);
+      cvt_jobs_add(js, L.w1, ff, dm, dm, bf(e->lb[l].w1), hf(e->lh[l].w1), ff, dm, bf(e->lbt[l].w1), ff, nullptr);
+      cvt_jobs_add(js, L.w2, dm, ff, ff, bf(e->lb[l].w2), nullptr, dm, ff, bf(e->lbt[l].w2), dm, nullptr);
+    }
+    {
       // transposed projections for the training backward; rows [n_feats, f_pad) of in_w^T and the zero vector are cleared
       auto* in_wt = c.take<__nv_bfloat16>((size_t)e->f_pad * dm);
       auto* out_wt = c.take<__nv_bfloat16>((size_t)dm * e->f_pad);
@@ -356,14 +364,6 @@ extern "C" int mst_engine_load_weights(mst_engine_t h, const mst_weights* w, voi
       cvt_jobs_add(js, w->in_w, dm, d.n_feats, d.n_feats, nullptr, nullptr, 0, 0, in_wt, dm, nullptr);     // [F, d]
       cvt_jobs_add(js, w->out_w, d.n_feats, dm, dm, nullptr, nullptr, 0, 0, out_wt, e->f_pad, nullptr);    // [d, Fpad]
       e->in_wt_bf = in_wt; e->out_wt_bf = out_wt; e->zero_pad = zeros;
-    }
-    if ((rc = cvt_multi(js, s, "pack_weights"))) return rc;
-        js = CvtJobs();
-      }
-      cvt_jobs_add(js, L.qkv_w, 3 * dm, dm, dm, bf(e->lb[l].qkv_w), hf(e->lh[l].qkv_w), 3 * dm, dm, bf(e->lbt[l].qkv_w), 3 * dm, nullptr);
-      cvt_jobs_add(js, L.o_w, dm, dm, dm, bf(e->lb[l].o_w), nullptr, dm, dm, bf(e->lbt[l].o_w), dm, nullptr);
-      cvt_jobs_add(js, L.w1, ff, dm, dm, bf(e->lb[l].w1), hf(e->lh[l].w1), ff, dm, bf(e->lbt[l].w1), ff, nullptr);
-      cvt_jobs_add(js, L.w2, dm, ff, ff, bf(e->lb[l].w2), nullptr, dm, ff, bf(e->lbt[l].w2), dm, nullptr);
     }
     if ((rc = cvt_multi(js, s, "pack_weights"))) return rc;
     {
