@@ -160,10 +160,10 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 
 // C(m, n) = sum_k a[m*lda + k] * b[n*ldb + k] for m < 16 MT, n < 80 (operands zero padded); K % 8 == 0.
 // Work unit = one 16-row tile x two 8-column tiles; the 5 MT units go round the 8 warps.
-template <int MT, typename Out>
+template <int MT, int NW = 8, typename Out>
 __device__ __forceinline__ void mma_gemm_nt80(const float* a, int lda, const float* b, int ldb, int K, Out out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  for (int u = warp; u < MT * 5; u += 8) {
+  for (int u = warp; u < MT * 5; u += NW) {
     const int mt = u / 5, n0 = (u - mt * 5) * 16;
     float c[2][4];
 #pragma unroll
@@ -189,23 +189,24 @@ __device__ __forceinline__ void mma_gemm_nt80(const float* a, int lda, const flo
 }
 
 // C(m, n) = sum_k A(m, k) * b[k*ldb + n] for 128 columns, m < 16 MT; A(m, k) = TA ? a[k*lda + m] : a[m*lda + k]; K % 8 == 0.
-// Warp w owns columns [16 w, 16 w + 16) of all row tiles.
-template <bool TA, int MT, typename Out>
+// Warp w of NW (8 or 16) owns the 128 / NW columns from (128 / NW) w on, of all row tiles.
+template <bool TA, int MT, int NW = 8, typename Out>
 __device__ __forceinline__ void mma_gemm_n128(const float* a, int lda, const float* b, int ldb, int K, Out out) {
+  constexpr int NTW = 16 / NW;  // 8-column tiles per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  float c[MT][2][4];
+  float c[MT][NTW][4];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < NTW; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) c[i][j][e] = 0.0f;
-  const float* bc = b + 16 * warp + g;
+  const float* bc = b + 8 * NTW * warp + g;
 #pragma unroll 2
   for (int k = 0; k < K; k += 8) {
-    uint32_t bf[2][2];
+    uint32_t bf[NTW][2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < NTW; ++j) {
       bf[j][0] = to_tf32(bc[(k + t) * ldb + 8 * j]);
       bf[j][1] = to_tf32(bc[(k + t + 4) * ldb + 8 * j]);
     }
@@ -225,14 +226,14 @@ __device__ __forceinline__ void mma_gemm_n128(const float* a, int lda, const flo
         af[3] = to_tf32(a[(m + 8) * lda + k + t + 4]);
       }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) mma_tf32(c[i][j], af, bf[j][0], bf[j][1]);
+      for (int j = 0; j < NTW; ++j) mma_tf32(c[i][j], af, bf[j][0], bf[j][1]);
     }
   }
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int m = 16 * i + g, n = 16 * warp + 8 * j + 2 * t;
+    for (int j = 0; j < NTW; ++j) {
+      const int m = 16 * i + g, n = 8 * NTW * warp + 8 * j + 2 * t;
       out(m, n, c[i][j][0], c[i][j][1]);  // columns n, n + 1
       out(m + 8, n, c[i][j][2], c[i][j][3]);
     }

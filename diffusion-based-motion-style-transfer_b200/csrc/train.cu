@@ -868,38 +868,39 @@ constexpr int SA_LDP = SA_MAXS + 4;  // P, dP rows
 // rows [0, S) x 128 columns of N global matrices (leading dimension ld, 16-byte aligned rows) -> smem [SA_MAXS][SA_LDX],
 // rows >= S zero.  256 threads; every thread issues its 10 float4 loads per matrix before the first shared-memory store, so
 // the CTA pays the global latency once instead of once per element (the scalar loop was ~60 % of the kernel).
-template <int N>
+template <int N, int NT = 256>
 __device__ __forceinline__ void sa_load(float* const (&dst)[N], const float* const (&src)[N], int ld, int S) {
-  constexpr int PER = SA_MAXS * (SA_DH / 4) / 256;  // 10
+  constexpr int PER = SA_MAXS * (SA_DH / 4) / NT;  // 10 (256 threads) / 5 (512)
   float4 v[N][PER];
 #pragma unroll
   for (int m = 0; m < N; ++m)
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-      const int idx = threadIdx.x + 256 * i, r = idx >> 5, c4 = idx & 31;
+      const int idx = threadIdx.x + NT * i, r = idx >> 5, c4 = idx & 31;
       v[m][i] = r < S ? __ldg(reinterpret_cast<const float4*>(src[m] + (long long)r * ld) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
   for (int m = 0; m < N; ++m)
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-      const int idx = threadIdx.x + 256 * i, r = idx >> 5, c4 = idx & 31;
+      const int idx = threadIdx.x + NT * i, r = idx >> 5, c4 = idx & 31;
       *reinterpret_cast<float4*>(dst[m] + r * SA_LDX + 4 * c4) = v[m][i];
     }
 }
 // [S][S] global -> smem [SA_MAXS][SA_LDP], zero padded (25 independent loads per thread)
+template <int NT = 256>
 __device__ __forceinline__ void sa_load_p(float* dst, const float* __restrict__ src, int S) {
-  constexpr int PER = SA_MAXS * SA_MAXS / 256;  // 25
+  constexpr int PER = (SA_MAXS * SA_MAXS + NT - 1) / NT;  // 25 (256 threads) / 13 (512)
   float v[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    const int idx = threadIdx.x + 256 * i, r = idx / SA_MAXS, c = idx - r * SA_MAXS;
+    const int idx = threadIdx.x + NT * i, r = idx / SA_MAXS, c = idx - r * SA_MAXS;
     v[i] = (r < S && c < S) ? __ldg(src + r * S + c) : 0.0f;
   }
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    const int idx = threadIdx.x + 256 * i, r = idx / SA_MAXS, c = idx - r * SA_MAXS;
-    dst[r * SA_LDP + c] = v[i];
+    const int idx = threadIdx.x + NT * i, r = idx / SA_MAXS, c = idx - r * SA_MAXS;
+    if (idx < SA_MAXS * SA_MAXS) dst[r * SA_LDP + c] = v[i];
   }
 }
 
@@ -1036,13 +1037,16 @@ __global__ void __launch_bounds__(256, 2) attn_small_fwd_kernel(const float* __r
 }
 
 // grid (heads, n_seqs).  dao [n_seqs*S, d] -> dqkv [n_seqs*S, 3d] (Q | K | V column blocks)
+// The tensor-core variant runs 16 warps (the kernel is a chain of latency-bound phases on ONE CTA per SM: twice the warps
+// hide twice the latency); the fp32 variant keeps the 16 x 16 thread grid its register-tiled products are written for.
 template <bool MMA>
-__global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ p_in,
+__global__ void __launch_bounds__(MMA ? 512 : 256) attn_small_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ p_in,
                                                              const float* __restrict__ pd_in, const float* __restrict__ dao,
                                                              float* __restrict__ dqkv, __nv_bfloat16* __restrict__ dqkv_bf, int S,
                                                              int d_model, int H, float scale, Drop drop, uint32_t site) {
   pdl_launch_dependents();
   pdl_wait();  // inputs come from the previous kernel of the stream (programmatic dependent launch)
+  constexpr int NT = MMA ? 512 : 256, NW = NT / 32;
   extern __shared__ float sm[];
   float* Qs = sm;
   float* Ks = Qs + SA_MAXS * SA_LDX;
@@ -1058,12 +1062,12 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   {
     float* const dst[3] = {Qs, Ks, Vs};
     const float* const src[3] = {base, base + d_model, base + 2 * d_model};
-    sa_load<3>(dst, src, 3 * d_model, S);
+    sa_load<3, NT>(dst, src, 3 * d_model, S);
     float* const dst_o[1] = {Os};
     const float* const src_o[1] = {dao + (long long)seq * S * d_model + head * SA_DH};
-    sa_load<1>(dst_o, src_o, d_model, S);
+    sa_load<1, NT>(dst_o, src_o, d_model, S);
   }
-  sa_load_p(Ps, (drop.on() ? pd_in : p_in) + pp, S);
+  sa_load_p<NT>(Ps, (drop.on() ? pd_in : p_in) + pp, S);
   __syncthreads();
   // dV = Pd^T dO
   // results of the 128-column products: column block `blk` (0 Q, 1 K, 2 V) of dqkv, scaled
@@ -1084,23 +1088,23 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
       }
     };
   };
-  if constexpr (MMA) mma_gemm_n128<true, 5>(Ps, SA_LDP, Os, SA_LDX, SA_MAXS, store2(2, 1.0f));
+  if constexpr (MMA) mma_gemm_n128<true, 5, NW>(Ps, SA_LDP, Os, SA_LDX, SA_MAXS, store2(2, 1.0f));
   else smem_gemm_n128<true, 5>(Ps, SA_LDP, Os, SA_LDX, SA_MAXS, store1(2, 1.0f));
   // dP = dO V^T (the forward's dropout mask is applied row by row below)
   if constexpr (MMA)
-    mma_gemm_nt80<5>(Os, SA_LDX, Vs, SA_LDX, SA_DH, [&](int i, int j, float v0, float v1) {
+    mma_gemm_nt80<5, NW>(Os, SA_LDX, Vs, SA_LDX, SA_DH, [&](int i, int j, float v0, float v1) {
       *reinterpret_cast<float2*>(Ds + i * SA_LDP + j) = make_float2(v0, v1);
     });
   else
     smem_gemm_nt2<5, 5>(Os, SA_LDX, Vs, SA_LDX, SA_DH, [&](int i, int j, float v) { Ds[i * SA_LDP + j] = v; });
   __syncthreads();
   if (drop.on()) {  // the softmax backward needs the probabilities BEFORE dropout
-    sa_load_p(Ps, p_in + pp, S);
+    sa_load_p<NT>(Ps, p_in + pp, S);
     __syncthreads();
   }
   // dS = P * (dP - sum_j P dP)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp; i < SA_MAXS; i += 8) {
+  for (int i = warp; i < SA_MAXS; i += NW) {
     const float* pr = Ps + i * SA_LDP;
     float* dr = Ds + i * SA_LDP;
     if (drop.on() && i < S) {  // dP *= mask: one Philox call per group of 4 consecutive elements (see the forward)
@@ -1125,8 +1129,8 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const float* __rest
   __syncthreads();
   // dQ = scale dS K ;  dK = scale dS^T Q
   if constexpr (MMA) {
-    mma_gemm_n128<false, 5>(Ds, SA_LDP, Ks, SA_LDX, SA_MAXS, store2(0, scale));
-    mma_gemm_n128<true, 5>(Ds, SA_LDP, Qs, SA_LDX, SA_MAXS, store2(1, scale));
+    mma_gemm_n128<false, 5, NW>(Ds, SA_LDP, Ks, SA_LDX, SA_MAXS, store2(0, scale));
+    mma_gemm_n128<true, 5, NW>(Ds, SA_LDP, Qs, SA_LDX, SA_MAXS, store2(1, scale));
   } else {
     smem_gemm_n128<false, 5>(Ds, SA_LDP, Ks, SA_LDX, SA_MAXS, store1(0, scale));
     smem_gemm_n128<true, 5>(Ds, SA_LDP, Qs, SA_LDX, SA_MAXS, store1(1, scale));
@@ -1470,7 +1474,7 @@ static int encoder_backward(Engine* e, const Tape& tp, const mst_layer_grads* gr
         MST_CUDA_OK(cudaFuncSetAttribute(attn_small_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_BWD_SMEM));
         MST_CUDA_OK(cudaFuncSetAttribute(attn_small_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_BWD_SMEM));
       }
-      MST_CUDA_OK(launch_pdl(attn_mma(tc) ? attn_small_bwd_kernel<true> : attn_small_bwd_kernel<false>, dim3(H, NS), dim3(256), SA_BWD_SMEM, s, (const float*)t.qkv, (const float*)t.p,
+      MST_CUDA_OK(launch_pdl(attn_mma(tc) ? attn_small_bwd_kernel<true> : attn_small_bwd_kernel<false>, dim3(H, NS), dim3(attn_mma(tc) ? 512 : 256), SA_BWD_SMEM, s, (const float*)t.qkv, (const float*)t.p,
                              (const float*)t.pd, (const float*)dao, w.dqkv, bf, S, dm, H, scale, drop, drop_site(l, 1)));
       MST_LAUNCHED("bwd_attn_small", s);
       dqkv_staged = bf != nullptr;
