@@ -701,6 +701,8 @@ __device__ __forceinline__ uint32_t f32x2_to_h2(float lo, float hi) {
   else return pack_bf16x2(lo, hi);
 }
 
+constexpr int LN_LEAD = 2;  // k-blocks of the next tile that enter the ring before a tile's residual (see the producer)
+
 struct LnCfg {
   static constexpr int BN = 256;
   static constexpr int STAGES = 5;  // ring slots shared by the k-blocks AND the two residual blocks of every tile
@@ -814,16 +816,15 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         mbar_wait(ring.empty(stage), phase ^ 1);
       };
-      for (int mp = cluster_id; mp < m_pairs; mp += n_clusters) {
-        const int m_blk = 2 * mp + (int)mrank;
-        for (int kb = 0; kb < k_blks; ++kb) {
-          acquire();
-          const uint32_t full_leader = map_to_cta(ring.full(stage), leader_rank);
-          if (leader) mbar_expect_tx(ring.full(stage), 2 * Cfg::STAGE_BYTES);
-          tma_load_2d_2cta(ring.a(stage), &tmap_a, full_leader, kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d_2cta(ring.b(stage), &tmap_w, full_leader, kb * BLOCK_K, (int)pair * BN + (int)mrank * (BN / 2));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-        }
+      auto load_kb = [&](int m_blk, int kb) {
+        acquire();
+        const uint32_t full_leader = map_to_cta(ring.full(stage), leader_rank);
+        if (leader) mbar_expect_tx(ring.full(stage), 2 * Cfg::STAGE_BYTES);
+        tma_load_2d_2cta(ring.a(stage), &tmap_a, full_leader, kb * BLOCK_K, m_blk * BLOCK_M);
+        tma_load_2d_2cta(ring.b(stage), &tmap_w, full_leader, kb * BLOCK_K, (int)pair * BN + (int)mrank * (BN / 2));
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      };
+      auto load_res = [&](int m_blk) {
         for (int h = 0; h < 2; ++h) {  // residual columns [256*pair + 128*h, +128) of this CTA's 128 rows
           acquire();
           mbar_expect_tx(res_full(h), Cfg::STAGE_BYTES);
@@ -833,12 +834,31 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         ++res_loads;
+      };
+      // Ring order: the residual of tile i goes in BEHIND the first LN_LEAD k-blocks of tile i+1 (directly behind its own
+      // k-blocks for the last tile).  Loaded right behind tile i's last k-block it parks two of the five slots from ~3
+      // k-blocks before the MMAs of tile i end until pass 1 of its epilogue is done, and the MMAs of tile i+1 start on a
+      // three-slot ring with nothing prefetched: a 1.3 k cycle wait at k-block 0 and 1.7 k at k-block 3 of every tile
+      // (profiles/r02o_ln_v4_probe_no_smem_epilogue.txt).  With the lead the wait at k-block 0 is gone and a shorter one
+      // appears at k-block 2 (the two slots are still parked): 19.0 -> 18.7 us (K = 512), 28.6 -> 27.9 us (K = 1024); leads
+      // of 1..5 all measure the same (profiles/r02o_ln_v4_residual_lead.txt).  MST_TEARDOWN=8 restores the old order.
+      const int lead = (p.td_mode == 8 || k_blks <= LN_LEAD) ? 0 : LN_LEAD;
+      int prev_blk = -1;
+      for (int mp = cluster_id; mp < m_pairs; mp += n_clusters) {
+        const int m_blk = 2 * mp + (int)mrank;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          if (kb == lead && prev_blk >= 0) load_res(prev_blk);
+          load_kb(m_blk, kb);
+        }
+        prev_blk = m_blk;
       }
+      if (prev_blk >= 0) load_res(prev_blk);
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN, 0);
       const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
+      const int lead = (p.td_mode == 8 || k_blks <= LN_LEAD) ? 0 : LN_LEAD;
       int stage = 0, acc = 0;
       uint32_t full_phase = 0, acc_phase = 0;  // bit s of full_phase: parity the next k-block in slot s completes
       long long* dbg = (p.dbg && cluster_id == 0 && rank == 0) ? p.dbg + (1 * 2 + 0) * 1024 : nullptr;
@@ -850,6 +870,9 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         MST_DBG_STAMP();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < k_blks; ++kb) {
+          if (kb == lead && mp != cluster_id)
+            for (int h = 0; h < 2; ++h)  // the two residual slots of the previous tile: nothing to multiply
+              if (++stage == Cfg::STAGES) stage = 0;
           mbar_wait_cluster(ring.full(stage), (full_phase >> stage) & 1u);
           full_phase ^= 1u << stage;
           tc_fence_after();
@@ -863,8 +886,6 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mma_commit_2cta(ring.empty(stage), pair_mask);
           if (++stage == Cfg::STAGES) stage = 0;
         }
-        for (int h = 0; h < 2; ++h)  // the two residual slots of the tile: nothing to multiply
-          if (++stage == Cfg::STAGES) stage = 0;
         mma_commit_2cta(ring.tfull(acc), pair_mask);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -897,7 +918,11 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(res_full(half), par);
       MST_DBG_STAMP();
       // ring slot that holds this half's residual: the tile's k-blocks come first, then residual half 0, half 1
-      const uint32_t res_smem = ring.a((it * (k_blks + 2) + k_blks + half) % Cfg::STAGES);
+      // ring entries before this tile's residual: the k-blocks of tiles 0..it, the residuals of tiles 0..it-1 and - unless
+      // this is the cluster's last tile - the first `lead` k-blocks of tile it+1
+      const bool last_tile = mp + n_clusters >= m_pairs;
+      const int lead = (p.td_mode == 8 || k_blks <= LN_LEAD) ? 0 : LN_LEAD;
+      const uint32_t res_smem = ring.a(((it + 1) * k_blks + 2 * it + (last_tile ? 0 : lead) + half) % Cfg::STAGES);
       const uint32_t tempty_leader = map_to_cta(ring.tempty(acc), leader_rank);
       // pass 1: x = acc + bias + residual (kept in registers as packed fp32 pairs), row sum and sum of squares on
       // four independent packed accumulators (fma.rn.f32x2: two elements per instruction)
