@@ -912,17 +912,26 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int m_blk = 2 * mp + (int)mrank;
       const uint32_t par = it & 1;
       MST_DBG_STAMP();
-      mbar_wait(ring.tfull(acc), acc_phase);
-      tc_fence_after();
-      MST_DBG_STAMP();
-      mbar_wait(res_full(half), par);
-      MST_DBG_STAMP();
+
       // ring slot that holds this half's residual: the tile's k-blocks come first, then residual half 0, half 1
       // ring entries before this tile's residual: the k-blocks of tiles 0..it, the residuals of tiles 0..it-1 and - unless
       // this is the cluster's last tile - the first `lead` k-blocks of tile it+1
       const bool last_tile = mp + n_clusters >= m_pairs;
       const int lead = (p.td_mode == 8 || k_blks <= LN_LEAD) ? 0 : LN_LEAD;
       const uint32_t res_smem = ring.a(((it + 1) * k_blks + 2 * it + (last_tile ? 0 : lead) + half) % Cfg::STAGES);
+      // The residual goes to registers BEFORE the accumulator is awaited (the epilogue warps are idle here while the MMAs of
+      // the tile finish, and the 64 registers are free until pass 1 builds x): its two ring slots go back to the producer
+      // ~2 k cycles earlier than when pass 1 read them from shared memory.
+      mbar_wait(res_full(half), par);
+      uint4 rres[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c)  // 16-byte piece c of this thread's 128 residual columns: box c / 8, piece c % 8 of the row
+        rres[c] = lds128(res_smem + (c >> 3) * Cfg::A_BYTES + my_row + (((c & 7) ^ (r & 7)) << 4));
+      mbar_arrive(res_free(half));  // the residual slot may be refilled
+      MST_DBG_STAMP();
+      mbar_wait(ring.tfull(acc), acc_phase);
+      tc_fence_after();
+      MST_DBG_STAMP();
       const uint32_t tempty_leader = map_to_cta(ring.tempty(acc), leader_rank);
       // pass 1: x = acc + bias + residual (kept in registers as packed fp32 pairs), row sum and sum of squares on
       // four independent packed accumulators (fma.rn.f32x2: two elements per instruction)
@@ -933,12 +942,11 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int c4 = 0; c4 < 4; ++c4) {  // 32 accumulator columns at a time
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_addr + (uint32_t)(acc * BN + half * 128 + c4 * 32), v);
-        const uint32_t row_smem = res_smem + (c4 >> 1) * Cfg::A_BYTES + my_row;  // columns 0-63 | 64-127 of the half
         uint4 rr[4], bb[8];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int j = (c4 & 1) * 4 + jj;  // 16-byte piece of the 128-byte staged row
-          rr[jj] = lds128(row_smem + ((j ^ (r & 7)) << 4));
+          rr[jj] = rres[(c4 >> 1) * 8 + j];
           bb[2 * jj] = lds128(bias_smem + (uint32_t)(c4 * 32 + jj * 8) * 4);
           bb[2 * jj + 1] = lds128(bias_smem + (uint32_t)(c4 * 32 + jj * 8 + 4) * 4);
         }
@@ -961,7 +969,6 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           s2b = add2(s2b, xo[3]); q2b = fma2(xo[3], xo[3], q2b);
         }
       }
-      mbar_arrive(res_free(half));  // the residual slot may be refilled
       float sum, sq;
       {
         float a0, a1, b0, b1;

@@ -112,7 +112,7 @@ for i in range(0, len(mma), per):
     print(f"  tile {i // per}: start {row[0]:7d} tempty+{row[1] - row[0]:5d} kblocks " + " ".join(f"{b - a_:4d}" for a_, b in zip(row[1:], row[2:])),
           f"| tile total {row[-1] - row[0]:6d}")
 if epi == 2:
-    print("LN epilogue (warp 2 lane 0) per tile: top | tfull wait | res wait | pass1 | stats exchange | pass2+fence | store+drain+next residual issue")
+    print("LN epilogue (warp 2 lane 0) per tile: top | residual wait + read | tfull wait | pass1 | stats exchange | pass2+fence | store+drain+next residual issue")
     for r in range(2):
         e = epi_t[r]
         for i in range(0, len(e), 7):
