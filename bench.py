@@ -565,13 +565,13 @@ def roofline_leg(K, model, dev, B, T, pk, ms_denoise_in_graph, steady=True):
     if roof is not None:
         # the secondary bound that explains the tensor fraction: every tile design here stages 128 A rows + 128 W rows
         # per CTA and k-block = 64 B/clk/SM of shared-memory fill at the full MMA rate, read back by the tensor core at
-        # another 64 B/clk/SM: the whole 128 B/clk shared-memory port (tools/ubench/tma_fill.cu: the fill alone tops out
-        # at 60.5 B/clk/SM from L2)
+        # another 64 B/clk/SM (tools/ubench/tma_fill.cu: the fill alone tops out at 60.5 B/clk/SM from L2)
         roof["fabric_note"] = ("ncu (profiles/r02h_*): crossbar->L1 at 28 %, LTS->crossbar at 36 % of their peaks in the QKV GEMM - "
                                "the L2 fabric is not the bound (round 1's '0.66 L2 cap' is withdrawn); measured bulk-copy fill "
                                "rate 60.5 B/clk/SM from L2 (profiles/r02p_ubench_tma_fill_rate.txt) against 64 needed at the "
-                               "full MMA rate, plus 64 B/clk/SM of operand reads: the shared-memory port is the bound, epilogue "
-                               "traffic comes out of the MMAs' share; see DESIGN.md section 4")
+                               "full MMA rate, plus 64 B/clk/SM of operand reads: epilogue shared-memory traffic comes out of the "
+                               "MMAs' share (LN GEMMs: probes in DESIGN.md section 4); an A-stationary QKV variant with half "
+                               "the fill traffic measured no faster, so QKV at 0.70 is not fill-bound")
     upd = [s for s in stages if s["kernel"] == "update"]
     if upd and roof is not None:
         by = 20 * B * F_FEATS * T  # out_c, out_u, x_t, x_inp read + x_{t-1} write, [F] mask, in-kernel Philox
