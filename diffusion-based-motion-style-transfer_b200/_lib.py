@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libmst_b200.so")
 SOURCES = ["api.cu", "update.cu", "simt.cu", "tc_gemm.cu", "tc_attn.cu", "train.cu", "text.cu"]
-HEADERS = ["common.cuh", "simt.cuh", "tc.cuh", "tc_ptx.cuh", "smem_gemm.cuh", os.path.join("..", "..", "include", "mst.h")]
+HEADERS = ["common.cuh", "simt.cuh", "tc.cuh", "tc_ptx.cuh", "smem_gemm.cuh", "dropout.cuh", os.path.join("..", "..", "include", "mst.h")]
 
 MAX_LAYERS = 32
 PREC_FP32, PREC_BF16 = 0, 1
